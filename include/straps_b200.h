@@ -1,0 +1,135 @@
+/*
+ * straps_b200.h -- C ABI of libstraps_b200.so (hand-written sm_100a CUDA for the STRAPS hot path).
+ *
+ * The reference (akashsengupta1997/STRAPS-3DHumanShapePose) has NO FFI / plugin layer: its boundary
+ * is the Python module surface.  Each entry point below replaces the torch-op
+ * cluster behind one reference interface, cited as file:line of the reference tree.  The Python
+ * drop-in modules under straps-3dhumanshapepose_b200/{models,utils,losses}/ bind these with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers + explicit sizes; no torch / C++ types cross the ABI.
+ *   - "dev" pointers are CUDA device pointers on the current device, "host" pointers are CPU memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Nothing synchronises
+ *     except the *_create functions (they upload constants) and straps_*_destroy.
+ *   - every function returns 0 on success, non-zero on failure; straps_last_error() then returns a
+ *     thread-local message.  No exceptions cross the ABI.
+ *   - tensors are fp32, C-contiguous unless a stride (in elements) is passed.
+ */
+#ifndef STRAPS_B200_H_
+#define STRAPS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* the library is built with -fvisibility=hidden; only the entry points below are exported */
+#pragma GCC visibility push(default)
+
+#define STRAPS_NUM_VERTS 6890
+#define STRAPS_NUM_JOINTS 24
+#define STRAPS_NUM_BETAS 10
+#define STRAPS_NUM_EXTRA_PICKS 21   /* smplx VertexJointSelector picks */
+#define STRAPS_NUM_EXTRA_ROWS 45    /* J_regressor_extra 9 + cocoplus 19 + h36m 17 (models/smpl_official.py:17-25) */
+#define STRAPS_NUM_SUPERSET_JOINTS 90
+#define STRAPS_IEF_PARAMS 157       /* 3 cam + 24*6 pose + 10 shape (models/regressor.py:25-26) */
+#define STRAPS_FEAT_DIM 512
+
+const char* straps_last_error(void);
+int straps_abi_version(void);
+/* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
+unsigned long long straps_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * SMPL body model -- replaces smplx.SMPL.__init__/forward + models/smpl_official.py:15-41.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct straps_smpl straps_smpl_t;
+
+/* Upload + pre-reduce the model constants (all HOST pointers, fp32 row-major):
+ *   v_template [6890,3]; shapedirs [6890,3,10]; posedirs [207,20670] (smplx layout: pose-feature major,
+ *   inner axis ordered (vertex, xyz)); J_regressor [24,6890]; lbs_weights [6890,24]; parents int64[24]
+ *   (parents[0] = -1); extra_regressors [45,6890] = rows of J_regressor_extra, cocoplus, h36m stacked in
+ *   that order; extra_pick_idx int64[21] vertex ids.  Synchronous. */
+int straps_smpl_create(straps_smpl_t** out,
+                       const float* v_template, const float* shapedirs, const float* posedirs,
+                       const float* J_regressor, const float* lbs_weights, const int64_t* parents,
+                       const float* extra_regressors, const int64_t* extra_pick_idx);
+void straps_smpl_destroy(straps_smpl_t* m);
+/* 1 if every vertex has <= 4 non-zero skinning weights (fast path), else 0 (dense path). */
+int straps_smpl_is_sparse4(const straps_smpl_t* m);
+
+/* SMPL forward (smplx lbs() + VertexJointSelector + the three extra regressors):
+ *   pose2rot == 0: global_orient dev [B,1,3,3] (row stride go_stride floats), body_pose dev [B,23,3,3]
+ *                  (row stride bp_stride) -- rotation matrices  (train/...:196-199).
+ *   pose2rot == 1: global_orient dev [B,3], body_pose dev [B,69] axis-angle (models/smpl_official.py:29
+ *                  default path, train/...:144,206).
+ *   betas dev [B,10] (row stride betas_stride); transl dev [B,3] or NULL.
+ * Outputs: vertices dev [B,6890,3]; joints dev [B,90,3] (24 posed + 21 picks + 9 + 19 + 17). */
+int straps_smpl_forward(const straps_smpl_t* m,
+                        const float* global_orient, int64_t go_stride,
+                        const float* body_pose, int64_t bp_stride,
+                        const float* betas, int64_t betas_stride,
+                        const float* transl, int batch, int pose2rot,
+                        float* vertices, float* joints, void* stream);
+
+/* utils/rigid_transform_utils.py:27-41 -- x6 dev [n,6] (interleaved a1/a2) -> R dev [n,3,3]. */
+int straps_rot6d_to_rotmat(const float* x6, int64_t n, float* R, void* stream);
+
+/* utils/cam_utils.py:5-26 -- points dev [B,N,3], cam dev [B,3] (row stride cam_stride) -> out dev [B,N,2]. */
+int straps_orthographic_project(const float* points, const float* cam, int64_t cam_stride,
+                                int batch, int npoints, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Regressor -- replaces models/regressor.py:43-47 = ResNet.forward (models/resnet.py:201-216) +
+ * IEFModule.forward (models/ief_module.py:48-64).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct straps_regressor straps_regressor_t;
+
+/* Conv precision modes for the encoder. */
+#define STRAPS_CONV_FP32_SIMT 0   /* fp32 FMA on CUDA cores (exact-order reference mode)           */
+#define STRAPS_CONV_BF16X3_TC 1   /* tcgen05 tensor cores, 2-term bf16 split, 3 MMA passes, fp32 acc */
+
+/* Allocates packed-weight storage + activation workspace for batches up to max_batch on the current
+ * device.  c_in = number of input channels (17 / 18 ...). */
+int straps_regressor_create(straps_regressor_t** out, int c_in, int max_batch);
+void straps_regressor_destroy(straps_regressor_t* r);
+size_t straps_regressor_workspace_bytes(const straps_regressor_t* r);
+/* Name of the i-th convolution (0..19) in the order straps_regressor_load expects: "conv1",
+ * "layer1.0.conv1", "layer1.0.conv2", ..., "layer2.0.downsample.0", ... (state_dict order). */
+const char* straps_regressor_conv_name(const straps_regressor_t* r, int i);
+
+/* (Re)pack weights from PyTorch-owned device tensors in the reference state_dict layout:
+ *   conv_w[20]  : OIHW fp32 conv weights in forward order (conv1, then per BasicBlock conv1, conv2,
+ *                 [downsample.0])  -- models/resnet.py:145,177-199.
+ *   bn[20*4]    : for each conv's BatchNorm: weight, bias, running_mean, running_var (fp32 [Cout]).
+ *   fc_w[3], fc_b[3] : IEF fc1 [512,669], fc2 [512,512], fc3 [157,512] and biases.
+ *   init_params : dev [157] initial estimate (models/ief_module.py:31).
+ * Eval-mode BN is folded into per-channel scale/shift here.  Asynchronous on `stream`. */
+int straps_regressor_load(straps_regressor_t* r, const float* const* conv_w, const float* const* bn,
+                          const float* const* fc_w, const float* const* fc_b, const float* init_params,
+                          void* stream);
+
+/* Encoder only: x dev [B,C,256,256] NCHW fp32 -> feat dev [B,512]. */
+int straps_encoder_forward(straps_regressor_t* r, const float* x, int batch, int conv_mode,
+                           float* feat, void* stream);
+/* IEF only: feat dev [B,512] -> params dev [B,157] after `iters` iterations. */
+int straps_ief_forward(straps_regressor_t* r, const float* feat, int batch, int iters,
+                       float* params, void* stream);
+/* Both: x -> params [B,157] (cam = [:, :3], pose6d = [:, 3:147], shape = [:, 147:]). */
+int straps_regressor_forward(straps_regressor_t* r, const float* x, int batch, int conv_mode,
+                             int iters, float* feat_or_null, float* params, void* stream);
+
+/* Debug/parity hook: copy a named intermediate activation (as NCHW fp32) of the last forward into
+ * out (dev).  Names: "stem", "pool", "layer1.0" ... "layer4.1".  Returns element count via *n. */
+int straps_encoder_read_activation(straps_regressor_t* r, const char* name, int batch, float* out,
+                                   int64_t* n, void* stream);
+
+#pragma GCC visibility pop
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STRAPS_B200_H_ */

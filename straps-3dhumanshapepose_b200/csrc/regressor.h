@@ -1,0 +1,69 @@
+// regressor.h -- internal structures shared by the encoder / IEF translation units.
+#pragma once
+#include "common.cuh"
+#include "../../include/straps_b200.h"
+#include <vector>
+#include <string>
+
+namespace straps {
+
+constexpr int IMG = 256;
+constexpr int NCONV = 20;
+constexpr int IEF_IN = STRAPS_FEAT_DIM + STRAPS_IEF_PARAMS;   // 669
+constexpr int IEF_H = 512;
+constexpr int IEF_OUT_PAD = 160;
+
+// One convolution (+ folded BatchNorm [+ residual] [+ ReLU]) of the ResNet-18 encoder.
+struct ConvSpec {
+  int cin, cin_pad, cout, ksize, stride, pad;
+  int hin, win, hout, wout;
+  int in_buf, out_buf, res_buf;   // activation buffer ids (-1 = none)
+  int relu;
+  std::string name;
+  // device pointers
+  float* w_simt;    // [(kh,kw,ci_pad)][cout] fp32
+  float* scale;     // [cout] gamma / sqrt(var + eps)
+  float* shift;     // [cout] beta - mean * scale
+  // tensor-core path (conv_tc.cu)
+  void* w_hi;       // [cout][k_eff] bf16, BN scale folded
+  void* w_lo;
+  int k_eff;        // padded reduction length of the tensor-core layout
+};
+
+struct ActBuf {
+  std::string name;   // "" = internal
+  int h, w, c;        // NHWC per body
+  size_t offset;      // bytes into the workspace (for max_batch bodies)
+  size_t bytes;
+};
+
+}  // namespace straps
+
+struct straps_regressor {
+  int c_in, c_in_pad, max_batch;
+  straps::ConvSpec conv[straps::NCONV];
+  std::vector<straps::ActBuf> bufs;
+  int buf_xin, buf_stem, buf_pool, buf_final;
+  unsigned char* ws;       // activation workspace
+  size_t ws_bytes;
+  float* wpool;            // packed weights pool
+  size_t wpool_bytes;
+  // IEF
+  float *w1t, *w2t, *w3t, *b1, *b2, *b3, *init, *feat_scratch;
+  // tensor-core path state (opaque, owned by conv_tc.cu)
+  void* tc;
+  int loaded;
+  int last_mode;
+};
+
+namespace straps {
+int ief_launch(const straps_regressor* r, const float* feat, int batch, int iters, float* params, cudaStream_t st);
+int ief_pack(straps_regressor* r, const float* const* fc_w, const float* const* fc_b, const float* init, cudaStream_t st);
+// tensor-core encoder (conv_tc.cu)
+int tc_create(straps_regressor* r);
+void tc_destroy(straps_regressor* r);
+int tc_pack(straps_regressor* r, const float* const* conv_w, cudaStream_t st);
+int tc_encoder_forward(straps_regressor* r, const float* x, int batch, float* feat, cudaStream_t st);
+int tc_read_activation(straps_regressor* r, int buf, int batch, float* out, cudaStream_t st);
+inline float* act_ptr(const straps_regressor* r, int buf) { return reinterpret_cast<float*>(r->ws + r->bufs[buf].offset); }
+}  // namespace straps

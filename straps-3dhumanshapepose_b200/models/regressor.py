@@ -1,0 +1,29 @@
+"""SingleInputRegressor, B200-native (drop-in for reference models/regressor.py:7-47).
+
+proxy representation [B, C, 256, 256] -> (cam [B,3], pose6d [B,144], shape [B,10]); `.image_encoder` and
+`.ief_module` keep the reference's names and state_dict (132 keys).  One engine packs both halves so the
+whole forward is a straight run of library kernels on the caller's CUDA stream.
+"""
+import torch.nn as nn
+
+from models.resnet import resnet18
+from models.ief_module import IEFModule
+from straps_b200.engine import RegressorEngine, require_inference
+
+
+class SingleInputRegressor(nn.Module):
+    def __init__(self, resnet_in_channels=1, resnet_layers=18, ief_iters=3, conv_mode=None):
+        """conv_mode: 'bf16x3_tc' (tcgen05, default) or 'fp32_simt' (CUDA-core fp32) -- B200 extension."""
+        super(SingleInputRegressor, self).__init__()
+        if resnet_layers != 18:
+            raise NotImplementedError('resnet_layers=%r: only the ResNet-18 regressor is on the B200 hot path'
+                                      % (resnet_layers,))
+        num_output_params = 3 + 24 * 6 + 10
+        self.image_encoder = resnet18(in_channels=resnet_in_channels, pretrained=False)
+        self.ief_module = IEFModule([512, 512], 512, num_output_params, iterations=ief_iters)
+        self._engine = RegressorEngine(encoder=self.image_encoder, ief=self.ief_module, conv_mode=conv_mode)
+
+    def forward(self, input):
+        require_inference(self, 'SingleInputRegressor.forward')
+        params = self._engine.forward(input, self.ief_module.iterations)
+        return params[:, :3], params[:, 3:147], params[:, 147:]

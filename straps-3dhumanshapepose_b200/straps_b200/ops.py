@@ -1,0 +1,214 @@
+"""Torch-tensor front ends of the C ABI (device memory and streams only -- the maths is in csrc/)."""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import StrapsError, check
+
+CONV_FP32_SIMT = 0
+CONV_BF16X3_TC = 1
+_MODE_NAMES = {'fp32_simt': CONV_FP32_SIMT, 'bf16x3_tc': CONV_BF16X3_TC}
+DEFAULT_CONV_MODE = os.environ.get('STRAPS_CONV_MODE', 'bf16x3_tc')
+
+
+def conv_mode_id(mode):
+    if isinstance(mode, int):
+        return mode
+    if mode not in _MODE_NAMES:
+        raise ValueError('unknown conv mode %r (expected one of %s)' % (mode, sorted(_MODE_NAMES)))
+    return _MODE_NAMES[mode]
+
+
+def _need_cuda(t, name):
+    if not torch.is_tensor(t) or not t.is_cuda:
+        raise StrapsError('%s must be a CUDA tensor: the B200 path has no CPU fallback' % name)
+    if t.dtype != torch.float32:
+        raise StrapsError('%s must be float32 (got %s)' % (name, t.dtype))
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def rot6d_to_rotmat(x):
+    """[..., 6k] -> [n, 3, 3]  (reference utils/rigid_transform_utils.py:27-41)."""
+    _need_cuda(x, 'x')
+    x = x.contiguous().view(-1, 6)
+    out = torch.empty((x.shape[0], 3, 3), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().straps_rot6d_to_rotmat(_p(x), x.shape[0], _p(out), _stream(x.device)), 'straps_rot6d_to_rotmat')
+    return out
+
+
+def orthographic_project(points3d, cam):
+    """[B,N,3], [B,3] -> [B,N,2]  (reference utils/cam_utils.py:5-26)."""
+    _need_cuda(points3d, 'points3D')
+    _need_cuda(cam, 'cam_params')
+    points3d = points3d.contiguous()
+    if cam.stride(1) != 1:
+        cam = cam.contiguous()
+    B, N = points3d.shape[0], points3d.shape[1]
+    out = torch.empty((B, N, 2), dtype=torch.float32, device=points3d.device)
+    with torch.cuda.device(points3d.device):
+        check(_lib.lib().straps_orthographic_project(_p(points3d), _p(cam), cam.stride(0), B, N, _p(out),
+                                                     _stream(points3d.device)), 'straps_orthographic_project')
+    return out
+
+
+class SmplHandle(object):
+    """Owns the device-resident packed SMPL constants of one CUDA device."""
+
+    def __init__(self, device, v_template, shapedirs, posedirs, J_regressor, lbs_weights, parents,
+                 extra_regressors, extra_pick_idx):
+        f32 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+        i64 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.int64))
+        arrs = [f32(v_template), f32(shapedirs), f32(posedirs), f32(J_regressor), f32(lbs_weights), i64(parents),
+                f32(extra_regressors), i64(extra_pick_idx)]
+        shapes = [(6890, 3), (6890, 3, 10), (207, 20670), (24, 6890), (6890, 24), (24,), (45, 6890), (21,)]
+        for a, s in zip(arrs, shapes):
+            if tuple(a.shape) != s:
+                raise StrapsError('SMPL constant has shape %s, expected %s' % (a.shape, s))
+        self.device = torch.device(device)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_smpl_create(ctypes.byref(self._h), *[ctypes.c_void_p(a.ctypes.data) for a in arrs]),
+                  'straps_smpl_create')
+        self.sparse4 = bool(_lib.lib().straps_smpl_is_sparse4(self._h))
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().straps_smpl_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def forward(self, global_orient, body_pose, betas, transl, pose2rot):
+        for n, t in (('global_orient', global_orient), ('body_pose', body_pose), ('betas', betas)):
+            _need_cuda(t, n)
+        B = max(betas.shape[0], global_orient.shape[0], body_pose.shape[0])
+        if pose2rot:
+            go = global_orient.reshape(global_orient.shape[0], 3)
+            bp = body_pose.reshape(body_pose.shape[0], 69)
+        else:
+            go = global_orient.reshape(global_orient.shape[0], 9)
+            bp = body_pose.reshape(body_pose.shape[0], 23 * 9)
+
+        def rows(t):
+            # row-strided views are passed as is; anything else is made contiguous
+            if t.stride(-1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+                t = t.contiguous()
+            if t.shape[0] != B:
+                t = t.expand(B, -1).contiguous()
+            return t
+        go, bp, be = rows(go), rows(bp), rows(betas.reshape(betas.shape[0], 10))
+        tr = None
+        if transl is not None:
+            _need_cuda(transl, 'transl')
+            tr = transl.reshape(-1, 3).expand(B, -1).contiguous()
+        verts = torch.empty((B, 6890, 3), dtype=torch.float32, device=betas.device)
+        joints = torch.empty((B, 90, 3), dtype=torch.float32, device=betas.device)
+        with torch.cuda.device(betas.device):
+            check(_lib.lib().straps_smpl_forward(self._h, _p(go), go.stride(0), _p(bp), bp.stride(0), _p(be), be.stride(0),
+                                                 _p(tr) if tr is not None else None, B, 1 if pose2rot else 0,
+                                                 _p(verts), _p(joints), _stream(betas.device)), 'straps_smpl_forward')
+        return verts, joints
+
+
+class RegressorHandle(object):
+    """Packed encoder + IEF weights and activation workspace of one CUDA device."""
+
+    def __init__(self, device, c_in, max_batch):
+        self.device = torch.device(device)
+        self.c_in, self.max_batch = c_in, max_batch
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_regressor_create(ctypes.byref(self._h), c_in, max_batch), 'straps_regressor_create')
+        self.conv_names = [_lib.lib().straps_regressor_conv_name(self._h, i).decode() for i in range(20)]
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().straps_regressor_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def workspace_bytes(self):
+        return int(_lib.lib().straps_regressor_workspace_bytes(self._h))
+
+    def load(self, conv_w, bn, fc_w, fc_b, init_params):
+        """conv_w: 20 tensors (order = self.conv_names); bn: 20 x (weight, bias, running_mean, running_var)."""
+        flat_bn = [t for quad in bn for t in quad]
+        tensors = list(conv_w) + flat_bn + list(fc_w) + list(fc_b) + [init_params]
+        keep = []
+        for t in tensors:
+            _need_cuda(t, 'weight')
+            keep.append(t.detach().contiguous())
+        arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        n = 0
+        cw = keep[n:n + 20]; n += 20
+        bb = keep[n:n + 80]; n += 80
+        fw = keep[n:n + 3]; n += 3
+        fb = keep[n:n + 3]; n += 3
+        ip = keep[n]
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_regressor_load(self._h, arr(cw), arr(bb), arr(fw), arr(fb), _p(ip), _stream(self.device)),
+                  'straps_regressor_load')
+        self._keep = keep   # the pack kernels are asynchronous: keep the sources alive
+
+    def encoder_forward(self, x, mode=DEFAULT_CONV_MODE):
+        _need_cuda(x, 'input')
+        x = x.contiguous()
+        B = x.shape[0]
+        if x.shape[1:] != (self.c_in, 256, 256):
+            raise StrapsError('encoder input must be [B,%d,256,256], got %s' % (self.c_in, tuple(x.shape)))
+        feat = torch.empty((B, 512), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_encoder_forward(self._h, _p(x), B, conv_mode_id(mode), _p(feat), _stream(self.device)),
+                  'straps_encoder_forward')
+        return feat
+
+    def ief_forward(self, feat, iters=3):
+        _need_cuda(feat, 'img_features')
+        feat = feat.contiguous()
+        params = torch.empty((feat.shape[0], 157), dtype=torch.float32, device=feat.device)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_ief_forward(self._h, _p(feat), feat.shape[0], iters, _p(params), _stream(self.device)),
+                  'straps_ief_forward')
+        return params
+
+    def forward(self, x, mode=DEFAULT_CONV_MODE, iters=3, out=None):
+        _need_cuda(x, 'input')
+        x = x.contiguous()
+        B = x.shape[0]
+        if x.shape[1:] != (self.c_in, 256, 256):
+            raise StrapsError('regressor input must be [B,%d,256,256], got %s' % (self.c_in, tuple(x.shape)))
+        params = out if out is not None else torch.empty((B, 157), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_regressor_forward(self._h, _p(x), B, conv_mode_id(mode), iters, None, _p(params),
+                                                      _stream(self.device)), 'straps_regressor_forward')
+        return params
+
+    def read_activation(self, name, batch):
+        shapes = {'stem': (64, 128, 128), 'pool': (64, 64, 64)}
+        for L, (c, hw) in enumerate(((64, 64), (128, 32), (256, 16), (512, 8))):
+            for blk in range(2):
+                for suffix in ('', '.a', '.ds'):
+                    shapes['layer%d.%d%s' % (L + 1, blk, suffix)] = (c, hw, hw)
+        c, h, w = shapes[name]
+        out = torch.empty((batch, c, h, w), dtype=torch.float32, device=self.device)
+        n = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_encoder_read_activation(self._h, name.encode(), batch, _p(out), ctypes.byref(n),
+                                                            _stream(self.device)), 'straps_encoder_read_activation')
+        assert n.value == out.numel()
+        return out

@@ -1,0 +1,130 @@
+"""GPU parity: fused SMPL forward / rot6d / projection kernels (through the drop-in API -> ctypes -> C ABI)
+against the CPU oracle and the reference-generated fixtures.  Tolerance: 1e-4 relative fp32 (north_star),
+bit-exact for index work (vertex picks, faces, parents)."""
+import numpy as np
+import pytest
+import torch
+
+import straps_oracle as O
+from conftest import golden, smpl_inputs, rel_err, RTOL
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def smpl(assets_root):
+    import config
+    from models.smpl_official import SMPL
+    return SMPL(config.SMPL_MODEL_DIR, batch_size=4).to(DEV)
+
+
+def _oracle_rotmats(smpl_oracle, pose6d, betas):
+    with torch.no_grad():
+        R = O.rot6d_to_rotmat(torch.from_numpy(pose6d)).view(-1, 24, 3, 3)
+        v, j = smpl_oracle.forward_rotmats(R, torch.from_numpy(betas))
+    return R, v, j
+
+
+def test_config1_b4_against_reference_fixture(smpl):
+    """BASELINE config 1: SMPL forward only, B=4, random pose/shape."""
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    g = golden('smpl_b4.npz')
+    betas, pose6d, aa = smpl_inputs(4, 11)
+    with torch.no_grad():
+        R = rot6d_to_rotmat(torch.from_numpy(pose6d).to(DEV)).view(-1, 24, 3, 3)
+        out = smpl(body_pose=R[:, 1:], global_orient=R[:, 0].unsqueeze(1), betas=torch.from_numpy(betas).to(DEV), pose2rot=False)
+        out_aa = smpl(body_pose=torch.from_numpy(aa[:, 3:]).to(DEV), global_orient=torch.from_numpy(aa[:, :3]).to(DEV),
+                      betas=torch.from_numpy(betas).to(DEV))
+        out_t = smpl(betas=torch.from_numpy(betas).to(DEV))
+    assert rel_err(R.cpu().numpy(), g['rotmats']) < 1e-5
+    assert rel_err(out.vertices.cpu().numpy(), g['vertices']) < RTOL
+    assert rel_err(out.joints.cpu().numpy(), g['joints']) < RTOL
+    assert rel_err(out_aa.vertices.cpu().numpy(), g['vertices_aa']) < RTOL
+    assert rel_err(out_aa.joints.cpu().numpy(), g['joints_aa']) < RTOL
+    assert rel_err(out_t.vertices.cpu().numpy(), g['vertices_tpose']) < RTOL
+    assert rel_err(out_t.joints.cpu().numpy(), g['joints_tpose']) < RTOL
+    # integer work is bit exact
+    assert np.array_equal(smpl.faces_tensor.cpu().numpy(), g['faces'])
+    assert np.array_equal(smpl.parents.cpu().numpy(), g['parents'])
+    assert out.full_pose is None and out.betas.shape == (4, 10) and out.joints.shape == (4, 90, 3)
+
+
+@pytest.mark.parametrize('B', [1, 2, 3, 5, 8, 13, 33, 64, 100])
+def test_ragged_batches_against_oracle(smpl, smpl_oracle, B):
+    betas, pose6d, aa = smpl_inputs(B, 100 + B)
+    R, v, j = _oracle_rotmats(smpl_oracle, pose6d, betas)
+    Rg = R.to(DEV)
+    with torch.no_grad():
+        out = smpl(body_pose=Rg[:, 1:], global_orient=Rg[:, 0].unsqueeze(1), betas=torch.from_numpy(betas).to(DEV), pose2rot=False)
+    assert rel_err(out.vertices.cpu().numpy(), v.numpy()) < RTOL
+    assert rel_err(out.joints.cpu().numpy(), j.numpy()) < RTOL
+    # the 21 picked joints are plain copies of vertices: bit exact against the kernel's own vertices
+    idx = smpl.extra_joints_idxs
+    assert torch.equal(out.joints[:, 24:45], out.vertices[:, idx])
+    # consumers' index selections (config.py:27-32) are exact gathers
+    import config
+    coco = out.joints[:, config.ALL_JOINTS_TO_COCO_MAP]
+    assert torch.equal(coco[:, 0], out.joints[:, 24]) and coco.shape == (B, 17, 3)
+
+
+def test_axis_angle_and_transl(smpl, smpl_oracle):
+    B = 6
+    betas, _, aa = smpl_inputs(B, 7)
+    transl = np.random.RandomState(5).normal(0, 1, (B, 3)).astype(np.float32)
+    with torch.no_grad():
+        v, j = smpl_oracle.forward(betas=torch.from_numpy(betas), body_pose=torch.from_numpy(aa[:, 3:]),
+                                   global_orient=torch.from_numpy(aa[:, :3]), pose2rot=True)
+        out = smpl(betas=torch.from_numpy(betas).to(DEV), body_pose=torch.from_numpy(aa[:, 3:]).to(DEV),
+                   global_orient=torch.from_numpy(aa[:, :3]).to(DEV), transl=torch.from_numpy(transl).to(DEV))
+    t = torch.from_numpy(transl)[:, None]
+    assert rel_err(out.vertices.cpu().numpy(), (v + t).numpy()) < RTOL
+    assert rel_err(out.joints.cpu().numpy(), (j + t).numpy()) < RTOL
+
+
+def test_zero_rotation_vector_has_no_nan(smpl):
+    """batch_rodrigues adds 1e-8 inside the norm, so an all-zero pose is finite (T-pose)."""
+    with torch.no_grad():
+        out = smpl(betas=torch.zeros(4, 10, device=DEV))
+    assert torch.isfinite(out.vertices).all() and torch.isfinite(out.joints).all()
+    assert rel_err(out.vertices[0].cpu().numpy(), smpl.v_template.cpu().numpy()) < 1e-6
+
+
+def test_properties_at_large_batch(smpl):
+    """Size-independent properties at B=256 (BASELINE config 5 sizes): identity pose -> shape blend; rigid root."""
+    B = 256
+    rng = np.random.RandomState(8)
+    betas = torch.from_numpy(rng.normal(0, 1, (B, 10)).astype(np.float32)).to(DEV)
+    R = torch.eye(3, device=DEV).repeat(B, 24, 1, 1)
+    with torch.no_grad():
+        out = smpl(body_pose=R[:, 1:], global_orient=R[:, :1], betas=betas, pose2rot=False)
+        v_shaped = smpl.v_template + torch.einsum('bl,mkl->bmk', betas, smpl.shapedirs)
+        J = torch.einsum('bik,ji->bjk', v_shaped, smpl.J_regressor)
+    assert rel_err(out.vertices.cpu().numpy(), v_shaped.cpu().numpy()) < 1e-5
+    assert rel_err(out.joints[:, :24].cpu().numpy(), J.cpu().numpy()) < 1e-5
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    R0 = rot6d_to_rotmat(torch.from_numpy(rng.normal(0, 1, (B, 6)).astype(np.float32)).to(DEV))
+    R2 = R.clone()
+    R2[:, 0] = R0
+    with torch.no_grad():
+        out2 = smpl(body_pose=R2[:, 1:], global_orient=R2[:, :1], betas=betas, pose2rot=False)
+        expect = torch.einsum('bij,bvj->bvi', R0, v_shaped - J[:, :1]) + J[:, :1]
+    assert rel_err(out2.vertices.cpu().numpy(), expect.cpu().numpy()) < 1e-5
+
+
+def test_rot6d_and_projection(smpl_oracle):
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    from utils.cam_utils import orthographic_project_torch
+    rng = np.random.RandomState(4)
+    x = rng.normal(0, 1, (64, 144)).astype(np.float32)
+    R = rot6d_to_rotmat(torch.from_numpy(x).to(DEV))
+    Ro = O.rot6d_to_rotmat(torch.from_numpy(x))
+    assert R.shape == (64 * 24, 3, 3)
+    assert rel_err(R.cpu().numpy(), Ro.numpy()) < 1e-5
+    assert (torch.linalg.det(R.cpu()) - 1).abs().max() < 1e-5
+    pts = rng.normal(0, 1, (7, 17, 3)).astype(np.float32)
+    params = rng.normal(0, 1, (7, 157)).astype(np.float32)
+    cam_view = torch.from_numpy(params).to(DEV)[:, :3]            # non-contiguous view, like the IEF output
+    out = orthographic_project_torch(torch.from_numpy(pts).to(DEV), cam_view)
+    ref = O.orthographic_project(torch.from_numpy(pts), torch.from_numpy(params)[:, :3])
+    assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-6
