@@ -90,7 +90,7 @@ typedef struct straps_regressor straps_regressor_t;
 
 /* Conv precision modes for the encoder. */
 #define STRAPS_CONV_FP32_SIMT 0   /* fp32 FMA on CUDA cores (exact-order reference mode)           */
-#define STRAPS_CONV_BF16X3_TC 1   /* tcgen05 tensor cores, 2-term bf16 split, 3 MMA passes, fp32 acc */
+#define STRAPS_CONV_F16X3_TC 1   /* tcgen05 tensor cores, 2-term fp16 split, 3 MMA passes, fp32 acc */
 
 /* Allocates packed-weight storage + activation workspace for batches up to max_batch on the current
  * device.  c_in = number of input channels (17 / 18 ...). */

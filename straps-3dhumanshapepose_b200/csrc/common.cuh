@@ -174,11 +174,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                          // SWIZZLE_128B   [61,64)
   return d;
 }
-// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
+// Instruction descriptors for kind::f16 (fp32 accumulate, both operands K-major).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4)            // c_format = F32
          | (1u << 7)          // a_format = BF16
          | (1u << 10)         // b_format = BF16
+         | ((N >> 3) << 17)   // n_dim
+         | ((M >> 4) << 24);  // m_dim
+}
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4)            // c_format = F32, a_format = b_format = F16 (0)
          | ((N >> 3) << 17)   // n_dim
          | ((M >> 4) << 24);  // m_dim
 }

@@ -11,7 +11,7 @@
 //
 // This file holds the STRAPS_CONV_FP32_SIMT mode: a classic 128x64x8 register-tiled implicit GEMM on the FP32
 // pipes (exact fp32 accumulation, used as the on-device cross-check of the tensor-core mode and wherever
-// bit-stable fp32 ordering is wanted).  The headline mode, STRAPS_CONV_BF16X3_TC, lives in conv_tc.cu.
+// bit-stable fp32 ordering is wanted).  The headline mode, STRAPS_CONV_F16X3_TC, lives in conv_tc.cu.
 #include "regressor.h"
 
 namespace straps {
@@ -389,7 +389,7 @@ extern "C" int straps_encoder_forward(straps_regressor_t* r, const float* x, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   r->last_mode = conv_mode;
   if (conv_mode == STRAPS_CONV_FP32_SIMT) return encoder_forward_simt(r, x, batch, feat, st);
-  if (conv_mode == STRAPS_CONV_BF16X3_TC) return tc_encoder_forward(r, x, batch, feat, st);
+  if (conv_mode == STRAPS_CONV_F16X3_TC) return tc_encoder_forward(r, x, batch, feat, st);
   STRAPS_CHECK(false, "straps_encoder_forward: unknown conv_mode %d", conv_mode);
 }
 
@@ -421,7 +421,7 @@ extern "C" int straps_encoder_read_activation(straps_regressor_t* r, const char*
   const size_t total = (size_t)batch * b.c * b.h * b.w;
   if (n) *n = (int64_t)total;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (r->last_mode == STRAPS_CONV_BF16X3_TC) return tc_read_activation(r, id, batch, out, st);
+  if (r->last_mode == STRAPS_CONV_F16X3_TC) return tc_read_activation(r, id, batch, out, st);
   nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(act_ptr(r, id), b.c, b.h, b.w, out, total);
   STRAPS_LAUNCH_CHECK();
   return 0;

@@ -13,7 +13,7 @@ from straps_b200.engine import RegressorEngine, require_inference
 
 class SingleInputRegressor(nn.Module):
     def __init__(self, resnet_in_channels=1, resnet_layers=18, ief_iters=3, conv_mode=None):
-        """conv_mode: 'bf16x3_tc' (tcgen05, default) or 'fp32_simt' (CUDA-core fp32) -- B200 extension."""
+        """conv_mode: 'f16x3_tc' (tcgen05, default) or 'fp32_simt' (CUDA-core fp32) -- B200 extension."""
         super(SingleInputRegressor, self).__init__()
         if resnet_layers != 18:
             raise NotImplementedError('resnet_layers=%r: only the ResNet-18 regressor is on the B200 hot path'
@@ -22,6 +22,9 @@ class SingleInputRegressor(nn.Module):
         self.image_encoder = resnet18(in_channels=resnet_in_channels, pretrained=False)
         self.ief_module = IEFModule([512, 512], 512, num_output_params, iterations=ief_iters)
         self._engine = RegressorEngine(encoder=self.image_encoder, ief=self.ief_module, conv_mode=conv_mode)
+        # the halves share the combined engine, so `.image_encoder(x)` / `.ief_module(f)` reuse the same packed weights
+        self.image_encoder._engine = self._engine
+        self.ief_module._engine = self._engine
 
     def forward(self, input):
         require_inference(self, 'SingleInputRegressor.forward')

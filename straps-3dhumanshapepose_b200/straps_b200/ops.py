@@ -9,9 +9,9 @@ from . import _lib
 from ._lib import StrapsError, check
 
 CONV_FP32_SIMT = 0
-CONV_BF16X3_TC = 1
-_MODE_NAMES = {'fp32_simt': CONV_FP32_SIMT, 'bf16x3_tc': CONV_BF16X3_TC}
-DEFAULT_CONV_MODE = os.environ.get('STRAPS_CONV_MODE', 'bf16x3_tc')
+CONV_F16X3_TC = 1
+_MODE_NAMES = {'fp32_simt': CONV_FP32_SIMT, 'f16x3_tc': CONV_F16X3_TC}
+DEFAULT_CONV_MODE = os.environ.get('STRAPS_CONV_MODE', 'f16x3_tc')
 
 
 def conv_mode_id(mode):
@@ -112,7 +112,12 @@ class SmplHandle(object):
         tr = None
         if transl is not None:
             _need_cuda(transl, 'transl')
-            tr = transl.reshape(-1, 3).expand(B, -1).contiguous()
+            tr = transl.reshape(-1, 3)
+            if tr.shape[0] not in (1, B):
+                # smplx broadcasts `vertices + transl.unsqueeze(1)`: a model built for another batch size fails there too
+                raise StrapsError('SMPL: transl has batch %d but the call has batch %d -- construct SMPL(batch_size=%d) '
+                                  '(reference run_train.py:109-110)' % (tr.shape[0], B, B))
+            tr = tr.expand(B, -1).contiguous()
         verts = torch.empty((B, 6890, 3), dtype=torch.float32, device=betas.device)
         joints = torch.empty((B, 90, 3), dtype=torch.float32, device=betas.device)
         with torch.cuda.device(betas.device):

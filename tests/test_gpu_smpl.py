@@ -12,11 +12,21 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-@pytest.fixture(scope='module')
-def smpl(assets_root):
+_MODELS = {}
+
+
+def _smpl(batch):
+    """SMPL default parameters are sized by the constructor's batch_size."""
     import config
     from models.smpl_official import SMPL
-    return SMPL(config.SMPL_MODEL_DIR, batch_size=4).to(DEV)
+    if batch not in _MODELS:
+        _MODELS[batch] = SMPL(config.SMPL_MODEL_DIR, batch_size=batch).to(DEV)
+    return _MODELS[batch]
+
+
+@pytest.fixture(scope='module')
+def smpl(assets_root):
+    return _smpl(4)
 
 
 def _oracle_rotmats(smpl_oracle, pose6d, betas):
@@ -51,7 +61,8 @@ def test_config1_b4_against_reference_fixture(smpl):
 
 
 @pytest.mark.parametrize('B', [1, 2, 3, 5, 8, 13, 33, 64, 100])
-def test_ragged_batches_against_oracle(smpl, smpl_oracle, B):
+def test_ragged_batches_against_oracle(assets_root, smpl_oracle, B):
+    smpl = _smpl(B)
     betas, pose6d, aa = smpl_inputs(B, 100 + B)
     R, v, j = _oracle_rotmats(smpl_oracle, pose6d, betas)
     Rg = R.to(DEV)
@@ -68,8 +79,9 @@ def test_ragged_batches_against_oracle(smpl, smpl_oracle, B):
     assert torch.equal(coco[:, 0], out.joints[:, 24]) and coco.shape == (B, 17, 3)
 
 
-def test_axis_angle_and_transl(smpl, smpl_oracle):
+def test_axis_angle_and_transl(assets_root, smpl_oracle):
     B = 6
+    smpl = _smpl(B)
     betas, _, aa = smpl_inputs(B, 7)
     transl = np.random.RandomState(5).normal(0, 1, (B, 3)).astype(np.float32)
     with torch.no_grad():
@@ -90,9 +102,18 @@ def test_zero_rotation_vector_has_no_nan(smpl):
     assert rel_err(out.vertices[0].cpu().numpy(), smpl.v_template.cpu().numpy()) < 1e-6
 
 
-def test_properties_at_large_batch(smpl):
+def test_batch_size_mismatch_is_rejected_like_the_reference(smpl):
+    from straps_b200._lib import StrapsError
+    with pytest.raises(StrapsError):
+        with torch.no_grad():
+            smpl(betas=torch.zeros(9, 10, device=DEV), body_pose=torch.zeros(9, 69, device=DEV),
+                 global_orient=torch.zeros(9, 3, device=DEV))
+
+
+def test_properties_at_large_batch(assets_root):
     """Size-independent properties at B=256 (BASELINE config 5 sizes): identity pose -> shape blend; rigid root."""
     B = 256
+    smpl = _smpl(B)
     rng = np.random.RandomState(8)
     betas = torch.from_numpy(rng.normal(0, 1, (B, 10)).astype(np.float32)).to(DEV)
     R = torch.eye(3, device=DEV).repeat(B, 24, 1, 1)

@@ -1,0 +1,71 @@
+"""BASELINE config 5: LBS-only kernel sweep, achieved HBM GB/s against the measured roofline.
+
+Algorithmic bytes per launch: 20,587,320 B of constants + 84,664 B per body.
+Usage: python tools/bench_lbs.py [--batches 1 8 64 256 1024 4096] [--iters 50]   -> one JSON line per batch size
+"""
+import argparse
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, 'straps-3dhumanshapepose_b200'))
+os.environ.setdefault('STRAPS_ASSETS_ROOT', os.path.join(REPO, 'tests', '_scratch', 'assets'))
+import numpy as np
+import torch
+from straps_b200 import synthetic_assets
+
+synthetic_assets.write_synthetic_assets(os.environ['STRAPS_ASSETS_ROOT'], seed=0)
+import config
+from models.smpl_official import SMPL
+from utils.rigid_transform_utils import rot6d_to_rotmat
+
+CONST_BYTES, BODY_BYTES = 20587320, 84664
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batches', type=int, nargs='+', default=[1, 8, 64, 256, 1024, 4096])
+    ap.add_argument('--iters', type=int, default=50)
+    args = ap.parse_args()
+    peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(REPO, 'MEASURED_PEAKS.json')) else {}
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    dev = 'cuda:0'
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # 256 MB > 126 MB L2
+    for B in args.batches:
+        smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(dev)
+        rng = np.random.RandomState(B)
+        betas = torch.from_numpy(rng.normal(0, 1, (B, 10)).astype(np.float32)).to(dev)
+        R = rot6d_to_rotmat(torch.from_numpy(rng.normal(0, 1, (B, 144)).astype(np.float32)).to(dev)).view(B, 24, 3, 3)
+        go, bp = R[:, :1], R[:, 1:]
+        with torch.no_grad():
+            for _ in range(5):
+                smpl(body_pose=bp, global_orient=go, betas=betas, pose2rot=False)
+            cold, warm = [], []
+            for it in range(args.iters):
+                flush.zero_()                                   # evict L2 between timed launches
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                smpl(body_pose=bp, global_orient=go, betas=betas, pose2rot=False)
+                e1.record()
+                torch.cuda.synchronize()
+                cold.append(e0.elapsed_time(e1))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for it in range(args.iters):
+                smpl(body_pose=bp, global_orient=go, betas=betas, pose2rot=False)
+            e1.record()
+            torch.cuda.synchronize()
+            warm_ms = e0.elapsed_time(e1) / args.iters
+        cold_ms = float(np.median(cold))
+        bytes_ = CONST_BYTES + BODY_BYTES * B
+        print(json.dumps({'workload': 'SMPL LBS forward (lbs_kernel + joints_kernel)', 'batch': B,
+                          'ms_cold_l2': cold_ms, 'ms_back_to_back': warm_ms, 'bodies_per_s': B / (warm_ms * 1e-3),
+                          'algorithmic_bytes': bytes_, 'achieved_gbs_cold': bytes_ / (cold_ms * 1e-3) / 1e9,
+                          'achieved_gbs_back_to_back': bytes_ / (warm_ms * 1e-3) / 1e9, 'peak_gbs': hbm,
+                          'frac_cold': bytes_ / (cold_ms * 1e-3) / 1e9 / hbm,
+                          'fma_gflops': 2 * 8.56e6 * B / (warm_ms * 1e-3) / 1e9}))
+
+
+if __name__ == '__main__':
+    main()
