@@ -31,6 +31,7 @@
 #include "regressor.h"
 #include <cuda_fp16.h>
 #include <map>
+#include <cstdlib>
 
 namespace straps {
 
@@ -61,14 +62,27 @@ struct TcConvParams {
   int relu;
 };
 
-template <int BN>
+// BN = output-channel tile, MT = number of 128-pixel M-tiles that share one weight tile per K-block.
+// Measured (tools/tc_probe.cu, profiles/r01_tc_probe.txt): an SS-mode tcgen05.mma M128xNx16 costs 48 / 64 / 128 cycles
+// for N = 64 / 128 / 256, i.e. it streams its operands from shared memory at the full 128 B/clk for N <= 128, so
+// the TMA writes of the next stages and the MMA operand reads share one 128 B/clk port and the kernel is
+// SHARED-MEMORY-BANDWIDTH bound:  cycles per K-block ~ (MMA operand bytes + TMA bytes) / 128.
+//   (64,1): 56 + 48 KB -> 812 cycles  (MMA alone 448)      (128,1): 80 + 64 KB -> 1125 cycles (MMA alone 768)
+// Wider tiles -- (128,2), (256,1) -- need fewer bytes per FLOP but only fit 2 ring stages and a single TMEM
+// accumulator stage; they measured 10-25 % SLOWER (profiles/r01_launches_tilecfg.txt) and are kept only as
+// template instantiations for the next round (2-CTA pairs halve the weight bytes per SM).
+template <int BN, int MT>
 struct TcCfg {
-  static constexpr int STAGES = (BN == 64) ? 4 : 3;
-  static constexpr int A_BYTES = BM_TC * 128;           // one plane of the A tile
+  static constexpr int A_BYTES = BM_TC * 128;           // one plane of one A tile
   static constexpr int W_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int STAGE_BYTES = MT * 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int STAGES = (220 * 1024 / STAGE_BYTES) > 4 ? 4 : (220 * 1024 / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TILE_COLS = 2 * BN;              // per M-tile: [hi.hi | lo terms]
+  static constexpr int ACC_COLS = MT * TILE_COLS;       // per accumulator stage
+  static constexpr int TSTAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = TSTAGES * ACC_COLS;
+  static_assert(STAGES >= 2 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "bad tile configuration");
 };
 
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
@@ -81,12 +95,12 @@ __device__ __forceinline__ uint32_t pack_f16(__half a, __half b) {
 __device__ __forceinline__ float f16lo_to_f(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
 __device__ __forceinline__ float f16hi_to_f(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
-template <int BN>
+template <int BN, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const TcConvParams p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, MT>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -97,7 +111,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = p.n_mtiles * p.n_ntiles;
+  const int n_groups = (p.n_mtiles + MT - 1) / MT;          // a work item = MT consecutive M-tiles x one N-tile
+  const int n_items = n_groups * p.n_ntiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
@@ -117,60 +132,85 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       // ================= TMA producer =================
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_ntiles, nt = tile % p.n_ntiles;
-        const long long pix0 = (long long)mt * BM_TC;
-        const int b0 = (int)(pix0 / p.hw_out);
-        const int oh0 = (int)((pix0 % p.hw_out) / p.wout);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
+        int b0[MT], oh0[MT];
+#pragma unroll
+        for (int t = 0; t < MT; ++t) {
+          const long long pix0 = (long long)(mg * MT + t) * BM_TC;   // tiles past the end land out of bounds -> zeros
+          b0[t] = (int)(pix0 / p.hw_out);
+          oh0[t] = (int)((pix0 % p.hw_out) / p.wout);
+        }
         for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
           const int st = it % Cfg::STAGES;
           mbar_wait(&empty[st], ((it / Cfg::STAGES) & 1) ^ 1);
           unsigned char* sa = smem + st * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
-          int c0, c1, c2;
+          int c0, c1, dh;
           if (p.conv1) {
             const int kh = kb / 3, j = kb % 3;
-            c0 = kh * (XP_W * XP_C) + j * 64; c1 = 0; c2 = oh0;
+            c0 = kh * (XP_W * XP_C) + j * 64; c1 = 0; dh = 0;
           } else {
             const int tap = kb / p.cchunks, cc = kb % p.cchunks;
             const int kh = tap / p.kw_count, kw = tap % p.kw_count;
-            c0 = cc * 64; c1 = kw - p.pad; c2 = oh0 * p.stride + kh - p.pad;
+            c0 = cc * 64; c1 = kw - p.pad; dh = kh - p.pad;
           }
-          tma_load_4d(sa, &map_a_hi, &full[st], c0, c1, c2, b0);
-          tma_load_4d(sa + Cfg::A_BYTES, &map_a_lo, &full[st], c0, c1, c2, b0);
-          tma_load_2d(sa + 2 * Cfg::A_BYTES, &map_w_hi, &full[st], kb * BK_TC, nt * BN);
-          tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &map_w_lo, &full[st], kb * BK_TC, nt * BN);
+#pragma unroll
+          for (int t = 0; t < MT; ++t) {
+            const int c2 = p.conv1 ? oh0[t] : oh0[t] * p.stride + dh;
+            tma_load_4d(sa + (2 * t) * Cfg::A_BYTES, &map_a_hi, &full[st], c0, c1, c2, b0[t]);
+            tma_load_4d(sa + (2 * t + 1) * Cfg::A_BYTES, &map_a_lo, &full[st], c0, c1, c2, b0[t]);
+          }
+          unsigned char* sw = sa + MT * 2 * Cfg::A_BYTES;
+          tma_load_2d(sw, &map_w_hi, &full[st], kb * BK_TC, nt * BN);
+          tma_load_2d(sw + Cfg::W_BYTES, &map_w_lo, &full[st], kb * BK_TC, nt * BN);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ================= MMA issuer =================
+      // W_hi and W_lo are adjacent in the stage, so for BN <= 128 ONE MMA of width 2*BN computes
+      // A_hi.[W_hi ; W_lo] into [acc_hi | acc_lo] (A_hi is read from shared memory once instead of twice).
+      // Two accumulators per tile: tensor-core fp32 accumulation truncates (measured -1e-8 relative per MMA, 5.6e-5
+      // at the features with a single accumulator), so the small lo-terms get their own accumulator and only
+      // K/16 additions happen at full magnitude; the two are summed in fp32 in the epilogue.
       constexpr uint32_t idesc = umma_idesc_f16(BM_TC, BN);
+      constexpr uint32_t idesc_wide = umma_idesc_f16(BM_TC, (2 * BN <= 256) ? 2 * BN : BN);
       uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t as = ti & 1;
-        mbar_wait(&tempty[as], ((ti >> 1) & 1) ^ 1);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+        const uint32_t as = ti % Cfg::TSTAGES;
+        mbar_wait(&tempty[as], ((ti / Cfg::TSTAGES) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
           const int st = it % Cfg::STAGES;
           mbar_wait(&full[st], (it / Cfg::STAGES) & 1);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
-          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + Cfg::A_BYTES);
-          const uint64_t w_hi = umma_desc_sw128(sa + 2 * Cfg::A_BYTES);
-          const uint64_t w_lo = umma_desc_sw128(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES);
+          const uint64_t w_hi = umma_desc_sw128(sa + MT * 2 * Cfg::A_BYTES);
+          const uint64_t w_lo = umma_desc_sw128(sa + MT * 2 * Cfg::A_BYTES + Cfg::W_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK_TC / 16; ++k) {
-            const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 bytes along K inside the 128-byte swizzle row
-            umma_f16(d_tmem, a_lo + ko, w_hi + ko, idesc, (kb | k) != 0);
-            umma_f16(d_tmem, a_hi + ko, w_lo + ko, idesc, 1);
-            umma_f16(d_tmem, a_hi + ko, w_hi + ko, idesc, 1);
+          for (int t = 0; t < MT; ++t) {
+            const uint64_t a_hi = umma_desc_sw128(sa + (2 * t) * Cfg::A_BYTES);
+            const uint64_t a_lo = umma_desc_sw128(sa + (2 * t + 1) * Cfg::A_BYTES);
+            const uint32_t d_hi = tmem_base + as * Cfg::ACC_COLS + t * Cfg::TILE_COLS, d_lo = d_hi + BN;
+#pragma unroll
+            for (int k = 0; k < BK_TC / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 bytes along K inside the 128-byte swizzle row
+              const uint32_t first = (kb | k) != 0;
+              if constexpr (2 * BN <= 256) {
+                umma_f16(d_hi, a_hi + ko, w_hi + ko, idesc_wide, first);   // -> [acc_hi | acc_lo]
+                umma_f16(d_lo, a_lo + ko, w_hi + ko, idesc, 1);
+              } else {
+                umma_f16(d_hi, a_hi + ko, w_hi + ko, idesc, first);
+                umma_f16(d_lo, a_hi + ko, w_lo + ko, idesc, first);
+                umma_f16(d_lo, a_lo + ko, w_hi + ko, idesc, 1);
+              }
+            }
           }
           umma_commit(&empty[st]);          // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&tfull[as]);            // accumulator complete -> epilogue
+        umma_commit(&tfull[as]);            // accumulators complete -> epilogue
       }
     }
   } else {
@@ -178,69 +218,74 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const int mt = tile / p.n_ntiles, nt = tile % p.n_ntiles;
-      const uint32_t as = ti & 1;
-      mbar_wait(&tfull[as], (ti >> 1) & 1);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+      const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
+      const uint32_t as = ti % Cfg::TSTAGES;
+      mbar_wait(&tfull[as], (ti / Cfg::TSTAGES) & 1);
       tc_fence_after();
-      const long long m = (long long)mt * BM_TC + row;
-      const bool valid = m < p.m_total;
-      const size_t obase = (size_t)m * p.cout + (size_t)nt * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + c0, v);
-        tmem_ld_wait();
-        float y[32];
-        const float4* sh4 = reinterpret_cast<const float4*>(p.shift + nt * BN + c0);
-        const float4* us4 = reinterpret_cast<const float4*>(p.unscale + nt * BN + c0);
+      for (int t = 0; t < MT; ++t) {
+        const long long m = (long long)(mg * MT + t) * BM_TC + row;
+        const bool valid = m < p.m_total;
+        const size_t obase = (size_t)m * p.cout + (size_t)nt * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32], vl[32];
+          const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + as * Cfg::ACC_COLS + t * Cfg::TILE_COLS + c0;
+          tmem_ld_32x32(tacc, v);
+          tmem_ld_32x32(tacc + BN, vl);
+          tmem_ld_wait();
+          float y[32];
+          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + nt * BN + c0);
+          const float4* us4 = reinterpret_cast<const float4*>(p.unscale + nt * BN + c0);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
-          y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]), u4.x, s4.x);
-          y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]), u4.y, s4.y);
-          y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]), u4.z, s4.z);
-          y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]), u4.w, s4.w);
-        }
-        if (valid) {
-          if (p.res_hi) {
-            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + obase + c0);
-            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + obase + c0);
+          for (int q = 0; q < 8; ++q) {
+            const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
+            y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
+            y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
+            y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
+            y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+          }
+          if (valid) {
+            if (p.res_hi) {
+              const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + obase + c0);
+              const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + obase + c0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 h = __ldg(rh + q), l = __ldg(rl + q);
-              const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+              for (int q = 0; q < 4; ++q) {
+                const uint4 h = __ldg(rh + q), l = __ldg(rl + q);
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                y[q * 8 + e * 2 + 0] += f16lo_to_f(hw[e]) + f16lo_to_f(lw[e]);
-                y[q * 8 + e * 2 + 1] += f16hi_to_f(hw[e]) + f16hi_to_f(lw[e]);
+                for (int e = 0; e < 4; ++e) {
+                  y[q * 8 + e * 2 + 0] += f16lo_to_f(hw[e]) + f16lo_to_f(lw[e]);
+                  y[q * 8 + e * 2 + 1] += f16hi_to_f(hw[e]) + f16hi_to_f(lw[e]);
+                }
               }
             }
-          }
-          if (p.relu) {
+            if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
-          }
-          if (p.out_f32) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
-          } else {
-            uint32_t ph[16], pl[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              __half h0, l0, h1, l1;
-              split_f16(y[2 * i], h0, l0);
-              split_f16(y[2 * i + 1], h1, l1);
-              ph[i] = pack_f16(h0, h1);
-              pl[i] = pack_f16(l0, l1);
+              for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
             }
-            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
-            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
+            if (p.out_f32) {
+              float4* o = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
-              ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
+              for (int q = 0; q < 8; ++q) o[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+            } else {
+              uint32_t ph[16], pl[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                __half h0, l0, h1, l1;
+                split_f16(y[2 * i], h0, l0);
+                split_f16(y[2 * i + 1], h1, l1);
+                ph[i] = pack_f16(h0, h1);
+                pl[i] = pack_f16(l0, l1);
+              }
+              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
+              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
+                ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
+              }
             }
           }
         }
@@ -257,22 +302,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
 }
 
-// x NCHW fp32 [B,C,256,256] -> padded NHWC split planes [B,262,264,24] (interior only; the halo stays zero)
-__global__ void pack_input_tc_kernel(const float* __restrict__ x, int C, __half* __restrict__ hi,
-                                     __half* __restrict__ lo) {
-  __shared__ float tile[XP_C][33];
-  const int w0 = blockIdx.x * 32, h = blockIdx.y, b = blockIdx.z;
-  for (int c = threadIdx.y; c < XP_C; c += blockDim.y)
-    tile[c][threadIdx.x] = (c < C) ? x[(((size_t)b * C + c) * IMG + h) * IMG + w0 + threadIdx.x] : 0.f;
-  __syncthreads();
-  const size_t base = (((size_t)b * XP_H + h + 3) * XP_W + (w0 + 3)) * XP_C;
-  for (int i = threadIdx.y * 32 + threadIdx.x; i < 32 * XP_C / 2; i += 32 * blockDim.y) {
-    const int w = (2 * i) / XP_C, c = (2 * i) % XP_C;
+// x NCHW fp32 [B,C,256,256] -> padded NHWC split planes [B,262,264,24] (interior only; the halo stays zero).
+// One CTA per (b, h) image row, one thread per pixel: the C channel rows are read with fully coalesced 1 KB
+// requests (all loads in flight before the first use), split to fp16 hi/lo and staged through shared memory so
+// that the two 12 KB output rows leave as contiguous 16-byte stores.  HBM-bound: 4*C + 96 bytes per pixel.
+__global__ void __launch_bounds__(256) pack_input_tc_kernel(const float* __restrict__ x, int C, __half* __restrict__ hi,
+                                                            __half* __restrict__ lo) {
+  __shared__ __align__(16) uint32_t srow[2][IMG * XP_C / 2];   // [plane][256 px * 12 half2]
+  const int h = blockIdx.x, b = blockIdx.y, w = threadIdx.x;
+  const float* src = x + ((size_t)b * C * IMG + h) * IMG + w;
+  float v[XP_C];
+#pragma unroll
+  for (int c = 0; c < XP_C; ++c) v[c] = (c < C) ? __ldg(src + (size_t)c * IMG * IMG) : 0.f;
+#pragma unroll
+  for (int c = 0; c < XP_C; c += 2) {
     __half h0, l0, h1, l1;
-    split_f16(tile[c][w], h0, l0);
-    split_f16(tile[c + 1][w], h1, l1);
-    reinterpret_cast<uint32_t*>(hi + base)[i] = pack_f16(h0, h1);
-    reinterpret_cast<uint32_t*>(lo + base)[i] = pack_f16(l0, l1);
+    split_f16(v[c], h0, l0);
+    split_f16(v[c + 1], h1, l1);
+    srow[0][w * (XP_C / 2) + c / 2] = pack_f16(h0, h1);
+    srow[1][w * (XP_C / 2) + c / 2] = pack_f16(l0, l1);
+  }
+  __syncthreads();
+  const size_t base = (((size_t)b * XP_H + h + 3) * XP_W + 3) * XP_C;   // 16-byte aligned (48 B per pixel)
+  uint4* dh = reinterpret_cast<uint4*>(hi + base);
+  uint4* dl = reinterpret_cast<uint4*>(lo + base);
+  const uint4* sh = reinterpret_cast<const uint4*>(srow[0]);
+  const uint4* sl = reinterpret_cast<const uint4*>(srow[1]);
+  for (int i = w; i < IMG * XP_C * 2 / 16; i += 256) {
+    dh[i] = sh[i];
+    dl[i] = sl[i];
   }
 }
 
@@ -497,7 +555,16 @@ static int encode(TcState* t, CUtensorMap* m, void* base, int rank, const cuuint
   return 0;
 }
 
-static int tile_bn(const ConvSpec& c) { return c.cout == 64 ? 64 : 128; }
+// tile configuration per layer (see TcCfg): BN, MT
+static void tile_cfg(const ConvSpec& c, int* bn, int* mt) {
+  const char* e = getenv("STRAPS_TC_TILES");      // "wide" selects the experimental (64,2)/(128,2)/(256,1) shapes
+  const bool wide = e && e[0] == 'w';
+  if (c.cout == 64) { *bn = 64; *mt = wide ? 2 : 1; }
+  else if (c.cout == 128) { *bn = 128; *mt = wide ? 2 : 1; }
+  else if (c.cout == 256 && wide) { *bn = 256; *mt = 1; }
+  else { *bn = 128; *mt = 1; }
+}
+static int tile_bn(const ConvSpec& c) { int bn, mt; tile_cfg(c, &bn, &mt); return bn; }
 
 static int build_maps(straps_regressor* r, int B, std::vector<TcLayerMaps>& out) {
   TcState* t = static_cast<TcState*>(r->tc);
@@ -543,17 +610,17 @@ static int build_maps(straps_regressor* r, int B, std::vector<TcLayerMaps>& out)
   return 0;
 }
 
-template <int BN>
+template <int BN, int MT>
 static int launch_conv_tc(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    STRAPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    STRAPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = p.n_mtiles * p.n_ntiles;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w_hi, m.w_lo, p);
+  const int items = ((p.n_mtiles + MT - 1) / MT) * p.n_ntiles;
+  const int grid = items < num_sms ? items : num_sms;
+  conv_tc_kernel<BN, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w_hi, m.w_lo, p);
   STRAPS_LAUNCH_CHECK();
   return 0;
 }
@@ -588,7 +655,12 @@ static int run_conv_tc(straps_regressor* r, const std::vector<TcLayerMaps>& maps
     p.res_hi = plane_hi(r, c.res_buf);
     p.res_lo = plane_lo(r, c.res_buf);
   }
-  return bn == 64 ? launch_conv_tc<64>(maps[ci], p, t->num_sms, st) : launch_conv_tc<128>(maps[ci], p, t->num_sms, st);
+  int mt;
+  { int bn2; tile_cfg(c, &bn2, &mt); }
+  if (bn == 64) return mt == 2 ? launch_conv_tc<64, 2>(maps[ci], p, t->num_sms, st) : launch_conv_tc<64, 1>(maps[ci], p, t->num_sms, st);
+  if (bn == 256) return launch_conv_tc<256, 1>(maps[ci], p, t->num_sms, st);
+  if (mt == 2) return launch_conv_tc<128, 2>(maps[ci], p, t->num_sms, st);
+  return launch_conv_tc<128, 1>(maps[ci], p, t->num_sms, st);
 }
 
 int tc_encoder_forward(straps_regressor* r, const float* x, int B, float* feat, cudaStream_t st) {
@@ -601,7 +673,7 @@ int tc_encoder_forward(straps_regressor* r, const float* x, int B, float* feat, 
     it = t->maps.emplace(B, std::move(v)).first;
   }
   const std::vector<TcLayerMaps>& maps = it->second;
-  pack_input_tc_kernel<<<dim3(IMG / 32, IMG, B), dim3(32, 8), 0, st>>>(x, r->c_in, t->xp, t->xp + t->xp_plane);
+  pack_input_tc_kernel<<<dim3(IMG, B), 256, 0, st>>>(x, r->c_in, t->xp, t->xp + t->xp_plane);
   STRAPS_LAUNCH_CHECK();
   if (run_conv_tc(r, maps, 0, B, st)) return 1;
   {

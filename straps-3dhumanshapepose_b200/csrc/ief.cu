@@ -31,16 +31,18 @@ struct IefSmem {
   float red[KQ][NLOC][TBI];     // K-slice partial sums (also used as [8][32][TBI] by fc3)
 };
 
-// acc[b] += sum_{k in [k0,k1)} wt[k*ld + col] * x[k][b]
+// acc[b] += sum_{k in [k0,k1)} wt[k*ld + col] * x[k][b].  The weight stream comes from L2 (~700 cycles away): 16
+// independent loads are issued before the first FMA so one thread keeps 16 requests in flight.
 __device__ __forceinline__ void dot_slice(const float* __restrict__ wt, int ld, int col, int k0, int k1,
                                           const float (*x)[TBI], float (&acc)[TBI]) {
+  constexpr int U = 16;
   int k = k0;
-  for (; k + 4 <= k1; k += 4) {
-    float w[4];
+  for (; k + U <= k1; k += U) {
+    float w[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = __ldg(wt + (size_t)(k + u) * ld + col);
+    for (int u = 0; u < U; ++u) w[u] = __ldg(wt + (size_t)(k + u) * ld + col);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const float4 x0 = *reinterpret_cast<const float4*>(&x[k + u][0]);
       const float4 x1 = *reinterpret_cast<const float4*>(&x[k + u][4]);
       acc[0] = fmaf(w[u], x0.x, acc[0]); acc[1] = fmaf(w[u], x0.y, acc[1]);
@@ -49,10 +51,17 @@ __device__ __forceinline__ void dot_slice(const float* __restrict__ wt, int ld, 
       acc[6] = fmaf(w[u], x1.z, acc[6]); acc[7] = fmaf(w[u], x1.w, acc[7]);
     }
   }
-  for (; k < k1; ++k) {
-    const float w = __ldg(wt + (size_t)k * ld + col);
+  if (k < k1) {
+    float w[U];
 #pragma unroll
-    for (int b = 0; b < TBI; ++b) acc[b] = fmaf(w, x[k][b], acc[b]);
+    for (int u = 0; u < U; ++u) w[u] = (k + u < k1) ? __ldg(wt + (size_t)(k + u) * ld + col) : 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (k + u < k1) {
+#pragma unroll
+        for (int b = 0; b < TBI; ++b) acc[b] = fmaf(w[u], x[k + u][b], acc[b]);
+      }
+    }
   }
 }
 

@@ -72,14 +72,21 @@ struct LbsArgs {
   float* joints;
 };
 
+// Prologue scratch (global transforms G, rotations R, rest joints Jr) lives in ring stages 1..2, which are not
+// filled until the prologue is over: 53 KB of shared memory per CTA instead of 71 KB -> 4 CTAs (16 warps) per SM.
+template <int TB>
+struct LbsScratch {
+  float G[TB][NJ][12];
+  float R[TB][NJ][9];
+  float Jr[TB][NJ][3];
+};
+static_assert(sizeof(LbsScratch<8>) <= 2 * KC * ROWF * sizeof(float), "prologue scratch must fit in ring stages 1..2");
+
 template <int TB>
 struct LbsSmem {
   float pbuf[NSTAGE][KC][ROWF];   // posedirs ring; reused as the output staging tile
   float pf[NPF_PAD][TB];          // pose feature, body-minor (float4 broadcast loads)
   float4 A[TB][NJ][3];            // skinning transforms, rows [R | t]
-  float G[TB][NJ][12];            // global transforms
-  float R[TB][NJ][9];
-  float Jr[TB][NJ][3];
   float beta[TB][STRAPS_NUM_BETAS];
   float tr[TB][4];
   uint64_t full[NSTAGE];
@@ -107,6 +114,7 @@ template <int TB, bool SPARSE>
 __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LbsSmem<TB>& s = *reinterpret_cast<LbsSmem<TB>*>(smem_raw);
+  LbsScratch<TB>& x = *reinterpret_cast<LbsScratch<TB>*>(&s.pbuf[1][0][0]);
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
   const int b0 = blockIdx.y * TB;
@@ -130,10 +138,7 @@ __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs 
     for (int r = 0; r < KC; ++r)
       bulk_g2s(&s.pbuf[st][r][0], slab + (size_t)(chunk * KC + r) * VP3, ROWF * 4, &s.full[st]);
   };
-  if (tid == 0) {
-    issue_chunk(0);
-    issue_chunk(1);
-  }
+  if (tid == 0) issue_chunk(0);
 
   // ---- prologue: rotations, pose feature, rest joints, kinematic chain (overlaps the first slab loads) ----
   for (int i = tid; i < TB * STRAPS_NUM_BETAS; i += TV) {
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs 
                                     : a.bp + (size_t)(b0 + b) * a.bp_stride + (j - 1) * 3;
         r[0] = src[0]; r[1] = src[1]; r[2] = src[2];
       }
-      rodrigues(r, &s.R[b][j][0]);
+      rodrigues(r, &x.R[b][j][0]);
     }
   } else {
     for (int i = tid; i < TB * NJ * 9; i += TV) {
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs 
       if (b < nb)
         v = (j == 0) ? a.go[(size_t)(b0 + b) * a.go_stride + e]
                      : a.bp[(size_t)(b0 + b) * a.bp_stride + (j - 1) * 9 + e];
-      s.R[b][j][e] = v;
+      x.R[b][j][e] = v;
     }
   }
   __syncthreads();
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs 
     float v = 0.f;
     if (k < NPF) {
       int e = k % 9;
-      v = s.R[b][1 + k / 9][e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+      v = x.R[b][1 + k / 9][e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
     }
     s.pf[k][b] = v;
   }
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs 
     float acc = 0.f;
 #pragma unroll
     for (int l = 0; l < STRAPS_NUM_BETAS; ++l) acc = fmaf(m.js[jc * STRAPS_NUM_BETAS + l], s.beta[b][l], acc);
-    s.Jr[b][jc / 3][jc % 3] = m.jt[jc] + acc;
+    x.Jr[b][jc / 3][jc % 3] = m.jt[jc] + acc;
   }
   __syncthreads();
   for (int lvl = 0; lvl < m.nlevels; ++lvl) {
@@ -188,15 +193,15 @@ __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs 
     for (int i = tid; i < TB * nj * 3; i += TV) {
       int b = i / (nj * 3), q = i % (nj * 3), j = m.lvl_joint[j0 + q / 3], r = q % 3;
       int p = m.parents[j];
-      const float* Rj = &s.R[b][j][0];
-      float* g = &s.G[b][j][r * 4];
+      const float* Rj = &x.R[b][j][0];
+      float* g = &x.G[b][j][r * 4];
       if (p < 0) {
-        g[0] = Rj[r * 3 + 0]; g[1] = Rj[r * 3 + 1]; g[2] = Rj[r * 3 + 2]; g[3] = s.Jr[b][j][r];
+        g[0] = Rj[r * 3 + 0]; g[1] = Rj[r * 3 + 1]; g[2] = Rj[r * 3 + 2]; g[3] = x.Jr[b][j][r];
       } else {
-        const float* gp = &s.G[b][p][r * 4];
-        float rel0 = s.Jr[b][j][0] - s.Jr[b][p][0];
-        float rel1 = s.Jr[b][j][1] - s.Jr[b][p][1];
-        float rel2 = s.Jr[b][j][2] - s.Jr[b][p][2];
+        const float* gp = &x.G[b][p][r * 4];
+        float rel0 = x.Jr[b][j][0] - x.Jr[b][p][0];
+        float rel1 = x.Jr[b][j][1] - x.Jr[b][p][1];
+        float rel2 = x.Jr[b][j][2] - x.Jr[b][p][2];
 #pragma unroll
         for (int c = 0; c < 3; ++c) g[c] = gp[0] * Rj[0 * 3 + c] + gp[1] * Rj[1 * 3 + c] + gp[2] * Rj[2 * 3 + c];
         g[3] = gp[0] * rel0 + gp[1] * rel1 + gp[2] * rel2 + gp[3];
@@ -206,12 +211,13 @@ __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs 
   }
   for (int i = tid; i < TB * NJ * 3; i += TV) {
     int b = i / (NJ * 3), q = i % (NJ * 3), j = q / 3, r = q % 3;
-    const float* g = &s.G[b][j][r * 4];
-    float t = g[3] - (g[0] * s.Jr[b][j][0] + g[1] * s.Jr[b][j][1] + g[2] * s.Jr[b][j][2]);
+    const float* g = &x.G[b][j][r * 4];
+    float t = g[3] - (g[0] * x.Jr[b][j][0] + g[1] * x.Jr[b][j][1] + g[2] * x.Jr[b][j][2]);
     s.A[b][j][r] = make_float4(g[0], g[1], g[2], t);
     if (tile == 0 && b < nb) a.joints[((size_t)(b0 + b) * STRAPS_NUM_SUPERSET_JOINTS + j) * 3 + r] = g[3] + s.tr[b][r];
   }
   __syncthreads();
+  if (tid == 0) issue_chunk(1);   // the scratch in stages 1..2 is dead from here on
 
   // ---- main loop: pose-corrective blend, acc[b][c] = sum_k pf[k][b] * posedirs[k][v*3+c] ----
   float acc[TB][3];
