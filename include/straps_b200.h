@@ -75,6 +75,24 @@ int straps_smpl_forward(const straps_smpl_t* m,
                         const float* transl, int batch, int pose2rot,
                         float* vertices, float* joints, void* stream);
 
+/* ---- training path of the SMPL side (backward of train/train_synthetic_otf_rendering.py:193-205) ---- */
+/* Same as straps_smpl_forward with pose2rot == 0 and rotmats dev [B,24,3,3] contiguous, and additionally saves what
+ * the backward needs: v_posed dev [B,6890,3] and the skinning transforms A dev [B,24,12]. */
+int straps_smpl_forward_train(const straps_smpl_t* m, const float* rotmats, const float* betas, int batch,
+                              float* vertices, float* joints, float* save_vposed, float* save_A, void* stream);
+/* Backward: g_joints dev [B,90,3]; gv_work dev [B,6890,3] = a WRITABLE COPY of the vertex gradient (the joint
+ * contributions are accumulated into it); scratch dev [B*(24*12+208+10)] floats.
+ * Outputs: d_rotmats dev [B,24,3,3], d_betas dev [B,10]. */
+int straps_smpl_backward(const straps_smpl_t* m, const float* rotmats, const float* betas, const float* v_posed,
+                         const float* A, const float* g_joints, float* gv_work, float* scratch, int batch,
+                         float* d_rotmats, float* d_betas, void* stream);
+/* Backward of rot6d_to_rotmat: x6 dev [n,6], dR dev [n,3,3] -> dx6 dev [n,6]. */
+int straps_rot6d_backward(const float* x6, const float* dR, int64_t n, float* dx6, void* stream);
+/* Backward of the weak-perspective projection: g_out dev [B,N,2] -> d_points dev [B,N,3], d_cam dev [B,3]. */
+int straps_orthographic_project_backward(const float* points, const float* cam, int64_t cam_stride,
+                                         const float* g_out, int batch, int npoints, float* d_points, float* d_cam,
+                                         void* stream);
+
 /* utils/rigid_transform_utils.py:27-41 -- x6 dev [n,6] (interleaved a1/a2) -> R dev [n,3,3]. */
 int straps_rot6d_to_rotmat(const float* x6, int64_t n, float* R, void* stream);
 
@@ -121,6 +139,32 @@ int straps_ief_forward(straps_regressor_t* r, const float* feat, int batch, int 
 /* Both: x -> params [B,157] (cam = [:, :3], pose6d = [:, 3:147], shape = [:, 147:]). */
 int straps_regressor_forward(straps_regressor_t* r, const float* x, int batch, int conv_mode,
                              int iters, float* feat_or_null, float* params, void* stream);
+
+/* ---- training path of the regressor (BASELINE config 3; reference train/...:186,230-233) ----
+ * Train-mode forward of the encoder: BatchNorm uses batch statistics (biased variance), and -- when
+ * update_running_stats != 0 -- updates the PyTorch-owned running_mean / running_var tensors given to
+ * straps_regressor_load in place (momentum 0.1, unbiased variance).  fp32 CUDA-core kernels.  Keeps every
+ * activation and pre-BN convolution output in the handle's training workspace for straps_encoder_backward. */
+int straps_encoder_train_forward(straps_regressor_t* r, const float* x, int batch, int update_running_stats,
+                                 float* feat, void* stream);
+/* Backward of the last straps_encoder_train_forward: dfeat dev [B,512] ->
+ *   d_conv_w[20] : OIHW fp32 weight gradients (same order as straps_regressor_load's conv_w), overwritten;
+ *   d_bn[40]     : (d_weight, d_bias) of the 20 BatchNorms, overwritten. */
+int straps_encoder_backward(straps_regressor_t* r, const float* dfeat, int batch, float* const* d_conv_w,
+                            float* const* d_bn, void* stream);
+/* IEF forward that also saves, per iteration, { p_k [B,157] | h1_k [B,512] | h2_k [B,512] } into
+ * saved dev [iters * B * 1181] for straps_ief_backward. */
+int straps_ief_forward_train(straps_regressor_t* r, const float* feat, int batch, int iters, float* params,
+                             float* saved, void* stream);
+/* IEF backward (shared-weight gradients accumulated over the iterations): d_params dev [B,157] ->
+ * d_feat dev [B,512], d_fc_w[3] (nn.Linear layout), d_fc_b[3]; scratch dev [B * 1850] floats. */
+int straps_ief_backward(straps_regressor_t* r, const float* feat, const float* saved, const float* d_params,
+                        int batch, int iters, float* d_feat, float* const* d_fc_w, float* const* d_fc_b,
+                        float* scratch, void* stream);
+/* torch.optim.Adam step (run_train.py:200-201 defaults: no weight decay) on a flat fp32 bucket; the gradient is
+ * multiplied by grad_scale first (1/world_size after the summing all-reduce).  step counts from 1. */
+int straps_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int step,
+                     float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* Debug/parity hook: copy a named intermediate activation (as NCHW fp32) of the last forward into
  * out (dev).  Names: "stem", "pool", "layer1.0" ... "layer4.1".  Returns element count via *n. */

@@ -69,7 +69,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(IEF_THREADS)
 ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const float* __restrict__ w1t,
            const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
            const float* __restrict__ w3t, const float* __restrict__ b3, int B, int iters,
-           float* __restrict__ params) {
+           float* __restrict__ params, float* __restrict__ saved) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   IefSmem& s = *reinterpret_cast<IefSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
@@ -104,7 +104,13 @@ ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const
     __syncthreads();
   }
 
+  // training: saved = [iters] x { p_k [B,157] | h1_k [B,512] | h2_k [B,512] }; CTA `rank` writes body b0+rank
+  const size_t per_iter = (size_t)B * (STRAPS_IEF_PARAMS + 2 * IEF_H);
+  const bool do_save = saved != nullptr && (b0 + rank < B);
   for (int it = 0; it < iters; ++it) {
+    if (do_save)
+      for (int k = tid; k < STRAPS_IEF_PARAMS; k += IEF_THREADS)
+        saved[it * per_iter + (size_t)(b0 + rank) * STRAPS_IEF_PARAMS + k] = s.xs[STRAPS_FEAT_DIM + k][rank];
     // ---- fc1 (params half) + ReLU -> all-gather h1
     {
       float acc[TBI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -123,6 +129,9 @@ ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const
         for (int peer = 0; peer < CL; ++peer) *cluster.map_shared_rank(local, peer) = v;
       }
       cluster.sync();
+      if (do_save)
+        for (int k = tid; k < IEF_H; k += IEF_THREADS)
+          saved[it * per_iter + (size_t)B * STRAPS_IEF_PARAMS + (size_t)(b0 + rank) * IEF_H + k] = s.h1[k][rank];
     }
     // ---- fc2 + ReLU -> all-gather h2
     {
@@ -140,6 +149,9 @@ ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const
         for (int peer = 0; peer < CL; ++peer) *cluster.map_shared_rank(local, peer) = v;
       }
       cluster.sync();
+      if (do_save)
+        for (int k = tid; k < IEF_H; k += IEF_THREADS)
+          saved[it * per_iter + (size_t)B * (STRAPS_IEF_PARAMS + IEF_H) + (size_t)(b0 + rank) * IEF_H + k] = s.h2[k][rank];
     }
     // ---- fc3: 20 outputs per CTA, 8 K-slices of 64;  p += delta -> all-gather the params rows of xs
     {
@@ -206,14 +218,17 @@ int ief_pack(straps_regressor* r, const float* const* fc_w, const float* const* 
   return 0;
 }
 
-int ief_launch(const straps_regressor* r, const float* feat, int batch, int iters, float* params, cudaStream_t st) {
+int ief_launch_train(const straps_regressor* r, const float* feat, int batch, int iters, float* params, float* saved, cudaStream_t st) {
   const int nclusters = ceil_div(batch, TBI);
   const size_t smem = sizeof(IefSmem);
   STRAPS_CUDA(cudaFuncSetAttribute(ief_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ief_kernel<<<nclusters * CL, IEF_THREADS, smem, st>>>(feat, r->init, r->w1t, r->b1, r->w2t, r->b2, r->w3t, r->b3,
-                                                       batch, iters, params);
+                                                       batch, iters, params, saved);
   STRAPS_LAUNCH_CHECK();
   return 0;
+}
+int ief_launch(const straps_regressor* r, const float* feat, int batch, int iters, float* params, cudaStream_t st) {
+  return ief_launch_train(r, feat, batch, iters, params, nullptr, st);
 }
 
 }  // namespace straps

@@ -69,16 +69,6 @@ __global__ void fold_bn_kernel(const float* g, const float* b, const float* m, c
   shift[i] = b[i] - m[i] * s;
 }
 
-struct ConvArgs {
-  const float* in;     // NHWC [B,hin,win,cin_pad]
-  const float* w;      // [(kh,kw,ci)][cout]
-  const float* scale;
-  const float* shift;
-  const float* res;    // NHWC [B,hout,wout,cout] or null
-  float* out;          // NHWC [B,hout,wout,cout]
-  int B, hin, win, cin, hout, wout, cout, ks, stride, pad, relu;
-};
-
 constexpr int BM = 128, BN = 64, BK = 8, APAD = 4;
 
 __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
@@ -108,9 +98,18 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
   auto gload = [&](int kc) {
     const int tap = kc / cchunks, ci0 = (kc % cchunks) * BK;
     const int kh = tap / a.ks, kw = tap % a.ks;
-    const int ih = loh * a.stride - a.pad + kh, iw = low * a.stride - a.pad + kw;
+    int ih, iw;
+    bool ok = lvalid;
+    if (!a.transposed) {
+      ih = loh * a.stride - a.pad + kh; iw = low * a.stride - a.pad + kw;
+    } else {
+      // data gradient: GEMM rows are INPUT pixels, the gathered tensor is dY at ((ih + pad - kh) / stride, ...)
+      const int th = loh + a.pad - kh, tw = low + a.pad - kw;
+      ok = ok && th >= 0 && tw >= 0 && (th % a.stride) == 0 && (tw % a.stride) == 0;
+      ih = th / a.stride; iw = tw / a.stride;
+    }
     areg = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lvalid && ih >= 0 && ih < a.hin && iw >= 0 && iw < a.win)
+    if (ok && ih >= 0 && ih < a.hin && iw >= 0 && iw < a.win)
       areg = *reinterpret_cast<const float4*>(a.in + (((size_t)lb * a.hin + ih) * a.win + iw) * a.cin + ci0 + lh);
     if (tid < 128) {
       const int kr = tid >> 4, c4 = (tid & 15) * 4;
@@ -239,6 +238,7 @@ extern "C" int straps_regressor_create(straps_regressor_t** out, int c_in, int m
   straps_regressor* r = new straps_regressor();
   r->c_in = c_in; r->c_in_pad = (c_in + 7) / 8 * 8; r->max_batch = max_batch;
   r->ws = nullptr; r->ws_bytes = 0; r->wpool = nullptr; r->tc = nullptr; r->loaded = 0; r->last_mode = -1;
+  r->train = nullptr;
   // activation buffers (NHWC)
   r->buf_xin = add_buf(r, "", IMG, IMG, 32);        // sized for the widest packed-input layout either mode uses
   r->buf_stem = add_buf(r, "stem", 128, 128, 64);
@@ -312,6 +312,7 @@ extern "C" int straps_regressor_create(straps_regressor_t** out, int c_in, int m
 extern "C" void straps_regressor_destroy(straps_regressor_t* r) {
   if (!r) return;
   tc_destroy(r);
+  train_destroy(r);
   if (r->ws) cudaFree(r->ws);
   if (r->wpool) cudaFree(r->wpool);
   delete r;
@@ -338,35 +339,60 @@ extern "C" int straps_regressor_load(straps_regressor_t* r, const float* const* 
     fold_bn_kernel<<<ceil_div(c.cout, 128), 128, 0, st>>>(bn[4 * i], bn[4 * i + 1], bn[4 * i + 2], bn[4 * i + 3], c.cout,
                                                          c.scale, c.shift);
     STRAPS_LAUNCH_CHECK();
+    c.w_oihw = conv_w[i];
+    c.gamma = bn[4 * i]; c.beta = bn[4 * i + 1];
+    c.rmean = const_cast<float*>(bn[4 * i + 2]); c.rvar = const_cast<float*>(bn[4 * i + 3]);
   }
+  for (int i = 0; i < 3; ++i) { r->fc_w[i] = fc_w[i]; r->fc_b[i] = fc_b[i]; }
   if (ief_pack(r, fc_w, fc_b, init_params, st)) return 1;
   if (tc_pack(r, conv_w, st)) return 1;
   r->loaded = 1;
   return 0;
 }
 
+namespace straps {
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
+  dim3 grid(ceil_div(a.B * a.hout * a.wout, BM), a.cout / BN);
+  conv_simt_kernel<<<grid, 256, 0, st>>>(a);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace straps
+
+namespace straps {
+int launch_nchw_to_nhwc(straps_regressor* r, const float* x, int B, cudaStream_t st) {
+  nchw_to_nhwc_kernel<<<dim3(IMG / 32, IMG, B), dim3(32, 8), 0, st>>>(x, r->c_in, r->c_in_pad, IMG, IMG, act_ptr(r, r->buf_xin));
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+int launch_maxpool(straps_regressor* r, int B, cudaStream_t st) {
+  const size_t n = (size_t)B * 64 * 64 * 16;
+  maxpool_nhwc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(act_ptr(r, r->buf_stem), B, 128, 128, 64, act_ptr(r, r->buf_pool));
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+int launch_avgpool(straps_regressor* r, int B, float* feat, cudaStream_t st) {
+  avgpool_nhwc_kernel<<<ceil_div(B * 512, 256), 256, 0, st>>>(act_ptr(r, r->buf_final), B, 64, 512, feat);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace straps
+
 static int run_conv_simt(const straps_regressor* r, const ConvSpec& c, int B, cudaStream_t st) {
   ConvArgs a;
+  a.transposed = 0;
   a.in = act_ptr(r, c.in_buf); a.w = c.w_simt; a.scale = c.scale; a.shift = c.shift;
   a.res = c.res_buf >= 0 ? act_ptr(r, c.res_buf) : nullptr;
   a.out = act_ptr(r, c.out_buf);
   a.B = B; a.hin = c.hin; a.win = c.win; a.cin = c.cin_pad; a.hout = c.hout; a.wout = c.wout; a.cout = c.cout;
   a.ks = c.ksize; a.stride = c.stride; a.pad = c.pad; a.relu = c.relu;
-  dim3 grid(ceil_div(B * c.hout * c.wout, BM), c.cout / BN);
-  conv_simt_kernel<<<grid, 256, 0, st>>>(a);
-  STRAPS_LAUNCH_CHECK();
-  return 0;
+  return launch_conv_simt(a, st);
 }
 
 static int encoder_forward_simt(straps_regressor* r, const float* x, int B, float* feat, cudaStream_t st) {
-  nchw_to_nhwc_kernel<<<dim3(IMG / 32, IMG, B), dim3(32, 8), 0, st>>>(x, r->c_in, r->c_in_pad, IMG, IMG, act_ptr(r, r->buf_xin));
-  STRAPS_LAUNCH_CHECK();
+  if (launch_nchw_to_nhwc(r, x, B, st)) return 1;
   if (run_conv_simt(r, r->conv[0], B, st)) return 1;
-  {
-    const size_t n = (size_t)B * 64 * 64 * 16;
-    maxpool_nhwc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(act_ptr(r, r->buf_stem), B, 128, 128, 64, act_ptr(r, r->buf_pool));
-    STRAPS_LAUNCH_CHECK();
-  }
+  if (launch_maxpool(r, B, st)) return 1;
   int i = 1;
   while (i < NCONV) {
     // a block is conv1, conv2[, downsample]; the downsample branch must run before conv2 consumes it
@@ -376,9 +402,7 @@ static int encoder_forward_simt(straps_regressor* r, const float* x, int B, floa
     if (run_conv_simt(r, r->conv[i + 1], B, st)) return 1;
     i += ds ? 3 : 2;
   }
-  avgpool_nhwc_kernel<<<ceil_div(B * 512, 256), 256, 0, st>>>(act_ptr(r, r->buf_final), B, 64, 512, feat);
-  STRAPS_LAUNCH_CHECK();
-  return 0;
+  return launch_avgpool(r, B, feat, st);
 }
 
 extern "C" int straps_encoder_forward(straps_regressor_t* r, const float* x, int batch, int conv_mode, float* feat,
@@ -399,6 +423,14 @@ extern "C" int straps_ief_forward(straps_regressor_t* r, const float* feat, int 
   STRAPS_CHECK(r->loaded, "straps_ief_forward: weights not loaded");
   STRAPS_CHECK(batch >= 1 && iters >= 0, "straps_ief_forward: bad batch/iters %d/%d", batch, iters);
   return ief_launch(r, feat, batch, iters, params, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int straps_ief_forward_train(straps_regressor_t* r, const float* feat, int batch, int iters, float* params, float* saved,
+                                        void* stream) {
+  STRAPS_CHECK(r && feat && params && saved, "straps_ief_forward_train: null argument");
+  STRAPS_CHECK(r->loaded, "straps_ief_forward_train: weights not loaded");
+  STRAPS_CHECK(batch >= 1 && iters >= 0, "straps_ief_forward_train: bad batch/iters %d/%d", batch, iters);
+  return ief_launch_train(r, feat, batch, iters, params, saved, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int straps_regressor_forward(straps_regressor_t* r, const float* x, int batch, int conv_mode, int iters,

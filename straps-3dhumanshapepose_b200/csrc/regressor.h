@@ -24,10 +24,28 @@ struct ConvSpec {
   float* w_simt;    // [(kh,kw,ci_pad)][cout] fp32
   float* scale;     // [cout] gamma / sqrt(var + eps)
   float* shift;     // [cout] beta - mean * scale
+  // training path (train.cu): the PyTorch-owned tensors of the last straps_regressor_load
+  const float* w_oihw;
+  const float* gamma;
+  const float* beta;
+  float* rmean;
+  float* rvar;
   // tensor-core path (conv_tc.cu)
-  void* w_hi;       // [cout][k_eff] bf16, BN scale folded
+  void* w_hi;       // [cout][k_eff] fp16, BN scale folded
   void* w_lo;
   int k_eff;        // padded reduction length of the tensor-core layout
+};
+
+// arguments of the fp32 CUDA-core implicit-GEMM convolution (regressor.cu), also used for the data gradient
+struct ConvArgs {
+  const float* in;     // NHWC [B,hin,win,cin]   (the gathered tensor: activations, or dY when transposed)
+  const float* w;      // [(kh,kw,cin)][cout]
+  const float* scale;
+  const float* shift;
+  const float* res;    // NHWC [B,hout,wout,cout] added before the ReLU, or null
+  float* out;          // NHWC [B,hout,wout,cout]
+  int B, hin, win, cin, hout, wout, cout, ks, stride, pad, relu;
+  int transposed;      // 1 = data-gradient gather (rows are input pixels, `in` is dY)
 };
 
 struct ActBuf {
@@ -52,6 +70,9 @@ struct straps_regressor {
   float *w1t, *w2t, *w3t, *b1, *b2, *b3, *init, *feat_scratch;
   // tensor-core path state (opaque, owned by conv_tc.cu)
   void* tc;
+  void* train;             // training workspace (train.cu), allocated on first use
+  const float* fc_w[3];    // PyTorch-owned IEF weights / biases of the last load (nn.Linear layout)
+  const float* fc_b[3];
   int loaded;
   int last_mode;
 };
@@ -59,6 +80,12 @@ struct straps_regressor {
 namespace straps {
 int ief_launch(const straps_regressor* r, const float* feat, int batch, int iters, float* params, cudaStream_t st);
 int ief_pack(straps_regressor* r, const float* const* fc_w, const float* const* fc_b, const float* init, cudaStream_t st);
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+int launch_nchw_to_nhwc(straps_regressor* r, const float* x, int B, cudaStream_t st);
+int launch_maxpool(straps_regressor* r, int B, cudaStream_t st);
+int launch_avgpool(straps_regressor* r, int B, float* feat, cudaStream_t st);
+int ief_launch_train(const straps_regressor* r, const float* feat, int batch, int iters, float* params, float* saved, cudaStream_t st);
+void train_destroy(straps_regressor* r);
 // tensor-core encoder (conv_tc.cu)
 int tc_create(straps_regressor* r);
 void tc_destroy(straps_regressor* r);

@@ -21,44 +21,10 @@
 //   the pose-corrective term costs 621 FMA per (vertex, body) and is the FP32-FMA bound at B >= 64.
 // Kernel 2 (joints_kernel): one warp per (body, superset joint 24..89): picks are plain copies (bit exact),
 //   regressed rows are CSR dot products over the just-written (L2 resident) vertices.
-#include "common.cuh"
-#include "../../include/straps_b200.h"
-#include <vector>
+#include "smpl.h"
 #include <cmath>
 
 namespace straps {
-
-constexpr int V = STRAPS_NUM_VERTS;
-constexpr int TV = 128;                 // vertices per CTA
-constexpr int NTILES = (V + TV - 1) / TV;   // 54
-constexpr int VPAD = NTILES * TV;       // 6912
-constexpr int VP3 = VPAD * 3;
-constexpr int NJ = STRAPS_NUM_JOINTS;
-constexpr int NPF = (NJ - 1) * 9;       // 207
-constexpr int NPF_PAD = 208;
-constexpr int KC = 8;                   // posedirs rows per pipeline stage
-constexpr int NSTAGE = 3;
-constexpr int NCHUNK = NPF_PAD / KC;    // 26
-constexpr int ROWF = TV * 3;            // 384 floats per slab row
-
-struct SmplDev {
-  const float* vt;
-  const float* sdir;
-  const float* pdir;
-  const float* jt;
-  const float* js;
-  const int* widx;
-  const float* wval;
-  const float* wdense;
-  const int* pick_idx;
-  const int* csr_ptr;
-  const int* csr_idx;
-  const float* csr_val;
-  int parents[NJ];
-  int lvl_joint[NJ];      // joints sorted by tree depth
-  int lvl_start[NJ + 1];  // level l owns lvl_joint[lvl_start[l] .. lvl_start[l+1])
-  int nlevels;
-};
 
 struct LbsArgs {
   const float* go;
@@ -70,6 +36,8 @@ struct LbsArgs {
   int pose2rot;
   float* verts;
   float* joints;
+  float* save_vposed;   // [B,6890,3] or null (training: input of lbs_bwd_kernel)
+  float* save_A;        // [B,24,12]  or null
 };
 
 // Prologue scratch (global transforms G, rotations R, rest joints Jr) lives in ring stages 1..2, which are not
@@ -214,6 +182,8 @@ __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs 
     const float* g = &x.G[b][j][r * 4];
     float t = g[3] - (g[0] * x.Jr[b][j][0] + g[1] * x.Jr[b][j][1] + g[2] * x.Jr[b][j][2]);
     s.A[b][j][r] = make_float4(g[0], g[1], g[2], t);
+    if (tile == 0 && b < nb && a.save_A)
+      *reinterpret_cast<float4*>(a.save_A + ((size_t)(b0 + b) * NJ + j) * 12 + r * 4) = make_float4(g[0], g[1], g[2], t);
     if (tile == 0 && b < nb) a.joints[((size_t)(b0 + b) * STRAPS_NUM_SUPERSET_JOINTS + j) * 3 + r] = g[3] + s.tr[b][r];
   }
   __syncthreads();
@@ -288,6 +258,10 @@ __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs 
 #pragma unroll
       for (int l = 0; l < STRAPS_NUM_BETAS; ++l) bs = fmaf(s.beta[b][l], sd[l][c], bs);
       vp[c] = acc[b][c] + (vt3[c] + bs);   // v_posed = pose_offsets + v_shaped
+    }
+    if (a.save_vposed && b < nb && v < V) {
+      float* sv = a.save_vposed + ((size_t)(b0 + b) * V + v) * 3;
+      sv[0] = vp[0]; sv[1] = vp[1]; sv[2] = vp[2];
     }
     float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
     if constexpr (SPARSE) {
@@ -383,11 +357,6 @@ __global__ void ortho_kernel(const float* __restrict__ pts, const float* __restr
 
 using namespace straps;
 
-struct straps_smpl {
-  SmplDev d;
-  int sparse4;
-  std::vector<void*> allocs;
-};
 
 template <typename T>
 static int upload(straps_smpl* m, const std::vector<T>& h, const T** dst) {
@@ -524,10 +493,10 @@ static int launch_lbs(const straps_smpl* m, const LbsArgs& a, cudaStream_t st) {
   return 0;
 }
 
-extern "C" int straps_smpl_forward(const straps_smpl_t* m, const float* global_orient, int64_t go_stride,
-                                   const float* body_pose, int64_t bp_stride, const float* betas,
-                                   int64_t betas_stride, const float* transl, int batch, int pose2rot,
-                                   float* vertices, float* joints, void* stream) {
+static int smpl_forward_impl(const straps_smpl_t* m, const float* global_orient, int64_t go_stride,
+                             const float* body_pose, int64_t bp_stride, const float* betas,
+                             int64_t betas_stride, const float* transl, int batch, int pose2rot,
+                             float* vertices, float* joints, float* save_vposed, float* save_A, void* stream) {
   STRAPS_CHECK(m && global_orient && body_pose && betas && vertices && joints, "straps_smpl_forward: null argument");
   STRAPS_CHECK(batch > 0, "straps_smpl_forward: batch must be positive (got %d)", batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -535,6 +504,7 @@ extern "C" int straps_smpl_forward(const straps_smpl_t* m, const float* global_o
   a.go = global_orient; a.bp = body_pose; a.betas = betas; a.transl = transl;
   a.go_stride = go_stride; a.bp_stride = bp_stride; a.betas_stride = betas_stride;
   a.B = batch; a.pose2rot = pose2rot; a.verts = vertices; a.joints = joints;
+  a.save_vposed = save_vposed; a.save_A = save_A;
   // bodies per CTA: enough CTAs to fill 148 SMs at small batch, 8-way register tiling once the batch allows it
   int rc;
   if (batch >= 32) rc = launch_lbs<8>(m, a, st);
@@ -546,6 +516,21 @@ extern "C" int straps_smpl_forward(const straps_smpl_t* m, const float* global_o
   joints_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(m->d, vertices, joints, batch);
   STRAPS_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int straps_smpl_forward(const straps_smpl_t* m, const float* global_orient, int64_t go_stride,
+                                   const float* body_pose, int64_t bp_stride, const float* betas,
+                                   int64_t betas_stride, const float* transl, int batch, int pose2rot,
+                                   float* vertices, float* joints, void* stream) {
+  return smpl_forward_impl(m, global_orient, go_stride, body_pose, bp_stride, betas, betas_stride, transl, batch, pose2rot,
+                           vertices, joints, nullptr, nullptr, stream);
+}
+
+extern "C" int straps_smpl_forward_train(const straps_smpl_t* m, const float* rotmats, const float* betas, int batch,
+                                         float* vertices, float* joints, float* save_vposed, float* save_A, void* stream) {
+  STRAPS_CHECK(rotmats && save_vposed && save_A, "straps_smpl_forward_train: null argument");
+  return smpl_forward_impl(m, rotmats, 24 * 9, rotmats + 9, 24 * 9, betas, STRAPS_NUM_BETAS, nullptr, batch, 0, vertices, joints,
+                           save_vposed, save_A, stream);
 }
 
 extern "C" int straps_rot6d_to_rotmat(const float* x6, int64_t n, float* R, void* stream) {

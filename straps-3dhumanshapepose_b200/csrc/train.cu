@@ -1,0 +1,631 @@
+// train.cu -- training path of the regressor (BASELINE config 3): train-mode BatchNorm forward, full backward of the
+// ResNet-18 encoder and of the IEF stack, and a fused Adam step on a flat parameter/gradient bucket.
+//
+// Replaces what autograd + optim.Adam do for the reference's step (train/train_synthetic_otf_rendering.py:186,230-233,
+// run_train.py:200-201): BasicBlock.forward (models/resnet.py:61-77) in training mode, IEFModule.forward
+// (models/ief_module.py:48-64) unrolled over its iterations with shared-weight gradient accumulation.
+//
+// This round the training kernels are fp32 CUDA-core code (correctness first, gradient-checked against the CPU
+// oracle's autograd); the tensor-core data/weight gradients are next-round work.
+//   conv forward / data gradient : conv_simt_kernel (regressor.cu), the data gradient is the same implicit GEMM with a
+//                                  transposed gather over dY and weights repacked to [(kh,kw,co)][ci]
+//   conv weight gradient          : wgrad_kernel, [tap x 64 ci] x [64 co] tiles, split over pixels, fp32 atomics
+//   BatchNorm                     : two-pass batch statistics with fp64 accumulation (PyTorch's CPU kernel accumulates
+//                                  in double), biased variance for normalisation, unbiased for the running estimate
+//                                  (momentum 0.1, eps 1e-5); backward = 2 per-channel reductions + 1 elementwise pass
+//   IEF backward                  : generic 32x32 SIMT GEMM (all four transpose combinations) + ReLU masks + column sums
+// HBM layout: NHWC fp32 activations (regressor.cu); every conv keeps its pre-BN output `raw` for the backward.
+#include "regressor.h"
+
+namespace straps {
+
+struct TrainState {
+  int max_batch;
+  float* pool;                 // one allocation
+  size_t pool_bytes;
+  float* raw[NCONV];           // pre-BN conv outputs
+  std::vector<float*> gbuf;    // gradient wrt every activation buffer
+  float* gmask;                // scratch: masked block-output gradient (largest block activation)
+  float* draw;                 // scratch: gradient wrt a raw conv output (largest)
+  float* mean[NCONV];
+  float* invstd[NCONV];
+  double* dstat;               // [2][512] fp64 accumulators
+  float* fstat;                // [2][512] fp32 reductions (dbeta, dgamma)
+  float* ones; float* zeros;   // [512]
+  float* w_dgrad[NCONV];       // [(kh,kw,co)][ci]
+  float* dw_packed;            // [(kh,kw,ci_pad)][cout] scratch for the weight gradient (largest conv)
+  int last_batch;
+};
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm kernels (NHWC: channel = fastest index)
+// ------------------------------------------------------------------------------------------------
+// pass 0: sum(x) ; pass 1: sum((x - mean)^2).  grid (chunks, C/64), block 256 = 64 channels x 4 pixel lanes
+__global__ void __launch_bounds__(256) bn_stat_kernel(const float* __restrict__ x, long long npix, int C, const float* __restrict__ mean,
+                                                      double* __restrict__ acc) {
+  __shared__ float red[4][64];
+  const int c = blockIdx.y * 64 + (threadIdx.x & 63), lane4 = threadIdx.x >> 6;
+  const float mu = mean ? mean[c] : 0.f;
+  float s = 0.f;
+  for (long long p = (long long)blockIdx.x * 4 + lane4; p < npix; p += (long long)gridDim.x * 4) {
+    const float v = x[p * C + c] - mu;
+    s += mean ? v * v : v;
+  }
+  red[lane4][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (threadIdx.x < 64) atomicAdd(&acc[c], (double)((red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x])));
+}
+__global__ void bn_mean_kernel(const double* __restrict__ acc, long long npix, int C, float* __restrict__ mean) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) mean[c] = (float)(acc[c] / (double)npix);
+}
+__global__ void bn_finalize_kernel(const double* __restrict__ acc2, long long npix, int C, const float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* __restrict__ rmean, float* __restrict__ rvar, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double var = acc2[c] / (double)npix;                       // biased: used for normalisation
+  invstd[c] = (float)(1.0 / sqrt(var + 1e-5));
+  if (rmean) {
+    const double unbiased = acc2[c] / (double)(npix - 1);
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean[c];
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+  }
+}
+// y = (x - mean) * invstd * gamma + beta (+ res) (ReLU)
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ res,
+                                int relu, long long n4, int C, float* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)((i * 4) % C);
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+  const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+  float4 o = make_float4((v.x - mu.x) * is.x * g.x + b.x, (v.y - mu.y) * is.y * g.y + b.y, (v.z - mu.z) * is.z * g.z + b.z,
+                         (v.w - mu.w) * is.w * g.w + b.w);
+  if (res) { const float4 r = reinterpret_cast<const float4*>(res)[i]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+  if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+  reinterpret_cast<float4*>(y)[i] = o;
+}
+// sums over pixels of dy and dy * xhat, with dy = gout * (act > 0) when act != null.  acc[0..C) = sum dy, acc[C..2C) = sum dy xhat
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ gout, const float* __restrict__ act,
+                                                            const float* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, long long npix, int C,
+                                                            float* __restrict__ acc) {
+  __shared__ float red[2][4][64];
+  const int c = blockIdx.y * 64 + (threadIdx.x & 63), lane4 = threadIdx.x >> 6;
+  const float mu = mean[c], is = invstd[c];
+  float s0 = 0.f, s1 = 0.f;
+  for (long long p = (long long)blockIdx.x * 4 + lane4; p < npix; p += (long long)gridDim.x * 4) {
+    float dy = gout[p * C + c];
+    if (act && !(act[p * C + c] > 0.f)) dy = 0.f;
+    s0 += dy;
+    s1 += dy * (x[p * C + c] - mu) * is;
+  }
+  red[0][lane4][threadIdx.x & 63] = s0;
+  red[1][lane4][threadIdx.x & 63] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int t = threadIdx.x;
+    atomicAdd(&acc[c], (red[0][0][t] + red[0][1][t]) + (red[0][2][t] + red[0][3][t]));
+    atomicAdd(&acc[C + c], (red[1][0][t] + red[1][1][t]) + (red[1][2][t] + red[1][3][t]));
+  }
+}
+// dx = gamma * invstd * (dy - sum_dy/N - xhat * sum_dy_xhat/N);   optionally also writes the masked dy
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ gout, const float* __restrict__ act, const float* __restrict__ x,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ acc, long long npix, int C, float* __restrict__ dx,
+                                    float* __restrict__ masked_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * C) return;
+  const int c = (int)(i % C);
+  float dy = gout[i];
+  if (act && !(act[i] > 0.f)) dy = 0.f;
+  if (masked_out) masked_out[i] = dy;
+  const float is = invstd[c];
+  const float xhat = (x[i] - mean[c]) * is;
+  const float inv_n = 1.f / (float)npix;
+  dx[i] = gamma[c] * is * (dy - acc[c] * inv_n - xhat * acc[C + c] * inv_n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling backward
+// ------------------------------------------------------------------------------------------------
+// feat = mean over the 8x8 map; g wrt the map = dfeat / 64
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, int B, int HW, int C, float* __restrict__ g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * HW * C) return;
+  const int c = (int)(i % C);
+  const long long b = i / ((long long)HW * C);
+  g[i] = dfeat[b * C + c] / (float)HW;
+}
+// 3x3/2 pad 1 max pool backward: the gradient of a window goes to its first maximum (scan order kh, kw)
+__global__ void maxpool_bwd_kernel(const float* __restrict__ in, const float* __restrict__ gout, int B, int H, int W, int C,
+                                   float* __restrict__ gin) {
+  const int HO = H / 2, WO = W / 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * HO * WO * C) return;
+  const int c = (int)(i % C);
+  long long t = i / C;
+  const int ow = (int)(t % WO); t /= WO;
+  const int oh = (int)(t % HO);
+  const long long b = t / HO;
+  float best = -INFINITY;
+  long long arg = -1;
+  for (int dh = 0; dh < 3; ++dh) {
+    const int ih = oh * 2 - 1 + dh;
+    if (ih < 0 || ih >= H) continue;
+    for (int dw = 0; dw < 3; ++dw) {
+      const int iw = ow * 2 - 1 + dw;
+      if (iw < 0 || iw >= W) continue;
+      const long long o = ((b * H + ih) * W + iw) * C + c;
+      const float v = in[o];
+      if (v > best) { best = v; arg = o; }
+    }
+  }
+  if (arg >= 0) atomicAdd(&gin[arg], gout[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// convolution weight gradient:  dW[(tap,ci)][co] = sum_pixels A[pixel][(tap,ci)] * dY[pixel][co]
+// grid (taps * ci_tiles, cout/64, splits); block 256: 16x16 threads, 4 ci x 4 co each; 16 pixels per step
+// ------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const float* in;   // NHWC [B,hin,win,cin]
+  const float* dy;   // NHWC [B,hout,wout,cout]
+  float* dw;         // [(kh,kw,cin)][cout], zero-initialised
+  int B, hin, win, cin, hout, wout, cout, ks, stride, pad, ci_tile;
+};
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Bs[16][64];
+  const int ci_tiles = (a.cin + a.ci_tile - 1) / a.ci_tile;
+  const int tap = blockIdx.x / ci_tiles, ci0 = (blockIdx.x % ci_tiles) * a.ci_tile;
+  const int kh = tap / a.ks, kw = tap % a.ks;
+  const int co0 = blockIdx.y * 64;
+  const long long npix = (long long)a.B * a.hout * a.wout;
+  const long long per = (npix + gridDim.z - 1) / gridDim.z;
+  const long long p0 = (long long)blockIdx.z * per, p1 = min(npix, p0 + per);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // loaders: 16 pixels x 64 values = 256 float4 -> one float4 per thread for each operand
+  const int lp = tid >> 4, l4 = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long pb = p0; pb < p1; pb += 16) {
+    const long long p = pb + lp;
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+    if (p < p1) {
+      const int ow = (int)(p % a.wout);
+      const long long t = p / a.wout;
+      const int oh = (int)(t % a.hout);
+      const long long b = t / a.hout;
+      const int ih = oh * a.stride - a.pad + kh, iw = ow * a.stride - a.pad + kw;
+      if (ih >= 0 && ih < a.hin && iw >= 0 && iw < a.win && ci0 + l4 < a.cin && l4 < a.ci_tile)
+        av = *reinterpret_cast<const float4*>(a.in + ((b * a.hin + ih) * a.win + iw) * a.cin + ci0 + l4);
+      bv = *reinterpret_cast<const float4*>(a.dy + p * a.cout + co0 + l4);
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[lp][l4]) = av;
+    *reinterpret_cast<float4*>(&Bs[lp][l4]) = bv;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {a4.x, a4.y, a4.z, a4.w}, br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + ty * 4 + i;
+    if (ci >= a.cin || ty * 4 + i >= a.ci_tile) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(&a.dw[((size_t)tap * a.cin + ci) * a.cout + co0 + tx * 4 + j], acc[i][j]);
+  }
+}
+// [(kh,kw,ci_pad)][cout] -> OIHW
+__global__ void unpack_w_kernel(const float* __restrict__ packed, int cout, int cin, int cin_pad, int ks, float* __restrict__ w) {
+  const int total = cout * cin * ks * ks;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int kw = i % ks;
+  int t = i / ks;
+  const int kh = t % ks; t /= ks;
+  const int ci = t % cin;
+  const int co = t / cin;
+  w[i] = packed[((size_t)(kh * ks + kw) * cin_pad + ci) * cout + co];
+}
+// OIHW -> [(kh,kw,co)][ci] for the data gradient
+__global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int ks, float* __restrict__ out) {
+  const int total = ks * ks * cout * cin;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = i % cin;
+  int t = i / cin;
+  const int co = t % cout; t /= cout;
+  const int kw = t % ks, kh = t / ks;
+  out[i] = w[(((size_t)co * cin + ci) * ks + kh) * ks + kw];
+}
+
+// ------------------------------------------------------------------------------------------------
+// small GEMM for the IEF backward:  C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C,  row-major with leading dims
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, int lda, int ta, const float* __restrict__ Bm, int ldb, int tb,
+                                                   float* __restrict__ C, int ldc, int M, int N, int K, float beta) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+      const int r = i >> 5, c = i & 31;
+      const int m = m0 + r, k = k0 + c;      // As[r][c] = op(A)[m][k]
+      As[r][c] = (m < M && k < K) ? (ta ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
+      const int kk = k0 + r, n = n0 + c;     // Bs[r][c] = op(B)[kk][n]
+      Bs[r][c] = (kk < K && n < N) ? (tb ? Bm[(size_t)n * ldb + kk] : Bm[(size_t)kk * ldb + n]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[ty * 2][k], a1 = As[ty * 2 + 1][k], b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = m0 + ty * 2 + i, n = n0 + tx * 2 + j;
+      if (m < M && n < N) C[(size_t)m * ldc + n] = acc[i][j] + (beta != 0.f ? beta * C[(size_t)m * ldc + n] : 0.f);
+    }
+}
+// y[b][n] *= (h[b][n] > 0)
+__global__ void relu_mask_kernel(float* __restrict__ y, const float* __restrict__ h, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(h[i] > 0.f)) y[i] = 0.f;
+}
+// out[n] += sum_b y[b][n]
+__global__ void colsum_acc_kernel(const float* __restrict__ y, int B, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += y[(size_t)b * N + n];
+  out[n] += s;
+}
+// dst[b][c] (ld) = a[b][c] + (add ? dst : 0)
+__global__ void add_block_kernel(const float* __restrict__ a, int lda, float* __restrict__ dst, int ldd, int B, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  dst[(size_t)(i / N) * ldd + i % N] += a[(size_t)(i / N) * lda + i % N];
+}
+
+// Adam (torch.optim.Adam defaults, no weight decay / amsgrad) on a flat fp32 bucket
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, float gscale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * gscale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+static int gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C, int ldc, int M, int N, int K, float beta,
+                cudaStream_t st) {
+  gemm_kernel<<<dim3(ceil_div(N, 32), ceil_div(M, 32)), 256, 0, st>>>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// training workspace
+// ------------------------------------------------------------------------------------------------
+static int train_ensure(straps_regressor* r) {
+  if (r->train) return 0;
+  TrainState* t = new TrainState();
+  t->max_batch = r->max_batch;
+  t->last_batch = 0;
+  size_t fl = 0;   // floats
+  auto take = [&](size_t n) { size_t o = fl; fl += (n + 63) & ~(size_t)63; return o; };
+  size_t off_raw[NCONV], off_wd[NCONV], off_mean[NCONV], off_inv[NCONV];
+  size_t max_act = 0, max_w = 0;
+  for (int i = 0; i < NCONV; ++i) {
+    const ConvSpec& c = r->conv[i];
+    const size_t n = (size_t)r->max_batch * c.hout * c.wout * c.cout;
+    off_raw[i] = take(n);
+    off_wd[i] = take((size_t)c.ksize * c.ksize * c.cout * c.cin);
+    off_mean[i] = take(512); off_inv[i] = take(512);
+    max_act = n > max_act ? n : max_act;
+    const size_t nw = (size_t)c.ksize * c.ksize * c.cin_pad * c.cout;
+    max_w = nw > max_w ? nw : max_w;
+  }
+  std::vector<size_t> off_g(r->bufs.size());
+  for (size_t i = 0; i < r->bufs.size(); ++i) {
+    const ActBuf& b = r->bufs[i];
+    off_g[i] = ((int)i == r->buf_xin) ? 0 : take((size_t)r->max_batch * b.h * b.w * b.c);
+  }
+  const size_t off_gmask = take((size_t)r->max_batch * 64 * 64 * 64);
+  const size_t off_draw = take(max_act);
+  const size_t off_dw = take(max_w);
+  const size_t off_fstat = take(1024), off_ones = take(512), off_zeros = take(512);
+  const size_t off_dstat = take(2048);   // 1024 doubles
+  t->pool_bytes = fl * sizeof(float);
+  if (cudaMalloc(&t->pool, t->pool_bytes) != cudaSuccess) {
+    set_error("training workspace: cudaMalloc of %zu bytes failed: %s", t->pool_bytes, cudaGetErrorString(cudaGetLastError()));
+    delete t;
+    return 1;
+  }
+  for (int i = 0; i < NCONV; ++i) {
+    t->raw[i] = t->pool + off_raw[i]; t->w_dgrad[i] = t->pool + off_wd[i];
+    t->mean[i] = t->pool + off_mean[i]; t->invstd[i] = t->pool + off_inv[i];
+  }
+  t->gbuf.resize(r->bufs.size());
+  for (size_t i = 0; i < r->bufs.size(); ++i) t->gbuf[i] = ((int)i == r->buf_xin) ? nullptr : t->pool + off_g[i];
+  t->gmask = t->pool + off_gmask; t->draw = t->pool + off_draw; t->dw_packed = t->pool + off_dw;
+  t->fstat = t->pool + off_fstat; t->ones = t->pool + off_ones; t->zeros = t->pool + off_zeros;
+  t->dstat = reinterpret_cast<double*>(t->pool + off_dstat);
+  std::vector<float> one(512, 1.f);
+  STRAPS_CUDA(cudaMemcpy(t->ones, one.data(), 512 * sizeof(float), cudaMemcpyHostToDevice));
+  STRAPS_CUDA(cudaMemset(t->zeros, 0, 512 * sizeof(float)));
+  r->train = t;
+  return 0;
+}
+
+void train_destroy(straps_regressor* r) {
+  TrainState* t = static_cast<TrainState*>(r->train);
+  if (!t) return;
+  if (t->pool) cudaFree(t->pool);
+  delete t;
+  r->train = nullptr;
+}
+
+static int conv_raw(straps_regressor* r, TrainState* t, int ci, int B, cudaStream_t st) {
+  const ConvSpec& c = r->conv[ci];
+  ConvArgs a;
+  a.in = act_ptr(r, c.in_buf); a.w = c.w_simt; a.scale = t->ones; a.shift = t->zeros; a.res = nullptr; a.out = t->raw[ci];
+  a.B = B; a.hin = c.hin; a.win = c.win; a.cin = c.cin_pad; a.hout = c.hout; a.wout = c.wout; a.cout = c.cout;
+  a.ks = c.ksize; a.stride = c.stride; a.pad = c.pad; a.relu = 0; a.transposed = 0;
+  return launch_conv_simt(a, st);
+}
+
+static int bn_forward(straps_regressor* r, TrainState* t, int ci, int B, const float* res, int relu, float* out, int update_running,
+                      cudaStream_t st) {
+  const ConvSpec& c = r->conv[ci];
+  const long long npix = (long long)B * c.hout * c.wout;
+  const int chunks = (int)std::min<long long>(1024, (npix + 63) / 64);
+  STRAPS_CUDA(cudaMemsetAsync(t->dstat, 0, 1024 * sizeof(double), st));
+  bn_stat_kernel<<<dim3(chunks, c.cout / 64), 256, 0, st>>>(t->raw[ci], npix, c.cout, nullptr, t->dstat);
+  STRAPS_LAUNCH_CHECK();
+  bn_mean_kernel<<<ceil_div(c.cout, 128), 128, 0, st>>>(t->dstat, npix, c.cout, t->mean[ci]);
+  STRAPS_LAUNCH_CHECK();
+  bn_stat_kernel<<<dim3(chunks, c.cout / 64), 256, 0, st>>>(t->raw[ci], npix, c.cout, t->mean[ci], t->dstat + 512);
+  STRAPS_LAUNCH_CHECK();
+  bn_finalize_kernel<<<ceil_div(c.cout, 128), 128, 0, st>>>(t->dstat + 512, npix, c.cout, t->mean[ci], t->invstd[ci],
+                                                           update_running ? c.rmean : nullptr, update_running ? c.rvar : nullptr, 0.1f);
+  STRAPS_LAUNCH_CHECK();
+  const long long n4 = npix * c.cout / 4;
+  bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(t->raw[ci], t->mean[ci], t->invstd[ci], c.gamma, c.beta, res, relu, n4,
+                                                              c.cout, out);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+// gout: gradient wrt the BN output (after the optional ReLU whose output is `act`); writes d(raw conv out) into t->draw,
+// dgamma/dbeta into the caller's tensors, and (optionally) the ReLU-masked gout into masked_out.
+static int bn_backward(straps_regressor* r, TrainState* t, int ci, int B, const float* gout, const float* act, float* masked_out,
+                       float* dgamma, float* dbeta, cudaStream_t st) {
+  const ConvSpec& c = r->conv[ci];
+  const long long npix = (long long)B * c.hout * c.wout;
+  const int chunks = (int)std::min<long long>(1024, (npix + 63) / 64);
+  STRAPS_CUDA(cudaMemsetAsync(t->fstat, 0, 1024 * sizeof(float), st));
+  bn_bwd_reduce_kernel<<<dim3(chunks, c.cout / 64), 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], npix, c.cout, t->fstat);
+  STRAPS_LAUNCH_CHECK();
+  const long long n = npix * c.cout;
+  bn_bwd_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], c.gamma, t->fstat, npix,
+                                                                 c.cout, t->draw, masked_out);
+  STRAPS_LAUNCH_CHECK();
+  STRAPS_CUDA(cudaMemcpyAsync(dbeta, t->fstat, c.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  STRAPS_CUDA(cudaMemcpyAsync(dgamma, t->fstat + c.cout, c.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+static int conv_wgrad(straps_regressor* r, TrainState* t, int ci, int B, float* dw_oihw, cudaStream_t st) {
+  const ConvSpec& c = r->conv[ci];
+  const size_t nw = (size_t)c.ksize * c.ksize * c.cin_pad * c.cout;
+  STRAPS_CUDA(cudaMemsetAsync(t->dw_packed, 0, nw * sizeof(float), st));
+  WgradArgs a;
+  a.in = act_ptr(r, c.in_buf); a.dy = t->draw; a.dw = t->dw_packed;
+  a.B = B; a.hin = c.hin; a.win = c.win; a.cin = c.cin_pad; a.hout = c.hout; a.wout = c.wout; a.cout = c.cout;
+  a.ks = c.ksize; a.stride = c.stride; a.pad = c.pad; a.ci_tile = c.cin_pad < 64 ? c.cin_pad : 64;
+  const int ci_tiles = (c.cin_pad + a.ci_tile - 1) / a.ci_tile;
+  const int base = c.ksize * c.ksize * ci_tiles * (c.cout / 64);
+  const long long npix = (long long)B * c.hout * c.wout;
+  int splits = (int)std::max<long long>(1, std::min<long long>((npix + 255) / 256, (592 + base - 1) / base));
+  wgrad_kernel<<<dim3(c.ksize * c.ksize * ci_tiles, c.cout / 64, splits), 256, 0, st>>>(a);
+  STRAPS_LAUNCH_CHECK();
+  const int total = c.cout * c.cin * c.ksize * c.ksize;
+  unpack_w_kernel<<<ceil_div(total, 256), 256, 0, st>>>(t->dw_packed, c.cout, c.cin, c.cin_pad, c.ksize, dw_oihw);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+// gin[in_buf] (+)= dgrad(t->draw);  add != null -> that tensor is added (identity / other-branch gradient)
+static int conv_dgrad(straps_regressor* r, TrainState* t, int ci, int B, const float* add, float* gin, cudaStream_t st) {
+  const ConvSpec& c = r->conv[ci];
+  ConvArgs a;
+  a.in = t->draw; a.w = t->w_dgrad[ci]; a.scale = t->ones; a.shift = t->zeros; a.res = add; a.out = gin;
+  a.B = B; a.hin = c.hout; a.win = c.wout; a.cin = c.cout; a.hout = c.hin; a.wout = c.win; a.cout = c.cin;
+  a.ks = c.ksize; a.stride = c.stride; a.pad = c.pad; a.relu = 0; a.transposed = 1;
+  return launch_conv_simt(a, st);
+}
+
+}  // namespace straps
+
+using namespace straps;
+
+extern "C" int straps_encoder_train_forward(straps_regressor_t* r, const float* x, int batch, int update_running_stats, float* feat,
+                                            void* stream) {
+  STRAPS_CHECK(r && x && feat, "straps_encoder_train_forward: null argument");
+  STRAPS_CHECK(r->loaded, "straps_encoder_train_forward: weights not loaded");
+  STRAPS_CHECK(batch >= 2 && batch <= r->max_batch, "straps_encoder_train_forward: batch %d outside [2,%d]", batch, r->max_batch);
+  if (train_ensure(r)) return 1;
+  TrainState* t = static_cast<TrainState*>(r->train);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  t->last_batch = batch;
+  r->last_mode = STRAPS_CONV_FP32_SIMT;
+  if (straps::launch_nchw_to_nhwc(r, x, batch, st)) return 1;
+  // stem: conv1 -> bn1 -> relu -> maxpool
+  if (conv_raw(r, t, 0, batch, st)) return 1;
+  if (bn_forward(r, t, 0, batch, nullptr, 1, act_ptr(r, r->buf_stem), update_running_stats, st)) return 1;
+  if (straps::launch_maxpool(r, batch, st)) return 1;
+  int i = 1;
+  while (i < NCONV) {
+    const bool ds = (i + 2 < NCONV) && r->conv[i + 2].ksize == 1;
+    const ConvSpec &c1 = r->conv[i], &c2 = r->conv[i + 1];
+    if (conv_raw(r, t, i, batch, st)) return 1;
+    if (bn_forward(r, t, i, batch, nullptr, 1, act_ptr(r, c1.out_buf), update_running_stats, st)) return 1;
+    if (ds) {
+      if (conv_raw(r, t, i + 2, batch, st)) return 1;
+      if (bn_forward(r, t, i + 2, batch, nullptr, 0, act_ptr(r, r->conv[i + 2].out_buf), update_running_stats, st)) return 1;
+    }
+    if (conv_raw(r, t, i + 1, batch, st)) return 1;
+    if (bn_forward(r, t, i + 1, batch, act_ptr(r, c2.res_buf), 1, act_ptr(r, c2.out_buf), update_running_stats, st)) return 1;
+    i += ds ? 3 : 2;
+  }
+  return straps::launch_avgpool(r, batch, feat, st);
+}
+
+// d_conv_w[20]: OIHW gradients (state_dict order); d_bn[40]: (dgamma, dbeta) per BatchNorm.  All PyTorch-owned, overwritten.
+extern "C" int straps_encoder_backward(straps_regressor_t* r, const float* dfeat, int batch, float* const* d_conv_w, float* const* d_bn,
+                                       void* stream) {
+  STRAPS_CHECK(r && dfeat && d_conv_w && d_bn, "straps_encoder_backward: null argument");
+  TrainState* t = static_cast<TrainState*>(r->train);
+  STRAPS_CHECK(t && t->last_batch == batch, "straps_encoder_backward: no matching straps_encoder_train_forward (batch %d)", batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 1; i < NCONV; ++i) {   // data-gradient weight layout (conv1 needs none)
+    const ConvSpec& c = r->conv[i];
+    const int total = c.ksize * c.ksize * c.cout * c.cin;
+    pack_w_dgrad_kernel<<<ceil_div(total, 256), 256, 0, st>>>(c.w_oihw, c.cout, c.cin, c.ksize, t->w_dgrad[i]);
+    STRAPS_LAUNCH_CHECK();
+  }
+  {
+    const long long n = (long long)batch * 64 * 512;
+    avgpool_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dfeat, batch, 64, 512, t->gbuf[r->buf_final]);
+    STRAPS_LAUNCH_CHECK();
+  }
+  // blocks in reverse
+  int starts[8], nblk = 0;
+  for (int i = 1; i < NCONV;) { starts[nblk++] = i; i += ((i + 2 < NCONV) && r->conv[i + 2].ksize == 1) ? 3 : 2; }
+  for (int bi = nblk - 1; bi >= 0; --bi) {
+    const int i = starts[bi];
+    const bool ds = (i + 2 < NCONV) && r->conv[i + 2].ksize == 1;
+    const ConvSpec &c1 = r->conv[i], &c2 = r->conv[i + 1];
+    const float* g_out = t->gbuf[c2.out_buf];
+    float* g_in = t->gbuf[c1.in_buf];
+    // conv2 branch: relu mask from the block output, bn2 backward (also materialises the masked gradient for the skip path)
+    if (bn_backward(r, t, i + 1, batch, g_out, act_ptr(r, c2.out_buf), t->gmask, d_bn[2 * (i + 1)], d_bn[2 * (i + 1) + 1], st)) return 1;
+    if (conv_wgrad(r, t, i + 1, batch, d_conv_w[i + 1], st)) return 1;
+    if (conv_dgrad(r, t, i + 1, batch, nullptr, t->gbuf[c1.out_buf], st)) return 1;           // gradient wrt a = relu(bn1(.))
+    // conv1 branch
+    if (bn_backward(r, t, i, batch, t->gbuf[c1.out_buf], act_ptr(r, c1.out_buf), nullptr, d_bn[2 * i], d_bn[2 * i + 1], st)) return 1;
+    if (conv_wgrad(r, t, i, batch, d_conv_w[i], st)) return 1;
+    if (!ds) {
+      if (conv_dgrad(r, t, i, batch, t->gmask, g_in, st)) return 1;                             // + identity gradient
+    } else {
+      if (conv_dgrad(r, t, i, batch, nullptr, g_in, st)) return 1;
+      if (bn_backward(r, t, i + 2, batch, t->gmask, nullptr, nullptr, d_bn[2 * (i + 2)], d_bn[2 * (i + 2) + 1], st)) return 1;
+      if (conv_wgrad(r, t, i + 2, batch, d_conv_w[i + 2], st)) return 1;
+      if (conv_dgrad(r, t, i + 2, batch, g_in, g_in, st)) return 1;                             // accumulate the downsample branch
+    }
+  }
+  // stem: maxpool backward -> bn1 (relu mask from the stem activation) -> conv1 weight gradient
+  {
+    const size_t nstem = (size_t)batch * 128 * 128 * 64;
+    STRAPS_CUDA(cudaMemsetAsync(t->gbuf[r->buf_stem], 0, nstem * sizeof(float), st));
+    const long long n = (long long)batch * 64 * 64 * 64;
+    maxpool_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(act_ptr(r, r->buf_stem), t->gbuf[r->buf_pool], batch, 128, 128, 64,
+                                                                  t->gbuf[r->buf_stem]);
+    STRAPS_LAUNCH_CHECK();
+    if (bn_backward(r, t, 0, batch, t->gbuf[r->buf_stem], act_ptr(r, r->buf_stem), nullptr, d_bn[0], d_bn[1], st)) return 1;
+    if (conv_wgrad(r, t, 0, batch, d_conv_w[0], st)) return 1;
+  }
+  return 0;
+}
+
+// saved: dev [iters] x { p_k [B,157] | h1_k [B,512] | h2_k [B,512] } written by straps_ief_forward_train.
+// Outputs (overwritten): d_feat [B,512], d_fc_w[3] in nn.Linear layout, d_fc_b[3].  scratch: dev [B * (157 + 512 + 512 + 669)].
+extern "C" int straps_ief_backward(straps_regressor_t* r, const float* feat, const float* saved, const float* d_params, int batch, int iters,
+                                   float* d_feat, float* const* d_fc_w, float* const* d_fc_b, float* scratch, void* stream) {
+  STRAPS_CHECK(r && feat && saved && d_params && d_feat && d_fc_w && d_fc_b && scratch, "straps_ief_backward: null argument");
+  STRAPS_CHECK(r->loaded, "straps_ief_backward: weights not loaded");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int B = batch, P = STRAPS_IEF_PARAMS, H = IEF_H, IN = IEF_IN, F = STRAPS_FEAT_DIM;
+  float* dp = scratch;                       // [B,157]
+  float* dh2 = dp + (size_t)B * P;           // [B,512]
+  float* dh1 = dh2 + (size_t)B * H;          // [B,512]
+  float* dsx = dh1 + (size_t)B * H;          // [B,669]
+  STRAPS_CUDA(cudaMemcpyAsync(dp, d_params, (size_t)B * P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  STRAPS_CUDA(cudaMemsetAsync(d_feat, 0, (size_t)B * F * sizeof(float), st));
+  STRAPS_CUDA(cudaMemsetAsync(d_fc_w[0], 0, (size_t)H * IN * sizeof(float), st));
+  STRAPS_CUDA(cudaMemsetAsync(d_fc_w[1], 0, (size_t)H * H * sizeof(float), st));
+  STRAPS_CUDA(cudaMemsetAsync(d_fc_w[2], 0, (size_t)P * H * sizeof(float), st));
+  STRAPS_CUDA(cudaMemsetAsync(d_fc_b[0], 0, H * sizeof(float), st));
+  STRAPS_CUDA(cudaMemsetAsync(d_fc_b[1], 0, H * sizeof(float), st));
+  STRAPS_CUDA(cudaMemsetAsync(d_fc_b[2], 0, P * sizeof(float), st));
+  const size_t per_iter = (size_t)B * (P + 2 * H);
+  for (int k = iters - 1; k >= 0; --k) {
+    const float* pk = saved + (size_t)k * per_iter;
+    const float* h1 = pk + (size_t)B * P;
+    const float* h2 = h1 + (size_t)B * H;
+    // fc3: delta = h2 W3^T + b3 ; d(delta) = dp
+    if (gemm(dp, P, 1, h2, H, 0, d_fc_w[2], H, P, H, B, 1.f, st)) return 1;                // dW3 += dp^T h2
+    colsum_acc_kernel<<<ceil_div(P, 128), 128, 0, st>>>(dp, B, P, d_fc_b[2]);
+    STRAPS_LAUNCH_CHECK();
+    if (gemm(dp, P, 0, r->fc_w[2], H, 0, dh2, H, B, H, P, 0.f, st)) return 1;               // dh2 = dp W3
+    relu_mask_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(dh2, h2, (long long)B * H);
+    STRAPS_LAUNCH_CHECK();
+    // fc2
+    if (gemm(dh2, H, 1, h1, H, 0, d_fc_w[1], H, H, H, B, 1.f, st)) return 1;                // dW2 += dh2^T h1
+    colsum_acc_kernel<<<ceil_div(H, 128), 128, 0, st>>>(dh2, B, H, d_fc_b[1]);
+    STRAPS_LAUNCH_CHECK();
+    if (gemm(dh2, H, 0, r->fc_w[1], H, 0, dh1, H, B, H, H, 0.f, st)) return 1;              // dh1 = dh2 W2
+    relu_mask_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(dh1, h1, (long long)B * H);
+    STRAPS_LAUNCH_CHECK();
+    // fc1 on state = [feat | p_k]
+    if (gemm(dh1, H, 1, feat, F, 0, d_fc_w[0], IN, H, F, B, 1.f, st)) return 1;             // dW1[:, :512] += dh1^T feat
+    if (gemm(dh1, H, 1, pk, P, 0, d_fc_w[0] + F, IN, H, P, B, 1.f, st)) return 1;           // dW1[:, 512:] += dh1^T p_k
+    colsum_acc_kernel<<<ceil_div(H, 128), 128, 0, st>>>(dh1, B, H, d_fc_b[0]);
+    STRAPS_LAUNCH_CHECK();
+    if (gemm(dh1, H, 0, r->fc_w[0], IN, 0, dsx, IN, B, IN, H, 0.f, st)) return 1;           // d(state) = dh1 W1
+    add_block_kernel<<<ceil_div(B * F, 256), 256, 0, st>>>(dsx, IN, d_feat, F, B, F);       // d_feat += d(state)[:, :512]
+    STRAPS_LAUNCH_CHECK();
+    add_block_kernel<<<ceil_div(B * P, 256), 256, 0, st>>>(dsx + F, IN, dp, P, B, P);       // dp_k = dp_{k+1} + d(state)[:, 512:]
+    STRAPS_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// torch.optim.Adam semantics (defaults: betas (0.9, 0.999), eps 1e-8, no weight decay) on a flat fp32 bucket.
+// grad_scale multiplies the gradient first (1/world_size after a summing all-reduce).  step >= 1.
+extern "C" int straps_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int step, float lr,
+                                float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  STRAPS_CHECK(params && grads && exp_avg && exp_avg_sq, "straps_adam_step: null argument");
+  STRAPS_CHECK(step >= 1, "straps_adam_step: step must be >= 1");
+  if (n <= 0) return 0;
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                                        eps, bc1, bc2, grad_scale);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}

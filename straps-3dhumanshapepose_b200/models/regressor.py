@@ -8,7 +8,8 @@ import torch.nn as nn
 
 from models.resnet import resnet18
 from models.ief_module import IEFModule
-from straps_b200.engine import RegressorEngine, require_inference
+from straps_b200.engine import RegressorEngine, needs_grad
+from straps_b200._lib import StrapsError
 
 
 class SingleInputRegressor(nn.Module):
@@ -27,6 +28,12 @@ class SingleInputRegressor(nn.Module):
         self.ief_module._engine = self._engine
 
     def forward(self, input):
-        require_inference(self, 'SingleInputRegressor.forward')
-        params = self._engine.forward(input, self.ief_module.iterations)
+        if needs_grad(self):
+            # training step (reference train/...:186): batch-statistics BatchNorm, autograd through the library's backward
+            params = self._engine.forward_train(input, self.ief_module.iterations)
+        else:
+            if self.training:
+                raise StrapsError('SingleInputRegressor: a train-mode forward under torch.no_grad() would use batch statistics in '
+                                  'the reference; call .eval() for inference')
+            params = self._engine.forward(input, self.ief_module.iterations)
         return params[:, :3], params[:, 3:147], params[:, 147:]

@@ -10,7 +10,7 @@ configuration of the reference is in scope.
 """
 import torch.nn as nn
 
-from straps_b200.engine import RegressorEngine, require_inference
+from straps_b200.engine import RegressorEngine, needs_grad
 
 __all__ = ['ResNet', 'BasicBlock', 'resnet18']
 
@@ -66,7 +66,8 @@ class ResNet(nn.Module):
 
     def forward(self, x):
         """[B, C, 256, 256] -> [B, 512] (reference resnet.py:201-216)."""
-        require_inference(self, 'ResNet.forward')
+        if needs_grad(self):
+            return self._engine.forward_train(x, 0, want='feat')
         return self._engine.encoder_forward(x)
 
 

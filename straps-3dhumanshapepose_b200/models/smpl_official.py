@@ -18,6 +18,7 @@ import torch.nn as nn
 
 import config
 from straps_b200 import ops
+from straps_b200.autograd import SmplForward
 from straps_b200._lib import StrapsError
 
 ModelOutput = namedtuple('ModelOutput', ['vertices', 'joints', 'full_pose', 'betas', 'global_orient', 'body_pose',
@@ -122,6 +123,25 @@ class SMPL(nn.Module):
                                                 cpu(self.extra_joints_idxs))
         return self._handles[key]
 
+    def _forward_with_grad(self, betas, body_pose, global_orient, transl, return_verts, return_full_pose, pose2rot):
+        """Training path (train/train_synthetic_otf_rendering.py:196-199): rotation-matrix input, autograd through
+        the library's backward kernels (csrc/smpl_bwd.cu).  The default parameters the reference never optimises
+        (run_train.py:200) do not receive gradients here."""
+        if pose2rot:
+            raise StrapsError('SMPL.forward: gradients through the axis-angle (pose2rot=True) input are not built; the '
+                              'reference trains with rotation matrices (pose2rot=False)')
+        B = max(betas.shape[0], global_orient.shape[0], body_pose.shape[0])
+        rotmats = torch.cat([global_orient.reshape(-1, 1, 3, 3), body_pose.reshape(-1, 23, 3, 3)], dim=1)
+        if betas.shape[0] != B:
+            betas = betas.expand(B, -1)
+        verts, joints = SmplForward.apply(self._handle(betas.device), rotmats, betas)
+        if transl is not None and transl.shape[0] in (1, B) and (transl is not getattr(self, 'transl', None)):
+            verts = verts + transl.unsqueeze(1)
+            joints = joints + transl.unsqueeze(1)
+        full_pose = torch.cat([global_orient, body_pose], dim=1) if return_full_pose else None
+        return ModelOutput(vertices=verts if return_verts else None, global_orient=global_orient, body_pose=body_pose,
+                           joints=joints, betas=betas, full_pose=full_pose)
+
     def forward(self, betas=None, body_pose=None, global_orient=None, transl=None, return_verts=True,
                 return_full_pose=False, pose2rot=True, **kwargs):
         # `get_skin` and friends arrive through **kwargs and are ignored, as in smplx (smpl_official.py:28)
@@ -130,11 +150,10 @@ class SMPL(nn.Module):
         betas = betas if betas is not None else self.betas
         if transl is None and hasattr(self, 'transl'):
             transl = self.transl
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (betas, body_pose, global_orient)):
-            raise StrapsError('SMPL.forward: the backward kernels are not built in this round; wrap the call in '
-                              'torch.no_grad() or detach the inputs')
         if not betas.is_cuda:
             raise StrapsError('SMPL.forward needs CUDA tensors: the B200 path has no CPU fallback')
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (betas, body_pose, global_orient)):
+            return self._forward_with_grad(betas, body_pose, global_orient, transl, return_verts, return_full_pose, pose2rot)
         verts, joints = self._handle(betas.device).forward(global_orient.detach(), body_pose.detach(), betas.detach(),
                                                            transl.detach() if transl is not None else None, pose2rot)
         full_pose = torch.cat([global_orient, body_pose], dim=1) if return_full_pose else None

@@ -21,6 +21,10 @@ SIGNATURES = {
     'straps_smpl_is_sparse4': (ctypes.c_int, [_vp]),
     'straps_smpl_forward': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, ctypes.c_int64, _vp, ctypes.c_int64, _vp,
                                            ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    'straps_smpl_forward_train': (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
+    'straps_smpl_backward': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp]),
+    'straps_rot6d_backward': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, _vp]),
+    'straps_orthographic_project_backward': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     'straps_rot6d_to_rotmat': (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp]),
     'straps_orthographic_project': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     'straps_regressor_create': (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int]),
@@ -32,6 +36,13 @@ SIGNATURES = {
     'straps_encoder_forward': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     'straps_ief_forward': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     'straps_regressor_forward': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    'straps_encoder_train_forward': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    'straps_encoder_backward': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp]),
+    'straps_ief_forward_train': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    'straps_ief_backward': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.POINTER(_vp),
+                                           ctypes.POINTER(_vp), _vp, _vp]),
+    'straps_adam_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
     'straps_encoder_read_activation': (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int, _vp, c_i64_p, _vp]),
 }
 

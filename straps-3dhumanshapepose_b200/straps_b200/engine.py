@@ -19,6 +19,7 @@ class RegressorEngine(object):
         self.conv_mode = conv_mode or ops.DEFAULT_CONV_MODE
         self._handle = None
         self._sig = None
+        self._train_steps = 0      # running statistics are updated through raw pointers: force a repack afterwards
 
     # -- tensors in the order the C ABI expects
     def _tensors(self, device):
@@ -64,7 +65,7 @@ class RegressorEngine(object):
         for t in flat:
             if t.device != device:
                 raise StrapsError('regressor parameters live on %s but the input is on %s' % (t.device, device))
-        sig = tuple((t.data_ptr(), t._version) for t in flat) + (init.cpu().numpy().tobytes(),)
+        sig = tuple((t.data_ptr(), t._version) for t in flat) + (init.cpu().numpy().tobytes(), self._train_steps)
         if sig != self._sig:
             self._handle.load([t.detach() for t in conv_w], [[t.detach() for t in q] for q in bn],
                               [t.detach() for t in fc_w], [t.detach() for t in fc_b], init)
@@ -91,6 +92,57 @@ class RegressorEngine(object):
     def read_activation(self, name, batch):
         return self._handle.read_activation(name, batch)
 
+    # ---- training path: torch.autograd.Function over the library's forward/backward kernels ----
+    def _train_tensors(self, device):
+        conv_w, bn, fc_w, fc_b, init = self._tensors(device)
+        return conv_w, bn, fc_w, fc_b
+
+    def forward_train(self, x, iters, want='params'):
+        """want: 'params' (encoder + IEF), 'feat' (encoder only).  Differentiable wrt all 66 regressor parameters."""
+        h = self._sync(x.device, x.shape[0], self._c_in())
+        conv_w, bn, fc_w, fc_b = self._train_tensors(x.device)
+        flat = list(conv_w) + [q[0] for q in bn] + [q[1] for q in bn] + list(fc_w) + list(fc_b)
+        out = _RegressorTrain.apply(self, h, x, iters, want, *flat)
+        if self.encoder is not None:
+            for m in self.encoder.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.num_batches_tracked += 1
+        self._train_steps += 1
+        return out
+
+
+class _RegressorTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, handle, x, iters, want, *params):
+        feat = handle.encoder_train_forward(x, update_running_stats=True)
+        ctx.handle, ctx.iters, ctx.want = handle, iters, want
+        ctx.conv_shapes = [tuple(p.shape) for p in params[:20]]
+        ctx.bn_channels = [p.shape[0] for p in params[20:40]]
+        if want == 'feat':
+            ctx.save_for_backward(feat)
+            return feat
+        out, saved = handle.ief_forward_train(feat, iters)
+        ctx.save_for_backward(feat, saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h = ctx.handle
+        if ctx.want == 'feat':
+            d_feat = g.contiguous()
+            dfw = [None] * 3
+            dfb = [None] * 3
+        else:
+            feat, saved = ctx.saved_tensors
+            d_feat, dfw, dfb = h.ief_backward(feat, saved, g, ctx.iters)
+        dws, dbn = h.encoder_backward(d_feat, ctx.conv_shapes, ctx.bn_channels)
+        grads = list(dws) + [p[0] for p in dbn] + [p[1] for p in dbn] + list(dfw) + list(dfb)
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def needs_grad(module):
+    return module.training and torch.is_grad_enabled()
+
 
 def _conv_shapes(c_in):
     shapes = {'conv1': (64, c_in, 7)}
@@ -107,7 +159,7 @@ def _conv_shapes(c_in):
 
 
 def require_inference(module, what):
-    """The training path (batch-statistics BN + backward kernels) is not part of this round."""
+    """Stand-alone halves (ResNet / IEFModule used on their own) only run the inference kernels."""
     if module.training and torch.is_grad_enabled():
-        raise StrapsError('%s: train-mode forward/backward kernels are not built in this round; call .eval() '
-                          'or wrap the call in torch.no_grad() (eval-mode BatchNorm statistics are used)' % what)
+        raise StrapsError('%s: the training path is wired through SingleInputRegressor (and ResNet for the encoder alone); '
+                          'call .eval() or wrap the call in torch.no_grad() here' % what)

@@ -62,6 +62,43 @@ def orthographic_project(points3d, cam):
     return out
 
 
+def rot6d_backward(x6, dR):
+    """Gradient of rot6d_to_rotmat: x6 [n,6], dR [n,3,3] -> [n,6]."""
+    _need_cuda(x6, 'x')
+    _need_cuda(dR, 'grad')
+    x6, dR = x6.contiguous(), dR.contiguous()
+    dx = torch.empty_like(x6)
+    with torch.cuda.device(x6.device):
+        check(_lib.lib().straps_rot6d_backward(_p(x6), _p(dR), x6.shape[0], _p(dx), _stream(x6.device)), 'straps_rot6d_backward')
+    return dx
+
+
+def orthographic_project_backward(points3d, cam, g_out):
+    """-> (d_points [B,N,3], d_cam [B,3])."""
+    points3d, g_out = points3d.contiguous(), g_out.contiguous()
+    if cam.stride(1) != 1:
+        cam = cam.contiguous()
+    B, N = points3d.shape[0], points3d.shape[1]
+    dp = torch.empty_like(points3d)
+    dc = torch.empty((B, 3), dtype=torch.float32, device=points3d.device)
+    with torch.cuda.device(points3d.device):
+        check(_lib.lib().straps_orthographic_project_backward(_p(points3d), _p(cam), cam.stride(0), _p(g_out), B, N, _p(dp), _p(dc),
+                                                              _stream(points3d.device)), 'straps_orthographic_project_backward')
+    return dp, dc
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    """torch.optim.Adam update on flat fp32 CUDA buffers (in place)."""
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        _need_cuda(t, 'adam buffer')
+        if not t.is_contiguous():
+            raise StrapsError('adam buffers must be contiguous')
+    with torch.cuda.device(params.device):
+        check(_lib.lib().straps_adam_step(_p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), int(step), float(lr),
+                                          float(betas[0]), float(betas[1]), float(eps), float(grad_scale), _stream(params.device)),
+              'straps_adam_step')
+
+
 class SmplHandle(object):
     """Owns the device-resident packed SMPL constants of one CUDA device."""
 
@@ -125,6 +162,35 @@ class SmplHandle(object):
                                                  _p(tr) if tr is not None else None, B, 1 if pose2rot else 0,
                                                  _p(verts), _p(joints), _stream(betas.device)), 'straps_smpl_forward')
         return verts, joints
+
+
+    def forward_train(self, rotmats, betas):
+        """rotmats [B,24,3,3], betas [B,10] -> (verts, joints, saved) with what straps_smpl_backward needs."""
+        _need_cuda(rotmats, 'rotmats')
+        _need_cuda(betas, 'betas')
+        rotmats, betas = rotmats.contiguous(), betas.contiguous()
+        B, dev = rotmats.shape[0], rotmats.device
+        verts = torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
+        joints = torch.empty((B, 90, 3), dtype=torch.float32, device=dev)
+        vposed = torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
+        A = torch.empty((B, 24, 12), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().straps_smpl_forward_train(self._h, _p(rotmats), _p(betas), B, _p(verts), _p(joints), _p(vposed), _p(A),
+                                                       _stream(dev)), 'straps_smpl_forward_train')
+        return verts, joints, (rotmats, betas, vposed, A)
+
+    def backward(self, saved, g_verts, g_joints):
+        rotmats, betas, vposed, A = saved
+        B, dev = rotmats.shape[0], rotmats.device
+        gv = g_verts.contiguous().clone()          # the kernel accumulates the joint contributions into it
+        gj = g_joints.contiguous()
+        scratch = torch.empty((B * (24 * 12 + 208 + 10),), dtype=torch.float32, device=dev)
+        d_rot = torch.empty_like(rotmats)
+        d_betas = torch.empty_like(betas)
+        with torch.cuda.device(dev):
+            check(_lib.lib().straps_smpl_backward(self._h, _p(rotmats), _p(betas), _p(vposed), _p(A), _p(gj), _p(gv), _p(scratch), B,
+                                                  _p(d_rot), _p(d_betas), _stream(dev)), 'straps_smpl_backward')
+        return d_rot, d_betas
 
 
 class RegressorHandle(object):
@@ -202,6 +268,56 @@ class RegressorHandle(object):
             check(_lib.lib().straps_regressor_forward(self._h, _p(x), B, conv_mode_id(mode), iters, None, _p(params),
                                                       _stream(self.device)), 'straps_regressor_forward')
         return params
+
+    # ---- training path ----
+    def encoder_train_forward(self, x, update_running_stats=True):
+        _need_cuda(x, 'input')
+        x = x.contiguous()
+        B = x.shape[0]
+        if x.shape[1:] != (self.c_in, 256, 256):
+            raise StrapsError('encoder input must be [B,%d,256,256], got %s' % (self.c_in, tuple(x.shape)))
+        feat = torch.empty((B, 512), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_encoder_train_forward(self._h, _p(x), B, 1 if update_running_stats else 0, _p(feat),
+                                                          _stream(self.device)), 'straps_encoder_train_forward')
+        return feat
+
+    def encoder_backward(self, dfeat, conv_shapes, bn_channels):
+        """-> (list of 20 OIHW weight gradients, list of 20 (d_weight, d_bias))."""
+        dfeat = dfeat.contiguous()
+        B = dfeat.shape[0]
+        dws = [torch.empty(s, dtype=torch.float32, device=self.device) for s in conv_shapes]
+        dbn = [(torch.empty(c, dtype=torch.float32, device=self.device), torch.empty(c, dtype=torch.float32, device=self.device))
+               for c in bn_channels]
+        flat_bn = [t for pair in dbn for t in pair]
+        arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_encoder_backward(self._h, _p(dfeat), B, arr(dws), arr(flat_bn), _stream(self.device)),
+                  'straps_encoder_backward')
+        return dws, dbn
+
+    def ief_forward_train(self, feat, iters=3):
+        feat = feat.contiguous()
+        B = feat.shape[0]
+        params = torch.empty((B, 157), dtype=torch.float32, device=feat.device)
+        saved = torch.empty((max(iters, 1) * B * (157 + 1024),), dtype=torch.float32, device=feat.device)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_ief_forward_train(self._h, _p(feat), B, iters, _p(params), _p(saved), _stream(self.device)),
+                  'straps_ief_forward_train')
+        return params, saved
+
+    def ief_backward(self, feat, saved, d_params, iters=3):
+        feat, d_params = feat.contiguous(), d_params.contiguous()
+        B, dev = feat.shape[0], feat.device
+        d_feat = torch.empty((B, 512), dtype=torch.float32, device=dev)
+        dw = [torch.empty(s, dtype=torch.float32, device=dev) for s in ((512, 669), (512, 512), (157, 512))]
+        db = [torch.empty(s, dtype=torch.float32, device=dev) for s in (512, 512, 157)]
+        scratch = torch.empty((B * 1850,), dtype=torch.float32, device=dev)
+        arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_ief_backward(self._h, _p(feat), _p(saved), _p(d_params), B, iters, _p(d_feat), arr(dw), arr(db),
+                                                 _p(scratch), _stream(self.device)), 'straps_ief_backward')
+        return d_feat, dw, db
 
     def read_activation(self, name, batch):
         shapes = {'stem': (64, 128, 128), 'pool': (64, 64, 64)}

@@ -1,0 +1,209 @@
+"""GPU parity of the training path (BASELINE config 3): every backward kernel and the assembled training step against
+the CPU oracle's autograd.  Tolerance 1e-4 relative (max-abs error / max-abs reference, per tensor) as for the forward."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import straps_oracle as O
+from conftest import rel_err, RTOL, WEIGHT_SEED
+from straps_b200 import synthetic_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+GTOL = 2e-4     # gradients: reductions over up to 1e6 pixels in a different order than the CPU oracle
+
+
+def _t(a, grad=False):
+    t = torch.from_numpy(np.asarray(a, dtype=np.float32))
+    return t.requires_grad_(grad)
+
+
+def test_rot6d_and_projection_backward():
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    from utils.cam_utils import orthographic_project_torch
+    rng = np.random.RandomState(0)
+    x = rng.normal(0, 1, (7, 144)).astype(np.float32)
+    g = rng.normal(0, 1, (7 * 24, 3, 3)).astype(np.float32)
+    xo = _t(x, True)
+    (O.rot6d_to_rotmat(xo) * _t(g)).sum().backward()
+    xg = _t(x).to(DEV).requires_grad_(True)
+    (rot6d_to_rotmat(xg) * _t(g).to(DEV)).sum().backward()
+    assert rel_err(xg.grad.cpu().numpy(), xo.grad.numpy()) < 1e-5
+    pts, cam, gg = rng.normal(0, 1, (5, 17, 3)), rng.normal(0, 1, (5, 3)), rng.normal(0, 1, (5, 17, 2))
+    po, co = _t(pts, True), _t(cam, True)
+    (O.orthographic_project(po, co) * _t(gg)).sum().backward()
+    pg, cg = _t(pts).to(DEV).requires_grad_(True), _t(cam).to(DEV).requires_grad_(True)
+    (orthographic_project_torch(pg, cg) * _t(gg).to(DEV)).sum().backward()
+    assert rel_err(pg.grad.cpu().numpy(), po.grad.numpy()) < 1e-6
+    assert rel_err(cg.grad.cpu().numpy(), co.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize('B', [1, 3, 13])
+def test_smpl_backward_against_oracle_autograd(B, assets_root, smpl_oracle):
+    import config
+    from models.smpl_official import SMPL
+    rng = np.random.RandomState(B)
+    betas = rng.normal(0, 1, (B, 10)).astype(np.float32)
+    R = O.rot6d_to_rotmat(_t(rng.normal(0, 1, (B, 144)))).view(B, 24, 3, 3).numpy()
+    gv = rng.normal(0, 1, (B, 6890, 3)).astype(np.float32)
+    gj = rng.normal(0, 1, (B, 90, 3)).astype(np.float32)
+    Ro, bo = _t(R, True), _t(betas, True)
+    v, j = smpl_oracle.forward_rotmats(Ro, bo)
+    ((v * _t(gv)).sum() + (j * _t(gj)).sum()).backward()
+    smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(DEV)
+    Rg, bg = _t(R).to(DEV).requires_grad_(True), _t(betas).to(DEV).requires_grad_(True)
+    out = smpl(body_pose=Rg[:, 1:], global_orient=Rg[:, 0].unsqueeze(1), betas=bg, pose2rot=False)
+    assert rel_err(out.vertices.detach().cpu().numpy(), v.detach().numpy()) < RTOL
+    ((out.vertices * _t(gv).to(DEV)).sum() + (out.joints * _t(gj).to(DEV)).sum()).backward()
+    assert rel_err(Rg.grad.cpu().numpy(), Ro.grad.numpy()) < GTOL
+    assert rel_err(bg.grad.cpu().numpy(), bo.grad.numpy()) < GTOL
+
+
+def _oracle_sd(C, seed, grad=True):
+    sd = O.make_regressor_state(C, seed=seed)
+    out = {}
+    for k, v in sd.items():
+        if v.dtype == torch.float32 and 'running' not in k and 'ief_layers' not in k:
+            out[k] = v.clone().requires_grad_(grad)
+        else:
+            out[k] = v.clone()
+    for i, n in ((0, 'fc1'), (2, 'fc2'), (4, 'fc3')):      # the duplicated IEF keys alias the same tensors
+        out['ief_module.ief_layers.%d.weight' % i] = out['ief_module.%s.weight' % n]
+        out['ief_module.ief_layers.%d.bias' % i] = out['ief_module.%s.bias' % n]
+    return sd, out
+
+
+def _regressor(C, sd, train=True):
+    from models.regressor import SingleInputRegressor
+    reg = SingleInputRegressor(C, 18, 3, conv_mode='fp32_simt')
+    reg.load_state_dict(sd)
+    reg = reg.to(DEV)
+    return reg.train() if train else reg.eval()
+
+
+def test_ief_backward_against_oracle_autograd(assets_root, additional_dir):
+    B = 5
+    sd, sdg = _oracle_sd(17, 3)
+    reg = _regressor(17, sd)
+    rng = np.random.RandomState(1)
+    feat = np.abs(rng.normal(0, 1.5, (B, 512))).astype(np.float32)
+    g = rng.normal(0, 1, (B, 157)).astype(np.float32)
+    init = O.load_initial_params(os.path.join(additional_dir, 'neutral_smpl_mean_params_6dpose.npz'))
+    fo = _t(feat, True)
+    (O.ief_forward(fo, sdg, init, 3) * _t(g)).sum().backward()
+    h = reg._engine._sync(torch.device(DEV), B, 17)
+    fg = _t(feat).to(DEV)
+    p, saved = h.ief_forward_train(fg, 3)
+    d_feat, dw, db = h.ief_backward(fg, saved, _t(g).to(DEV), 3)
+    assert rel_err(d_feat.cpu().numpy(), fo.grad.numpy()) < GTOL
+    for i, n in enumerate(('fc1', 'fc2', 'fc3')):
+        assert rel_err(dw[i].cpu().numpy(), sdg['ief_module.%s.weight' % n].grad.numpy()) < GTOL, n
+        assert rel_err(db[i].cpu().numpy(), sdg['ief_module.%s.bias' % n].grad.numpy()) < GTOL, n
+
+
+@pytest.mark.parametrize('C,B', [(17, 4), (18, 3)])
+def test_encoder_train_forward_backward_against_oracle(C, B, assets_root):
+    sd, sdg = _oracle_sd(C, 7)
+    reg = _regressor(C, sd)
+    x = synthetic_inputs.make_proxy_batch(B, C, seed=13)
+    g = np.random.RandomState(2).normal(0, 1, (B, 512)).astype(np.float32)
+    stats = {}
+    feat_o = O.encoder_forward(_t(x), sdg, train=True, stats_out=stats)
+    (feat_o * _t(g)).sum().backward()
+    feat = reg.image_encoder(_t(x).to(DEV))
+    assert rel_err(feat.detach().cpu().numpy(), feat_o.detach().numpy()) < RTOL
+    (feat * _t(g).to(DEV)).sum().backward()
+    new = reg.state_dict()
+    for k, v in stats.items():                                  # running statistics (momentum 0.1, unbiased variance)
+        assert rel_err(new['image_encoder.' + k].cpu().numpy(), v.numpy()) < 1e-5, k
+    assert int(new['image_encoder.bn1.num_batches_tracked']) == 1
+    worst = 0.0
+    for name, p in reg.image_encoder.named_parameters():
+        ref = sdg['image_encoder.' + name].grad
+        e = rel_err(p.grad.cpu().numpy(), ref.numpy())
+        worst = max(worst, e)
+        assert e < GTOL, (name, e)
+    # eval-mode inference after a training step sees the UPDATED running statistics (packed copy refreshed)
+    reg.eval()
+    sd2 = {k: v.detach().cpu() for k, v in reg.state_dict().items()}
+    with torch.no_grad():
+        f_eval = reg.image_encoder(_t(x).to(DEV))
+        f_eval_o = O.encoder_forward(_t(x), sd2, train=False)
+    assert rel_err(f_eval.cpu().numpy(), f_eval_o.numpy()) < RTOL
+
+
+@pytest.mark.parametrize('B', [4, 16])
+def test_config3_training_step_gradients(B, assets_root, additional_dir, smpl_oracle):
+    """encoder + IEF + rot6d + SMPL + projection + the five-term multi-task loss: every parameter gradient."""
+    import config
+    from models.smpl_official import SMPL
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    from utils.cam_utils import orthographic_project_torch
+    from utils.joints2d_utils import check_joints2d_visibility_torch
+    from losses.multi_task_loss import HomoscedasticUncertaintyWeightedMultiTaskLoss as Loss
+    C = 17
+    W = {'verts': 1.0, 'joints2D': 0.1, 'pose_params': 0.1, 'shape_params': 0.1, 'joints3D': 1.0}    # run_train.py:53-54
+    tasks = ['verts', 'joints2D', 'joints3D', 'pose_params', 'shape_params']
+    sd, sdg = _oracle_sd(C, WEIGHT_SEED)
+    rng = np.random.RandomState(B)
+    x = synthetic_inputs.make_proxy_batch(B, C, seed=21)
+    # targets from the oracle SMPL on seeded random pose / shape
+    t_betas = rng.normal(0, 1, (B, 10)).astype(np.float32)
+    with torch.no_grad():
+        t_R = O.rot6d_to_rotmat(_t(rng.normal(0, 1, (B, 144)))).view(B, 24, 3, 3)
+        t_v, t_j = smpl_oracle.forward_rotmats(t_R, _t(t_betas))
+    t_j2d = rng.uniform(-20, 276, (B, 17, 2)).astype(np.float32)
+    init = O.load_initial_params(os.path.join(additional_dir, 'neutral_smpl_mean_params_6dpose.npz'))
+
+    # ---- oracle
+    o = O.regress_and_pose(_t(x), sdg, init, smpl_oracle, train=True)
+    lv = {k: v.clone().requires_grad_(True) for k, v in O.init_log_vars(W).items()}
+    labels_o = {'verts': t_v, 'joints2D': _t(t_j2d), 'joints3D': t_j[:, O.ALL_JOINTS_TO_H36M_MAP][:, O.H36M_TO_J14],
+                'shape_params': _t(t_betas), 'pose_params_rot_matrices': t_R, 'vis': O.joints2d_visibility(_t(t_j2d))}
+    outs_o = {'verts': o['vertices'], 'joints2D': o['joints2d_coco'], 'joints3D': o['joints_h36mlsp'], 'shape_params': o['shape'],
+              'pose_params_rot_matrices': o['rotmats']}
+    loss_o, _ = O.multi_task_loss(labels_o, outs_o, lv)
+    loss_o.backward()
+
+    # ---- B200 path through the drop-in API, exactly as train/train_synthetic_otf_rendering.py:186-232 calls it
+    reg = _regressor(C, sd)
+    smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(DEV)
+    crit = Loss(tasks, init_loss_weights=W).to(DEV)
+    cam, pose, shape = reg(_t(x).to(DEV))
+    R = rot6d_to_rotmat(pose.contiguous()).view(-1, 24, 3, 3)
+    out = smpl(body_pose=R[:, 1:], global_orient=R[:, 0].unsqueeze(1), betas=shape, pose2rot=False)
+    j_h36mlsp = out.joints[:, config.ALL_JOINTS_TO_H36M_MAP, :][:, config.H36M_TO_J14, :]
+    j2d = orthographic_project_torch(out.joints[:, config.ALL_JOINTS_TO_COCO_MAP, :], cam)
+    tj2d = _t(t_j2d).to(DEV)
+    labels = {'verts': t_v.to(DEV), 'joints2D': tj2d, 'joints3D': labels_o['joints3D'].to(DEV), 'shape_params': _t(t_betas).to(DEV),
+              'pose_params_rot_matrices': t_R.to(DEV), 'vis': check_joints2d_visibility_torch(tj2d, config.REGRESSOR_IMG_WH)}
+    outs = {'verts': out.vertices, 'joints2D': j2d, 'joints3D': j_h36mlsp, 'shape_params': shape, 'pose_params_rot_matrices': R}
+    loss, parts = crit(labels, outs)
+    loss.backward()
+    assert rel_err(loss.detach().cpu().numpy(), loss_o.detach().numpy()) < RTOL
+    errs = {}
+    for name, p in reg.named_parameters():
+        if 'ief_layers' in name:
+            continue
+        errs[name] = rel_err(p.grad.cpu().numpy(), sdg[name].grad.numpy())
+    for t in tasks:
+        errs[t + '_log_var'] = rel_err(getattr(crit, t + '_log_var').grad.cpu().numpy(), lv[t].grad.numpy())
+    bad = {k: v for k, v in errs.items() if not v < GTOL}
+    assert not bad, (bad, max(errs.values()))
+
+
+def test_fused_adam_matches_torch_adam():
+    from straps_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(10007, generator=g)
+    pc = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pc], lr=1e-4)
+    p, m, v = p0.clone().to(DEV), torch.zeros(10007, device=DEV), torch.zeros(10007, device=DEV)
+    for step in range(1, 4):
+        grad = torch.randn(10007, generator=g)
+        pc.grad = grad.clone()
+        opt.step()
+        ops.adam_step(p, (2.0 * grad).to(DEV), m, v, step, lr=1e-4, grad_scale=0.5)
+    assert rel_err(p.cpu().numpy(), pc.detach().numpy()) < 1e-6
