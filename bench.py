@@ -212,21 +212,35 @@ def run_gpu(args):
             ev[i][1].record()
         barrier()
         enc_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-        # ---- e2e: pinned host input -> H2D -> hot path -> D2H of every result, per step ----
+        # ---- e2e: pinned host input -> H2D -> hot path -> D2H of every result, every step, through the public API.
+        # The copy of step i+1 is issued on a second stream so that it overlaps the kernels of step i (two staging buffers),
+        # the way a caller of a device-tensor API pipelines its input; every byte still moves inside the timed region.
         out_host = [torch.empty((B, 3)).pin_memory(), torch.empty((B, 6890, 3)).pin_memory(), torch.empty((B, 90, 3)).pin_memory()]
-        x_stage = torch.empty_like(x_dev)
+        stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        for ev_ in free:
+            ev_.record(cur)
 
-        def e2e_step():
-            x_stage.copy_(x_host, non_blocking=True)
-            res = hot_path(x_stage)
+        def e2e_step(i):
+            sidx = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[sidx])
+                stage[sidx].copy_(x_host, non_blocking=True)
+                ready[sidx].record(copy_stream)
+            cur.wait_event(ready[sidx])
+            res = hot_path(stage[sidx])
+            free[sidx].record(cur)
             for h, d in zip(out_host, res):
                 h.copy_(d, non_blocking=True)
-        for _ in range(3):
-            e2e_step()
+        for i in range(4):
+            e2e_step(i)
         barrier()
         e0.record()
         for i in range(args.steps):
-            e2e_step()
+            e2e_step(i)
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))

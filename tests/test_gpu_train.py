@@ -39,10 +39,10 @@ def _perturbed(sdg, seed=5):
 
 
 def _check_grads(got, ref, noise, what):
-    """got / ref / noise: dict name -> tensor (noise = the oracle's gradients under the 3e-7 perturbation)."""
+    """got / ref: dict name -> tensor; noise: list of dicts = the oracle's gradients under independent 3e-7 perturbations."""
     bad = {}
     for k, r in ref.items():
-        floor = rel_err(noise[k].numpy(), r.numpy()) if noise is not None else 0.0
+        floor = max([rel_err(n[k].numpy(), r.numpy()) for n in noise]) if noise else 0.0
         tol = max(GTOL, NOISE_FACTOR * floor)
         e = rel_err(got[k], r.numpy())
         if not e < tol:
@@ -147,8 +147,11 @@ def test_encoder_train_forward_backward_against_oracle(C, B, assets_root):
     stats = {}
     feat_o = O.encoder_forward(_t(x), sdg, train=True, stats_out=stats)
     (feat_o * _t(g)).sum().backward()
-    sdn = _perturbed(sdg)
-    (O.encoder_forward(_t(x), sdn, train=True) * _t(g)).sum().backward()
+    noise = []
+    for seed in (5, 6, 7):
+        sdn = _perturbed(sdg, seed)
+        (O.encoder_forward(_t(x), sdn, train=True) * _t(g)).sum().backward()
+        noise.append(sdn)
     feat = reg.image_encoder(_t(x).to(DEV))
     assert rel_err(feat.detach().cpu().numpy(), feat_o.detach().numpy()) < RTOL
     (feat * _t(g).to(DEV)).sum().backward()
@@ -158,7 +161,8 @@ def test_encoder_train_forward_backward_against_oracle(C, B, assets_root):
     assert int(new['image_encoder.bn1.num_batches_tracked']) == 1
     names = [n for n, _ in reg.image_encoder.named_parameters()]
     _check_grads({n: p.grad.cpu().numpy() for n, p in reg.image_encoder.named_parameters()},
-                 {n: sdg['image_encoder.' + n].grad for n in names}, {n: sdn['image_encoder.' + n].grad for n in names}, 'encoder')
+                 {n: sdg['image_encoder.' + n].grad for n in names},
+                 [{n: sn['image_encoder.' + n].grad for n in names} for sn in noise], 'encoder')
     # eval-mode inference after a training step sees the UPDATED running statistics (packed copy refreshed)
     reg.eval()
     sd2 = {k: v.detach().cpu() for k, v in reg.state_dict().items()}
@@ -202,14 +206,15 @@ def test_config3_training_step_gradients(B, assets_root, additional_dir, smpl_or
     loss_o.backward()
     # the oracle once more with conv weights perturbed by 3e-7: its own fp32 noise floor (B=4 with these seeds is flip-free
     # and is held to the plain 2e-4 bar)
-    sdn, lvn = None, None
-    if B != 4:
-        sdn = _perturbed(sdg)
+    noise_runs = []
+    for seed in ((5, 6, 7) if B != 4 else ()):
+        sdn = _perturbed(sdg, seed)
         on = O.regress_and_pose(_t(x), sdn, init, smpl_oracle, train=True)
         lvn = {k: v.detach().clone().requires_grad_(True) for k, v in lv.items()}
         outs_n = {'verts': on['vertices'], 'joints2D': on['joints2d_coco'], 'joints3D': on['joints_h36mlsp'], 'shape_params': on['shape'],
                   'pose_params_rot_matrices': on['rotmats']}
         O.multi_task_loss(labels_o, outs_n, lvn)[0].backward()
+        noise_runs.append((sdn, lvn))
 
     # ---- B200 path through the drop-in API, exactly as train/train_synthetic_otf_rendering.py:186-232 calls it
     reg = _regressor(C, sd)
@@ -227,17 +232,17 @@ def test_config3_training_step_gradients(B, assets_root, additional_dir, smpl_or
     loss, parts = crit(labels, outs)
     loss.backward()
     assert rel_err(loss.detach().cpu().numpy(), loss_o.detach().numpy()) < RTOL
-    got, ref, noise = {}, {}, ({} if sdn is not None else None)
+    got, ref, noise = {}, {}, [dict() for _ in noise_runs]
     for name, p in reg.named_parameters():
         if 'ief_layers' in name:
             continue
         got[name], ref[name] = p.grad.cpu().numpy(), sdg[name].grad
-        if noise is not None:
-            noise[name] = sdn[name].grad
+        for d, (sdn, lvn) in zip(noise, noise_runs):
+            d[name] = sdn[name].grad
     for t in tasks:
         got[t + '_log_var'], ref[t + '_log_var'] = getattr(crit, t + '_log_var').grad.cpu().numpy(), lv[t].grad
-        if noise is not None:
-            noise[t + '_log_var'] = lvn[t].grad
+        for d, (sdn, lvn) in zip(noise, noise_runs):
+            d[t + '_log_var'] = lvn[t].grad
     assert len(ref) == 71            # 71 gradient tensors in the bucket
     _check_grads(got, ref, noise, 'config3 B=%d' % B)
 
