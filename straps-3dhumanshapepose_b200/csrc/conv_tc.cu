@@ -194,8 +194,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint64_t a_hi = umma_desc_sw128(sa + (2 * t) * Cfg::A_BYTES);
             const uint64_t a_lo = umma_desc_sw128(sa + (2 * t + 1) * Cfg::A_BYTES);
             const uint32_t d_hi = tmem_base + as * Cfg::ACC_COLS + t * Cfg::TILE_COLS, d_lo = d_hi + BN;
+            // conv1: the third 64-element chunk of a filter row holds taps 5.33..7 = 40 real + 24 zero-weight elements;
+            // its last K=16 step is all padding and is skipped (11 of 12 MMAs per filter row)
+            const int ksteps = (p.conv1 && (kb % 3) == 2) ? 3 : BK_TC / 16;
 #pragma unroll
             for (int k = 0; k < BK_TC / 16; ++k) {
+              if (k >= ksteps) break;
               const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 bytes along K inside the 128-byte swizzle row
               const uint32_t first = (kb | k) != 0;
               if constexpr (2 * BN <= 256) {
@@ -299,6 +303,211 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster compute M = 256 output pixels together.  Each CTA stages its own
+// 128-pixel A tile but only HALF of the weight tile (BN/2 rows); the pair's MMA (issued by the leader) reads the other half
+// from the peer's shared memory, so per SM the weight bytes -- TMA writes and MMA operand reads -- halve.  That is the
+// lever profiles/r01_tc_probe.txt points at for the shared-memory-bandwidth-bound BN = 128 layers.
+//   full[s]   : leader's barrier; TMA of BOTH CTAs completes on it (cta_group::2 loads may signal the peer's barrier)
+//   empty[s]  : one per CTA, released by the leader's tcgen05.commit multicast to both CTAs
+//   tfull[a]  : one per CTA (multicast commit); tempty[a]: leader's, 256 arrivals (epilogue threads of both CTAs)
+// ---------------------------------------------------------------------------------------------------------
+template <int BN>
+struct TcCfg2 {
+  static constexpr int A_BYTES = BM_TC * 128;
+  static constexpr int WH_BYTES = (BN / 2) * 128;      // this CTA's half of one weight plane
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * WH_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 5 ? 5 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int ACC_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(TMEM_COLS <= 512, "BN too large for the CTA-pair kernel");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                const TcConvParams p) {
+  using Cfg = TcCfg2<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_pairs = (p.n_mtiles + 1) / 2;
+  const int n_items = n_pairs * p.n_ntiles;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 256); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer (both CTAs) =================
+      uint32_t it = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
+        const long long pix0 = (long long)(mg * 2 + (int)rank) * BM_TC;
+        const int b0 = (int)(pix0 / p.hw_out);
+        const int oh0 = (int)((pix0 % p.hw_out) / p.wout);
+        for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
+          const int st = it % Cfg::STAGES;
+          mbar_wait(&empty[st], ((it / Cfg::STAGES) & 1) ^ 1);
+          unsigned char* sa = smem + st * Cfg::STAGE_BYTES;
+          const uint32_t full_leader = mapa_u32(smem_u32(&full[st]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full[st], 2 * Cfg::STAGE_BYTES);   // bytes landing in BOTH CTAs
+          int c0, c1, c2;
+          if (p.conv1) {
+            const int kh = kb / 3, j = kb % 3;
+            c0 = kh * (XP_W * XP_C) + j * 64; c1 = 0; c2 = oh0;
+          } else {
+            const int tap = kb / p.cchunks, cc = kb % p.cchunks;
+            const int kh = tap / p.kw_count, kw = tap % p.kw_count;
+            c0 = cc * 64; c1 = kw - p.pad; c2 = oh0 * p.stride + kh - p.pad;
+          }
+          tma_load_4d_2cta(sa, &map_a_hi, full_leader, c0, c1, c2, b0);
+          tma_load_4d_2cta(sa + Cfg::A_BYTES, &map_a_lo, full_leader, c0, c1, c2, b0);
+          const int wrow = nt * BN + (int)rank * (BN / 2);
+          tma_load_2d_2cta(sa + 2 * Cfg::A_BYTES, &map_w_hi, full_leader, kb * BK_TC, wrow);
+          tma_load_2d_2cta(sa + 2 * Cfg::A_BYTES + Cfg::WH_BYTES, &map_w_lo, full_leader, kb * BK_TC, wrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ================= MMA issuer (leader CTA only) =================
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM_TC, BN);
+      uint32_t it = 0, ti = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters, ++ti) {
+        const uint32_t as = ti & 1;
+        mbar_wait(&tempty[as], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_hi = tmem_base + as * Cfg::ACC_COLS, d_lo = d_hi + BN;
+        for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
+          const int st = it % Cfg::STAGES;
+          mbar_wait(&full[st], (it / Cfg::STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
+          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + Cfg::A_BYTES);
+          const uint64_t w_hi = umma_desc_sw128(sa + 2 * Cfg::A_BYTES);
+          const uint64_t w_lo = umma_desc_sw128(sa + 2 * Cfg::A_BYTES + Cfg::WH_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK_TC / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * 32 >> 4);
+            const uint32_t first = (kb | k) != 0;
+            umma_f16_2cta(d_hi, a_hi + ko, w_hi + ko, idesc, first);
+            umma_f16_2cta(d_lo, a_hi + ko, w_lo + ko, idesc, first);
+            umma_f16_2cta(d_lo, a_lo + ko, w_hi + ko, idesc, 1);
+          }
+          umma_commit_2cta(&empty[st]);
+        }
+        umma_commit_2cta(&tfull[as]);
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..5 (both CTAs, each its own 128 rows) =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint32_t ti = 0;
+    for (int item = cluster_id; item < n_items; item += n_clusters, ++ti) {
+      const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
+      const uint32_t as = ti & 1;
+      mbar_wait(&tfull[as], (ti >> 1) & 1);
+      tc_fence_after();
+      const long long m = (long long)(mg * 2 + (int)rank) * BM_TC + row;
+      const bool valid = m < p.m_total;
+      const size_t obase = (size_t)m * p.cout + (size_t)nt * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32], vl[32];
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + as * Cfg::ACC_COLS + c0;
+        tmem_ld_32x32(tacc, v);
+        tmem_ld_32x32(tacc + BN, vl);
+        tmem_ld_wait();
+        float y[32];
+        const float4* sh4 = reinterpret_cast<const float4*>(p.shift + nt * BN + c0);
+        const float4* us4 = reinterpret_cast<const float4*>(p.unscale + nt * BN + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
+          y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
+          y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
+          y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
+          y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+        }
+        if (valid) {
+          if (p.res_hi) {
+            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + obase + c0);
+            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + obase + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 h = __ldg(rh + q), l = __ldg(rl + q);
+              const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                y[q * 8 + e * 2 + 0] += f16lo_to_f(hw[e]) + f16lo_to_f(lw[e]);
+                y[q * 8 + e * 2 + 1] += f16hi_to_f(hw[e]) + f16hi_to_f(lw[e]);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
+          }
+          if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+          } else {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              __half h0, l0, h1, l1;
+              split_f16(y[2 * i], h0, l0);
+              split_f16(y[2 * i + 1], h1, l1);
+              ph[i] = pack_f16(h0, h1);
+              pl[i] = pack_f16(l0, l1);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
+            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
+              ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));     // the leader's accumulator-free barrier
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();          // nobody leaves (or frees TMEM) while the peer may still touch its shared memory / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -455,6 +664,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct TcLayerMaps {
   CUtensorMap a_hi, a_lo, w_hi, w_lo;
+  CUtensorMap w2_hi, w2_lo;     // half-tile (BN/2 rows) boxes for the CTA-pair kernel
 };
 
 struct TcState {
@@ -587,6 +797,9 @@ static int build_maps(straps_regressor* r, int B, std::vector<TcLayerMaps>& out)
       cuuint32_t es[2] = {1, 1};
       if (encode(t, &out[i].w_hi, c.w_hi, 2, dims, str, box, es)) return 1;
       if (encode(t, &out[i].w_lo, c.w_lo, 2, dims, str, box, es)) return 1;
+      cuuint32_t box2[2] = {64, (cuuint32_t)((c.cout == 64 ? 64 : 128) / 2)};
+      if (encode(t, &out[i].w2_hi, c.w_hi, 2, dims, str, box2, es)) return 1;
+      if (encode(t, &out[i].w2_lo, c.w_lo, 2, dims, str, box2, es)) return 1;
     }
     if (i == 0) {
       // conv1: (flattened kw,c run | ow | oh | b) over the padded input, strides bake in the stride-2 sampling
@@ -625,6 +838,21 @@ static int launch_conv_tc(const TcLayerMaps& m, const TcConvParams& p, int num_s
   return 0;
 }
 
+template <int BN>
+static int launch_conv_tc2(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg2<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    STRAPS_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int items = ((p.n_mtiles + 1) / 2) * p.n_ntiles;
+  const int clusters = items < num_sms / 2 ? items : num_sms / 2;
+  conv_tc2_kernel<BN><<<2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w2_hi, m.w2_lo, p);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
 static int run_conv_tc(straps_regressor* r, const std::vector<TcLayerMaps>& maps, int ci, int B, cudaStream_t st) {
   TcState* t = static_cast<TcState*>(r->tc);
   const ConvSpec& c = r->conv[ci];
@@ -657,6 +885,13 @@ static int run_conv_tc(straps_regressor* r, const std::vector<TcLayerMaps>& maps
   }
   int mt;
   { int bn2; tile_cfg(c, &bn2, &mt); }
+  {
+    // STRAPS_TC_PAIR: "128" = CTA pairs for the Cout >= 128 layers, "all" = every layer, unset/"0" = single-CTA kernels
+    const char* e = getenv("STRAPS_TC_PAIR");
+    const bool pair = e && ((e[0] == 'a') || (e[0] == '1' && c.cout >= 128));
+    if (pair && mt == 1 && bn <= 128)
+      return bn == 64 ? launch_conv_tc2<64>(maps[ci], p, t->num_sms, st) : launch_conv_tc2<128>(maps[ci], p, t->num_sms, st);
+  }
   if (bn == 64) return mt == 2 ? launch_conv_tc<64, 2>(maps[ci], p, t->num_sms, st) : launch_conv_tc<64, 1>(maps[ci], p, t->num_sms, st);
   if (bn == 256) return launch_conv_tc<256, 1>(maps[ci], p, t->num_sms, st);
   if (mt == 2) return launch_conv_tc<128, 2>(maps[ci], p, t->num_sms, st);

@@ -3,74 +3,66 @@
 // Replaces IEFModule.forward (reference models/ief_module.py:48-64):
 //     p0 = init.repeat(B,1);  3 x { state = [feat | p]; p += fc3(relu(fc2(relu(fc1(state))))) }
 //
-// B200 mapping: the fc stack is tiny (1.37 MFLOP/body/iteration, 2.74 MB of fp32 weights) and strictly
-// layer-serial, so it is latency bound.  One thread-block CLUSTER of 8 CTAs owns 8 bodies: CTA `c` owns
-// neurons [64c, 64c+64) of fc1/fc2 and outputs [20c, 20c+20) of fc3, streams only its slice of the
-// (pre-transposed, L2-resident) weights with fully coalesced loads, and all-gathers the activations into
-// every peer's shared memory through DSMEM stores + a cluster barrier.  The iteration-invariant half of
-// fc1 (feat . W1[:, :512]^T + b1) is computed once and kept in shared memory.  Shared-weight layout in HBM:
-//     w1t [669][512], w2t [512][512], w3t [512][160]  (input-major = transposed nn.Linear weights, fc3 padded).
+// B200 mapping: the fc stack is tiny (1.37 MFLOP/body/iteration, 2.74 MB of fp32 weights) and strictly layer-serial, so it
+// is latency bound (ncu, profiles/r01_small_kernels_ncu.txt: the first version streamed its weight slices from L2 in
+// every iteration and spent its time in long-scoreboard stalls).  One thread-block CLUSTER of 16 CTAs (non-portable
+// size, one cluster per GPC) owns 8 bodies: CTA c owns neurons [32c, 32c+32) of fc1/fc2 and outputs [10c, 10c+10) of fc3.
+// Its weight slices (fc1 params-half 20 KB, fc2 64 KB, fc3 32 KB) are bulk-copied (TMA) into shared memory ONCE and stay
+// resident for all iterations; the iteration-invariant half of fc1 (feat . W1[:, :512]^T + b1) is computed once from a slice
+// that is streamed through the fc2 region before fc2's weights land there.  Activations are all-gathered into every peer's
+// shared memory with DSMEM stores + a cluster barrier (3 per iteration).
+// HBM layout (packed by ief_pack): per-CTA contiguous slices  w1f [16][512][32], w1p [16][157][32], w2 [16][512][32],
+// w3 [16][512][16] (10 real outputs + 6 zero columns), input-major so that a warp reads 32 consecutive floats.
 #include "regressor.h"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
 namespace straps {
 
-constexpr int CL = 8;          // CTAs per cluster
+constexpr int CL = 16;         // CTAs per cluster
 constexpr int TBI = 8;         // bodies per cluster
-constexpr int NLOC = IEF_H / CL;            // 64 neurons per CTA
-constexpr int OLOC = IEF_OUT_PAD / CL;      // 20 outputs per CTA
+constexpr int NLOC = IEF_H / CL;            // 32 neurons per CTA
+constexpr int OLOC = IEF_OUT_PAD / CL;      // 10 outputs per CTA
+constexpr int OPAD = 16;                    // padded fc3 slice width
 constexpr int IEF_THREADS = 256;
-constexpr int KQ = IEF_THREADS / NLOC;      // 4 K-slices per neuron
+constexpr int KQ = IEF_THREADS / NLOC;      // 8 K-slices per neuron (one per warp)
+
+struct IefWeights {       // owned by ief.cu
+  float *w1f, *w1p, *w2, *w3;
+};
 
 struct IefSmem {
   float xs[IEF_IN][TBI];        // state, k-major / body-minor:  rows 0..511 feat, 512..668 params
   float h1[IEF_H][TBI];
   float h2[IEF_H][TBI];
   float base1[NLOC][TBI];       // b1 + W1[:, :512] . feat for this CTA's neurons
-  float red[KQ][NLOC][TBI];     // K-slice partial sums (also used as [8][32][TBI] by fc3)
+  float red[KQ][NLOC][TBI];     // K-slice partial sums (fc3 views it as [16][16][TBI])
+  float w1p[STRAPS_IEF_PARAMS][NLOC];
+  float w2[IEF_H][NLOC];        // holds the w1f slice first
+  float w3[IEF_H][OPAD];
+  uint64_t bar[3];
 };
 
-// acc[b] += sum_{k in [k0,k1)} wt[k*ld + col] * x[k][b].  The weight stream comes from L2 (~700 cycles away): 16
-// independent loads are issued before the first FMA so one thread keeps 16 requests in flight.
-__device__ __forceinline__ void dot_slice(const float* __restrict__ wt, int ld, int col, int k0, int k1,
-                                          const float (*x)[TBI], float (&acc)[TBI]) {
-  constexpr int U = 16;
-  int k = k0;
-  for (; k + U <= k1; k += U) {
-    float w[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) w[u] = __ldg(wt + (size_t)(k + u) * ld + col);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float4 x0 = *reinterpret_cast<const float4*>(&x[k + u][0]);
-      const float4 x1 = *reinterpret_cast<const float4*>(&x[k + u][4]);
-      acc[0] = fmaf(w[u], x0.x, acc[0]); acc[1] = fmaf(w[u], x0.y, acc[1]);
-      acc[2] = fmaf(w[u], x0.z, acc[2]); acc[3] = fmaf(w[u], x0.w, acc[3]);
-      acc[4] = fmaf(w[u], x1.x, acc[4]); acc[5] = fmaf(w[u], x1.y, acc[5]);
-      acc[6] = fmaf(w[u], x1.z, acc[6]); acc[7] = fmaf(w[u], x1.w, acc[7]);
-    }
-  }
-  if (k < k1) {
-    float w[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) w[u] = (k + u < k1) ? __ldg(wt + (size_t)(k + u) * ld + col) : 0.f;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (k + u < k1) {
-#pragma unroll
-        for (int b = 0; b < TBI; ++b) acc[b] = fmaf(w[u], x[k + u][b], acc[b]);
-      }
-    }
+// acc[b] += sum_{k in [k0,k1)} w[k][col] * x[k][b]   (w in shared memory, row stride LD)
+template <int LD>
+__device__ __forceinline__ void dot_smem(const float* __restrict__ w, int col, int k0, int k1, const float (*x)[TBI], float (&acc)[TBI]) {
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    const float wv = w[k * LD + col];
+    const float4 x0 = *reinterpret_cast<const float4*>(&x[k][0]);
+    const float4 x1 = *reinterpret_cast<const float4*>(&x[k][4]);
+    acc[0] = fmaf(wv, x0.x, acc[0]); acc[1] = fmaf(wv, x0.y, acc[1]);
+    acc[2] = fmaf(wv, x0.z, acc[2]); acc[3] = fmaf(wv, x0.w, acc[3]);
+    acc[4] = fmaf(wv, x1.x, acc[4]); acc[5] = fmaf(wv, x1.y, acc[5]);
+    acc[6] = fmaf(wv, x1.z, acc[6]); acc[7] = fmaf(wv, x1.w, acc[7]);
   }
 }
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(IEF_THREADS)
-ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const float* __restrict__ w1t,
-           const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
-           const float* __restrict__ w3t, const float* __restrict__ b3, int B, int iters,
-           float* __restrict__ params, float* __restrict__ saved) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(IEF_THREADS)
+ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const IefWeights wts, const float* __restrict__ b1,
+           const float* __restrict__ b2, const float* __restrict__ b3, int B, int iters, float* __restrict__ params,
+           float* __restrict__ saved) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   IefSmem& s = *reinterpret_cast<IefSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -78,6 +70,19 @@ ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const
   const int tid = threadIdx.x;
   const int nl = tid % NLOC, kq = tid / NLOC;
 
+  if (tid == 0) {
+    mbar_init(&s.bar[0], 1); mbar_init(&s.bar[1], 1); mbar_init(&s.bar[2], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&s.bar[0], IEF_H * NLOC * 4);
+    bulk_g2s(&s.w2[0][0], wts.w1f + (size_t)rank * IEF_H * NLOC, IEF_H * NLOC * 4, &s.bar[0]);
+    mbar_arrive_expect_tx(&s.bar[1], STRAPS_IEF_PARAMS * NLOC * 4);
+    bulk_g2s(&s.w1p[0][0], wts.w1p + (size_t)rank * STRAPS_IEF_PARAMS * NLOC, STRAPS_IEF_PARAMS * NLOC * 4, &s.bar[1]);
+    mbar_arrive_expect_tx(&s.bar[2], IEF_H * OPAD * 4);
+    bulk_g2s(&s.w3[0][0], wts.w3 + (size_t)rank * IEF_H * OPAD, IEF_H * OPAD * 4, &s.bar[2]);
+  }
   // state: feat (transposed into k-major) + initial estimate
   for (int i = tid; i < STRAPS_FEAT_DIM * TBI; i += IEF_THREADS) {
     const int b = i / STRAPS_FEAT_DIM, k = i % STRAPS_FEAT_DIM;
@@ -89,24 +94,35 @@ ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const
   }
   __syncthreads();
 
-  // iteration-invariant half of fc1
+  // iteration-invariant half of fc1 (its weight slice sits in the fc2 region for now)
+  mbar_wait(&s.bar[0], 0);
   {
     float acc[TBI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const int kspan = STRAPS_FEAT_DIM / KQ;
-    dot_slice(w1t, IEF_H, rank * NLOC + nl, kq * kspan, (kq + 1) * kspan, s.xs, acc);
+    constexpr int span = STRAPS_FEAT_DIM / KQ;
+    dot_smem<NLOC>(&s.w2[0][0], nl, kq * span, (kq + 1) * span, s.xs, acc);
 #pragma unroll
     for (int b = 0; b < TBI; ++b) s.red[kq][nl][b] = acc[b];
     __syncthreads();
-    for (int i = tid; i < NLOC * TBI; i += IEF_THREADS) {
-      const int n = i / TBI, b = i % TBI;
-      s.base1[n][b] = b1[rank * NLOC + n] + ((s.red[0][n][b] + s.red[1][n][b]) + (s.red[2][n][b] + s.red[3][n][b]));
+    {
+      const int n = tid / TBI, b = tid % TBI;    // 256 threads = 32 neurons x 8 bodies
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < KQ; ++q) t += s.red[q][n][b];
+      s.base1[n][b] = b1[rank * NLOC + n] + t;
     }
     __syncthreads();
   }
+  if (tid == 0) {   // the fc2 region is free now: stream fc2's slice into it
+    fence_proxy_async();
+    mbar_arrive_expect_tx(&s.bar[0], IEF_H * NLOC * 4);
+    bulk_g2s(&s.w2[0][0], wts.w2 + (size_t)rank * IEF_H * NLOC, IEF_H * NLOC * 4, &s.bar[0]);
+  }
+  mbar_wait(&s.bar[1], 0);
 
-  // training: saved = [iters] x { p_k [B,157] | h1_k [B,512] | h2_k [B,512] }; CTA `rank` writes body b0+rank
+  // training: saved = [iters] x { p_k [B,157] | h1_k [B,512] | h2_k [B,512] }; CTA `rank` < 8 writes body b0+rank
   const size_t per_iter = (size_t)B * (STRAPS_IEF_PARAMS + 2 * IEF_H);
-  const bool do_save = saved != nullptr && (b0 + rank < B);
+  const bool owner = rank < TBI && (b0 + rank < B);
+  const bool do_save = saved != nullptr && owner;
   for (int it = 0; it < iters; ++it) {
     if (do_save)
       for (int k = tid; k < STRAPS_IEF_PARAMS; k += IEF_THREADS)
@@ -114,16 +130,18 @@ ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const
     // ---- fc1 (params half) + ReLU -> all-gather h1
     {
       float acc[TBI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const int kspan = (STRAPS_IEF_PARAMS + KQ - 1) / KQ;   // 40
-      const int k0 = STRAPS_FEAT_DIM + kq * kspan;
-      const int k1 = min(IEF_IN, k0 + kspan);
-      dot_slice(w1t, IEF_H, rank * NLOC + nl, k0, k1, s.xs, acc);
+      constexpr int span = (STRAPS_IEF_PARAMS + KQ - 1) / KQ;   // 20
+      const int k0 = kq * span, k1 = min(STRAPS_IEF_PARAMS, k0 + span);
+      dot_smem<NLOC>(&s.w1p[0][0], nl, k0, k1, s.xs + STRAPS_FEAT_DIM, acc);
 #pragma unroll
       for (int b = 0; b < TBI; ++b) s.red[kq][nl][b] = acc[b];
       __syncthreads();
-      for (int i = tid; i < NLOC * TBI; i += IEF_THREADS) {
-        const int n = i / TBI, b = i % TBI;
-        const float v = fmaxf(s.base1[n][b] + ((s.red[0][n][b] + s.red[1][n][b]) + (s.red[2][n][b] + s.red[3][n][b])), 0.f);
+      {
+        const int n = tid / TBI, b = tid % TBI;
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) t += s.red[q][n][b];
+        const float v = fmaxf(s.base1[n][b] + t, 0.f);
         float* local = &s.h1[rank * NLOC + n][b];
 #pragma unroll
         for (int peer = 0; peer < CL; ++peer) *cluster.map_shared_rank(local, peer) = v;
@@ -134,16 +152,20 @@ ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const
           saved[it * per_iter + (size_t)B * STRAPS_IEF_PARAMS + (size_t)(b0 + rank) * IEF_H + k] = s.h1[k][rank];
     }
     // ---- fc2 + ReLU -> all-gather h2
+    if (it == 0) mbar_wait(&s.bar[0], 1);
     {
       float acc[TBI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const int kspan = IEF_H / KQ;
-      dot_slice(w2t, IEF_H, rank * NLOC + nl, kq * kspan, (kq + 1) * kspan, s.h1, acc);
+      constexpr int span = IEF_H / KQ;
+      dot_smem<NLOC>(&s.w2[0][0], nl, kq * span, (kq + 1) * span, s.h1, acc);
 #pragma unroll
       for (int b = 0; b < TBI; ++b) s.red[kq][nl][b] = acc[b];
       __syncthreads();
-      for (int i = tid; i < NLOC * TBI; i += IEF_THREADS) {
-        const int n = i / TBI, b = i % TBI;
-        const float v = fmaxf(b2[rank * NLOC + n] + ((s.red[0][n][b] + s.red[1][n][b]) + (s.red[2][n][b] + s.red[3][n][b])), 0.f);
+      {
+        const int n = tid / TBI, b = tid % TBI;
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) t += s.red[q][n][b];
+        const float v = fmaxf(b2[rank * NLOC + n] + t, 0.f);
         float* local = &s.h2[rank * NLOC + n][b];
 #pragma unroll
         for (int peer = 0; peer < CL; ++peer) *cluster.map_shared_rank(local, peer) = v;
@@ -153,27 +175,24 @@ ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const
         for (int k = tid; k < IEF_H; k += IEF_THREADS)
           saved[it * per_iter + (size_t)B * (STRAPS_IEF_PARAMS + IEF_H) + (size_t)(b0 + rank) * IEF_H + k] = s.h2[k][rank];
     }
-    // ---- fc3: 20 outputs per CTA, 8 K-slices of 64;  p += delta -> all-gather the params rows of xs
+    // ---- fc3: 10 (padded 16) outputs per CTA, 16 K-slices of 32;  p += delta -> all-gather the params rows of xs
+    if (it == 0) mbar_wait(&s.bar[2], 0);
     {
-      float (*red3)[32][TBI] = reinterpret_cast<float (*)[32][TBI]>(&s.red[0][0][0]);   // [8][32][TBI] = 8 KB
-      const int ol = tid % 32, ks = tid / 32;
-      if (ol < OLOC) {
-        float acc[TBI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        dot_slice(w3t, IEF_OUT_PAD, rank * OLOC + ol, ks * 64, (ks + 1) * 64, s.h2, acc);
+      float (*red3)[OPAD][TBI] = reinterpret_cast<float (*)[OPAD][TBI]>(&s.red[0][0][0]);   // [16][16][TBI]
+      const int ol = tid % OPAD, ks = tid / OPAD;
+      float acc[TBI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      dot_smem<OPAD>(&s.w3[0][0], ol, ks * 32, (ks + 1) * 32, s.h2, acc);
 #pragma unroll
-        for (int b = 0; b < TBI; ++b) red3[ks][ol][b] = acc[b];
-      }
+      for (int b = 0; b < TBI; ++b) red3[ks][ol][b] = acc[b];
       __syncthreads();
-      for (int i = tid; i < OLOC * TBI; i += IEF_THREADS) {
-        const int o = i / TBI, b = i % TBI, og = rank * OLOC + o;
+      if (tid < OLOC * TBI) {
+        const int o = tid / TBI, b = tid % TBI, og = rank * OLOC + o;
         if (og < STRAPS_IEF_PARAMS) {
-          float d = b3[og];
           float t = 0.f;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) t += red3[q][o][b];
-          d += t;
+          for (int q = 0; q < 16; ++q) t += red3[q][o][b];
           float* local = &s.xs[STRAPS_FEAT_DIM + og][b];
-          const float v = *local + d;
+          const float v = *local + (b3[og] + t);
 #pragma unroll
           for (int peer = 0; peer < CL; ++peer) *cluster.map_shared_rank(local, peer) = v;
         }
@@ -181,34 +200,65 @@ ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const
       cluster.sync();
     }
   }
-  // every CTA holds the full parameter block; CTA `rank` writes body b0+rank
-  if (b0 + rank < B)
+  // every CTA holds the full parameter block; CTA `rank` < 8 writes body b0+rank
+  if (owner)
     for (int k = tid; k < STRAPS_IEF_PARAMS; k += IEF_THREADS)
       params[(size_t)(b0 + rank) * STRAPS_IEF_PARAMS + k] = s.xs[STRAPS_FEAT_DIM + k][rank];
 }
 
-// dst[k*ld_dst + n] = src[n*K + k]   (nn.Linear weight [N,K] -> input-major, zero padded to ld_dst columns)
-__global__ void transpose_linear_kernel(const float* __restrict__ src, int N, int K, float* __restrict__ dst, int ld_dst) {
-  __shared__ float tile[32][33];
-  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int n = n0 + r, k = k0 + threadIdx.x;
-    tile[r][threadIdx.x] = (n < N && k < K) ? src[(size_t)n * K + k] : 0.f;
+// dst[c][k][j] = (j < nloc && c*nloc+j < N) ? W[(c*nloc + j)*K + k0 + k] : 0      (W = nn.Linear weight [N,K])
+__global__ void pack_slices_kernel(const float* __restrict__ W, int N, int K, int k0, int kcount, int nloc, int npad,
+                                   float* __restrict__ dst) {
+  const int total = CL * kcount * npad;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = i % npad;
+  int t = i / npad;
+  const int k = t % kcount, c = t / kcount;
+  const int n = c * nloc + j;
+  dst[i] = (j < nloc && n < N) ? W[(size_t)n * K + k0 + k] : 0.f;
+}
+
+static IefWeights* ief_state(const straps_regressor* r) { return static_cast<IefWeights*>(r->ief); }
+
+int ief_create(straps_regressor* r) {
+  IefWeights* w = new IefWeights();
+  r->ief = w;
+  const size_t n = (size_t)CL * (IEF_H * NLOC + STRAPS_IEF_PARAMS * NLOC + IEF_H * NLOC + IEF_H * OPAD);
+  float* p = nullptr;
+  if (cudaMalloc(&p, n * sizeof(float)) != cudaSuccess) {
+    set_error("ief_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    w->w1f = nullptr;
+    return 1;
   }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int k = k0 + r, n = n0 + threadIdx.x;
-    if (k < K && n < ld_dst) dst[(size_t)k * ld_dst + n] = tile[threadIdx.x][r];
-  }
+  w->w1f = p; p += (size_t)CL * IEF_H * NLOC;
+  w->w1p = p; p += (size_t)CL * STRAPS_IEF_PARAMS * NLOC;
+  w->w2 = p; p += (size_t)CL * IEF_H * NLOC;
+  w->w3 = p;
+  return 0;
+}
+
+void ief_destroy(straps_regressor* r) {
+  IefWeights* w = ief_state(r);
+  if (!w) return;
+  if (w->w1f) cudaFree(w->w1f);
+  delete w;
+  r->ief = nullptr;
 }
 
 int ief_pack(straps_regressor* r, const float* const* fc_w, const float* const* fc_b, const float* init, cudaStream_t st) {
-  dim3 blk(32, 8);
-  transpose_linear_kernel<<<dim3(ceil_div(IEF_IN, 32), ceil_div(IEF_H, 32)), blk, 0, st>>>(fc_w[0], IEF_H, IEF_IN, r->w1t, IEF_H);
+  IefWeights* w = ief_state(r);
+  auto pack = [&](const float* W, int N, int K, int k0, int kcount, int nloc, int npad, float* dst) {
+    const int total = CL * kcount * npad;
+    pack_slices_kernel<<<ceil_div(total, 256), 256, 0, st>>>(W, N, K, k0, kcount, nloc, npad, dst);
+  };
+  pack(fc_w[0], IEF_H, IEF_IN, 0, STRAPS_FEAT_DIM, NLOC, NLOC, w->w1f);
   STRAPS_LAUNCH_CHECK();
-  transpose_linear_kernel<<<dim3(ceil_div(IEF_H, 32), ceil_div(IEF_H, 32)), blk, 0, st>>>(fc_w[1], IEF_H, IEF_H, r->w2t, IEF_H);
+  pack(fc_w[0], IEF_H, IEF_IN, STRAPS_FEAT_DIM, STRAPS_IEF_PARAMS, NLOC, NLOC, w->w1p);
   STRAPS_LAUNCH_CHECK();
-  transpose_linear_kernel<<<dim3(ceil_div(IEF_H, 32), ceil_div(IEF_OUT_PAD, 32)), blk, 0, st>>>(fc_w[2], STRAPS_IEF_PARAMS, IEF_H, r->w3t, IEF_OUT_PAD);
+  pack(fc_w[1], IEF_H, IEF_H, 0, IEF_H, NLOC, NLOC, w->w2);
+  STRAPS_LAUNCH_CHECK();
+  pack(fc_w[2], STRAPS_IEF_PARAMS, IEF_H, 0, IEF_H, OLOC, OPAD, w->w3);
   STRAPS_LAUNCH_CHECK();
   STRAPS_CUDA(cudaMemcpyAsync(r->b1, fc_b[0], IEF_H * sizeof(float), cudaMemcpyDeviceToDevice, st));
   STRAPS_CUDA(cudaMemcpyAsync(r->b2, fc_b[1], IEF_H * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -221,12 +271,30 @@ int ief_pack(straps_regressor* r, const float* const* fc_w, const float* const* 
 int ief_launch_train(const straps_regressor* r, const float* feat, int batch, int iters, float* params, float* saved, cudaStream_t st) {
   const int nclusters = ceil_div(batch, TBI);
   const size_t smem = sizeof(IefSmem);
-  STRAPS_CUDA(cudaFuncSetAttribute(ief_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ief_kernel<<<nclusters * CL, IEF_THREADS, smem, st>>>(feat, r->init, r->w1t, r->b1, r->w2t, r->b2, r->w3t, r->b3,
-                                                       batch, iters, params, saved);
-  STRAPS_LAUNCH_CHECK();
+  static bool attr_set = false;
+  if (!attr_set) {
+    STRAPS_CUDA(cudaFuncSetAttribute(ief_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    STRAPS_CUDA(cudaFuncSetAttribute(ief_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(nclusters * CL);
+  cfg.blockDim = dim3(IEF_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const IefWeights wts = *ief_state(r);
+  const float* b1 = r->b1; const float* b2 = r->b2; const float* b3 = r->b3; const float* init = r->init;
+  STRAPS_CUDA(cudaLaunchKernelEx(&cfg, ief_kernel, feat, init, wts, b1, b2, b3, batch, iters, params, saved));
+  count_launch();
   return 0;
 }
+
 int ief_launch(const straps_regressor* r, const float* feat, int batch, int iters, float* params, cudaStream_t st) {
   return ief_launch_train(r, feat, batch, iters, params, nullptr, st);
 }

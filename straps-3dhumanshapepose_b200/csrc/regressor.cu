@@ -238,7 +238,7 @@ extern "C" int straps_regressor_create(straps_regressor_t** out, int c_in, int m
   straps_regressor* r = new straps_regressor();
   r->c_in = c_in; r->c_in_pad = (c_in + 7) / 8 * 8; r->max_batch = max_batch;
   r->ws = nullptr; r->ws_bytes = 0; r->wpool = nullptr; r->tc = nullptr; r->loaded = 0; r->last_mode = -1;
-  r->train = nullptr;
+  r->train = nullptr; r->ief = nullptr;
   // activation buffers (NHWC)
   r->buf_xin = add_buf(r, "", IMG, IMG, 32);        // sized for the widest packed-input layout either mode uses
   r->buf_stem = add_buf(r, "stem", 128, 128, 64);
@@ -304,7 +304,7 @@ extern "C" int straps_regressor_create(straps_regressor_t** out, int c_in, int m
   r->b3 = p; p += IEF_OUT_PAD;
   r->init = p; p += 256;
   r->feat_scratch = p; p += (size_t)max_batch * STRAPS_FEAT_DIM;
-  if (tc_create(r)) { straps_regressor_destroy(r); return 1; }
+  if (tc_create(r) || ief_create(r)) { straps_regressor_destroy(r); return 1; }
   *out = r;
   return 0;
 }
@@ -313,6 +313,7 @@ extern "C" void straps_regressor_destroy(straps_regressor_t* r) {
   if (!r) return;
   tc_destroy(r);
   train_destroy(r);
+  ief_destroy(r);
   if (r->ws) cudaFree(r->ws);
   if (r->wpool) cudaFree(r->wpool);
   delete r;

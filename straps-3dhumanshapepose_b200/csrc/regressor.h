@@ -70,6 +70,7 @@ struct straps_regressor {
   float *w1t, *w2t, *w3t, *b1, *b2, *b3, *init, *feat_scratch;
   // tensor-core path state (opaque, owned by conv_tc.cu)
   void* tc;
+  void* ief;               // IEF weight slices (ief.cu)
   void* train;             // training workspace (train.cu), allocated on first use
   const float* fc_w[3];    // PyTorch-owned IEF weights / biases of the last load (nn.Linear layout)
   const float* fc_b[3];
@@ -79,6 +80,8 @@ struct straps_regressor {
 
 namespace straps {
 int ief_launch(const straps_regressor* r, const float* feat, int batch, int iters, float* params, cudaStream_t st);
+int ief_create(straps_regressor* r);
+void ief_destroy(straps_regressor* r);
 int ief_pack(straps_regressor* r, const float* const* fc_w, const float* const* fc_b, const float* init, cudaStream_t st);
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_nchw_to_nhwc(straps_regressor* r, const float* x, int B, cudaStream_t st);
