@@ -100,6 +100,15 @@ int straps_rot6d_to_rotmat(const float* x6, int64_t n, float* R, void* stream);
 int straps_orthographic_project(const float* points, const float* cam, int64_t cam_stride,
                                 int batch, int npoints, float* out, void* stream);
 
+/* ---- proxy-representation synthesis on the device (the step right before the path) ----
+ * utils/label_conversions.py:90-127 -- joints2d dev [B,J,2] (pixels) -> heatmaps dev [B,J,img_wh,img_wh]: zero, with the
+ * (2*half_size)^2 truncated Gaussian `table` (dev, row-major, computed by the caller exactly as the reference does)
+ * pasted at the truncated-to-int joint position with the reference's clipping rules. */
+int straps_joints2d_to_heatmaps(const float* joints2d, int batch, int num_joints, int img_wh, int half_size,
+                                const float* table, float* heatmaps, void* stream);
+/* utils/label_conversions.py:48-55 -- out[i] = (labels[i] != 0) ? 1 : 0  (fp32 in, fp32 out). */
+int straps_multiclass_to_binary(const float* labels, int64_t n, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Regressor -- replaces models/regressor.py:43-47 = ResNet.forward (models/resnet.py:201-216) +
  * IEFModule.forward (models/ief_module.py:48-64).

@@ -100,6 +100,12 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, 'loss_b3.npz'), total=total.detach().numpy(),
                         vis=labels['vis'].numpy(), log_vars=np.array([p.item() for p in crit.parameters()]),
                         **{'part_' + k: v.detach().numpy() for k, v in parts.items()})
+    # ---- N1: joint heat-maps (utils/label_conversions.py:90-127) incl. border / out-of-range joints ----------
+    rng = np.random.RandomState(31)
+    j = rng.uniform(-12, 270, (4, 17, 2)).astype(np.float32)
+    j[0, 0] = [0., 0.]; j[0, 1] = [255., 255.]; j[0, 2] = [-7.9, 262.9]; j[0, 3] = [-8., 100.]; j[0, 4] = [263., 5.]
+    j[0, 5] = [247.5, 8.2]; j[0, 6] = [254.99, 0.5]
+    np.savez_compressed(os.path.join(GOLDEN, 'heatmaps_b4.npz'), joints2d=j, heatmaps=ref.heatmaps(torch.from_numpy(j), 256).numpy())
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

@@ -284,3 +284,33 @@ def regress_and_pose(x, sd, init_params, smpl, train=False, iters=3, stats_out=N
     return {'feat': feat, 'params': p, 'cam': cam, 'pose6d': pose6d, 'shape': shape, 'rotmats': R,
             'vertices': verts, 'joints': joints, 'joints2d_coco': orthographic_project(j_coco, cam),
             'joints_h36mlsp': j_h36m[:, H36M_TO_J14, :]}
+
+
+# ----------------------------------------------------------------------------------------------
+# proxy-representation synthesis (utils/label_conversions.py:48-55, 90-127)
+# ----------------------------------------------------------------------------------------------
+def binary_labels(multiclass_labels):
+    out = torch.zeros_like(multiclass_labels)
+    out[multiclass_labels != 0] = 1
+    return out
+
+
+def joints2d_to_heatmaps(joints2d, img_wh, std=4):
+    """numpy-style restatement of convert_2Djoints_to_gaussian_heatmaps_torch (integer window arithmetic spelled out)."""
+    jr = joints2d.int()
+    B, N = jr.shape[0], jr.shape[1]
+    hm = torch.zeros((B, N, img_wh, img_wh), dtype=torch.float32)
+    size = 2 * std
+    x, y = torch.meshgrid(torch.linspace(-size, size, 2 * size), torch.linspace(-size, size, 2 * size), indexing='ij')
+    d = torch.sqrt(x * x + y * y)
+    g = torch.exp(-(d ** 2 / (2.0 * std ** 2)))
+    for i in range(B):
+        for j in range(N):
+            cx, cy = int(jr[i, j, 0]), int(jr[i, j, 1])
+            if cx > -size and cy > -size and cx < img_wh - 1 + size and cy < img_wh - 1 + size:
+                hsx, hex_ = max(0, cx - size), min(img_wh - 1, cx + size)
+                hsy, hey = max(0, cy - size), min(img_wh - 1, cy + size)
+                gsx, gex = max(0, size - cx), min(2 * size, 2 * size - (size + cx - (img_wh - 1)))
+                gsy, gey = max(0, size - cy), min(2 * size, 2 * size - (size + cy - (img_wh - 1)))
+                hm[i, j, hsy:hey, hsx:hex_] = g[gsy:gey, gsx:gex]
+    return hm

@@ -60,6 +60,7 @@ struct TcConvParams {
   const __half* res_hi;     // residual (identity) planes or null
   const __half* res_lo;
   int relu;
+  int debug;        // timing experiments only (STRAPS_TC_DEBUG): 1 = no TMA traffic, 2 = no MMAs, 3 = no epilogue stores
 };
 
 // BN = output-channel tile, MT = number of 128-pixel M-tiles that share one weight tile per K-block.
@@ -145,6 +146,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int st = it % Cfg::STAGES;
           mbar_wait(&empty[st], ((it / Cfg::STAGES) & 1) ^ 1);
           unsigned char* sa = smem + st * Cfg::STAGE_BYTES;
+          if (p.debug == 1) { mbar_arrive(&full[st]); continue; }      // timing experiment: stale operands, no TMA traffic
           mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
           int c0, c1, dh;
           if (p.conv1) {
@@ -191,6 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint64_t w_lo = umma_desc_sw128(sa + MT * 2 * Cfg::A_BYTES + Cfg::W_BYTES);
 #pragma unroll
           for (int t = 0; t < MT; ++t) {
+            if (p.debug == 2) break;                                     // timing experiment: TMA only
             const uint64_t a_hi = umma_desc_sw128(sa + (2 * t) * Cfg::A_BYTES);
             const uint64_t a_lo = umma_desc_sw128(sa + (2 * t + 1) * Cfg::A_BYTES);
             const uint32_t d_hi = tmem_base + as * Cfg::ACC_COLS + t * Cfg::TILE_COLS, d_lo = d_hi + BN;
@@ -250,7 +253,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
             y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
           }
-          if (valid) {
+          if (valid && p.debug != 3) {
             if (p.res_hi) {
               const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + obase + c0);
               const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + obase + c0);
@@ -873,6 +876,7 @@ static int run_conv_tc(straps_regressor* r, const std::vector<TcLayerMaps>& maps
   p.shift = c.shift;
   p.unscale = t->unscale + t->ch_off[ci];
   p.relu = c.relu;
+  { const char* d = getenv("STRAPS_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
   if (out_is_f32(r, ci)) {
     p.out_f32 = act_ptr(r, c.out_buf);
   } else {

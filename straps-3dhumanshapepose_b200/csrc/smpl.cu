@@ -550,3 +550,51 @@ extern "C" int straps_orthographic_project(const float* points, const float* cam
   STRAPS_LAUNCH_CHECK();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// on-device proxy-representation synthesis, the step right before the hot path
+// (reference utils/label_conversions.py:48-55 and 90-127, called at train/...:178-182).
+// ------------------------------------------------------------------------------------------------
+namespace straps {
+// one block per (b, joint): paste the (2*size)^2 truncated Gaussian window with the reference's clipping rules
+__global__ void heatmaps_paste_kernel(const float* __restrict__ joints2d, const float* __restrict__ table, int size, int img_wh,
+                                      float* __restrict__ out) {
+  const int bj = blockIdx.x;
+  const float fx = joints2d[bj * 2 + 0], fy = joints2d[bj * 2 + 1];
+  const int cx = (int)fx, cy = (int)fy;                       // Tensor.int(): truncation toward zero
+  if (!(cx > -size && cy > -size && cx < img_wh - 1 + size && cy < img_wh - 1 + size)) return;
+  const int hsx = max(0, cx - size), hex = min(img_wh - 1, cx + size);
+  const int hsy = max(0, cy - size), hey = min(img_wh - 1, cy + size);
+  const int gsx = max(0, size - cx), gex = min(2 * size, 2 * size - (size + cx - (img_wh - 1)));
+  const int gsy = max(0, size - cy), gey = min(2 * size, 2 * size - (size + cy - (img_wh - 1)));
+  const int w = min(hex - hsx, gex - gsx), h = min(hey - hsy, gey - gsy);
+  float* o = out + (size_t)bj * img_wh * img_wh;
+  for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+    const int yy = i / w, xx = i % w;
+    o[(size_t)(hsy + yy) * img_wh + hsx + xx] = table[(gsy + yy) * 2 * size + gsx + xx];
+  }
+}
+__global__ void binary_labels_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (in[i] != 0.f) ? 1.f : 0.f;
+}
+}  // namespace straps
+
+extern "C" int straps_joints2d_to_heatmaps(const float* joints2d, int batch, int num_joints, int img_wh, int half_size,
+                                           const float* table, float* heatmaps, void* stream) {
+  STRAPS_CHECK(joints2d && table && heatmaps, "straps_joints2d_to_heatmaps: null argument");
+  STRAPS_CHECK(batch > 0 && num_joints > 0 && img_wh > 0 && half_size > 0 && half_size <= 64, "straps_joints2d_to_heatmaps: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  STRAPS_CUDA(cudaMemsetAsync(heatmaps, 0, (size_t)batch * num_joints * img_wh * img_wh * sizeof(float), st));
+  heatmaps_paste_kernel<<<batch * num_joints, 256, 0, st>>>(joints2d, table, half_size, img_wh, heatmaps);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int straps_multiclass_to_binary(const float* labels, int64_t n, float* out, void* stream) {
+  STRAPS_CHECK(labels && out, "straps_multiclass_to_binary: null argument");
+  if (n <= 0) return 0;
+  binary_labels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(labels, n, out);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}

@@ -27,6 +27,8 @@ SIGNATURES = {
     'straps_orthographic_project_backward': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     'straps_rot6d_to_rotmat': (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp]),
     'straps_orthographic_project': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    'straps_joints2d_to_heatmaps': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    'straps_multiclass_to_binary': (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp]),
     'straps_regressor_create': (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int]),
     'straps_regressor_destroy': (None, [_vp]),
     'straps_regressor_workspace_bytes': (ctypes.c_size_t, [_vp]),

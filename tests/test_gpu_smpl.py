@@ -149,3 +149,20 @@ def test_rot6d_and_projection(smpl_oracle):
     out = orthographic_project_torch(torch.from_numpy(pts).to(DEV), cam_view)
     ref = O.orthographic_project(torch.from_numpy(pts), torch.from_numpy(params)[:, :3])
     assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-6
+
+
+def test_proxy_representation_synthesis_bit_exact(assets_root):
+    """SURVEY.md 8f row N1 (utils/label_conversions.py:48-55, 90-127): bit-exact against the reference fixture and the oracle."""
+    from utils.label_conversions import convert_2Djoints_to_gaussian_heatmaps_torch, convert_multiclass_to_binary_labels_torch
+    g = golden('heatmaps_b4.npz')
+    hm = convert_2Djoints_to_gaussian_heatmaps_torch(torch.from_numpy(g['joints2d']).to(DEV), 256)
+    assert hm.shape == (4, 17, 256, 256) and np.array_equal(hm.cpu().numpy(), g['heatmaps'])
+    rng = np.random.RandomState(3)
+    j = torch.from_numpy(rng.uniform(-20, 280, (64, 17, 2)).astype(np.float32))
+    assert torch.equal(convert_2Djoints_to_gaussian_heatmaps_torch(j.to(DEV), 256).cpu(), O.joints2d_to_heatmaps(j, 256))
+    seg = torch.from_numpy(rng.randint(0, 7, (5, 256, 256)).astype(np.float32))
+    b = convert_multiclass_to_binary_labels_torch(seg.to(DEV))
+    assert torch.equal(b.cpu(), O.binary_labels(seg)) and b.dtype == torch.float32
+    # the reference assembles the regressor input like this (train/...:178-182)
+    x = torch.cat([b.unsqueeze(1)[:4], hm], dim=1)
+    assert x.shape == (4, 18, 256, 256)
