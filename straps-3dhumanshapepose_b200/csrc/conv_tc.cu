@@ -78,8 +78,7 @@ struct TcCfg {
   static constexpr int W_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = MT * 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int STAGES = (220 * 1024 / STAGE_BYTES) > 4 ? 4 : (220 * 1024 / STAGE_BYTES);
-  static constexpr int EPI_BYTES = 5120;                // per epilogue warp: 32 rows x (2 x 80 B) or 32 x 144 B, padded rows
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4 * EPI_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static constexpr int TILE_COLS = 2 * BN;              // per M-tile: [hi.hi | lo terms]
   static constexpr int ACC_COLS = MT * TILE_COLS;       // per accumulator stage
   static constexpr int TSTAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
@@ -224,7 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else {
     // ================= epilogue warps 2..5 =================
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
-    unsigned char* stg = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + quad * Cfg::EPI_BYTES;   // this warp's staging tile
+    const int row = quad * 32 + lane;
     uint32_t ti = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
       const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
@@ -233,6 +232,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       tc_fence_after();
 #pragma unroll 1
       for (int t = 0; t < MT; ++t) {
+        const long long m = (long long)(mg * MT + t) * BM_TC + row;
+        const bool valid = m < p.m_total;
+        const size_t obase = (size_t)m * p.cout + (size_t)nt * BN;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32], vl[32];
@@ -251,31 +253,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
             y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
           }
-          // Staged epilogue I/O.  A lane owns one output row, so direct 16-byte accesses would touch 32 different lines per
-          // instruction (in-situ experiment profiles/r01_conv_experiments.txt: the stores alone cost 18-29 % of a layer).
-          // Each warp bounces its 32-row x 32-column chunk through a private padded shared-memory tile so that every
-          // global instruction moves whole 64-byte (fp16 planes) / 128-byte (fp32) row segments: 8 resp. 4 rows per instruction.
-          const long long m0w = (long long)(mg * MT + t) * BM_TC + quad * 32;     // first row of this warp
-          if (p.debug != 3) {
-            const int r8 = lane >> 2, q4 = lane & 3;      // fp16 planes: 8 rows x 4 16-byte pieces per instruction
+          if (valid && p.debug != 3) {
             if (p.res_hi) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const long long mr = m0w + 8 * i + r8;
-                uint4 h = make_uint4(0, 0, 0, 0), l = h;
-                if (mr < p.m_total) {
-                  const size_t o = (size_t)mr * p.cout + (size_t)nt * BN + c0 + q4 * 8;
-                  h = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o));
-                  l = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o));
-                }
-                *reinterpret_cast<uint4*>(stg + (8 * i + r8) * 80 + q4 * 16) = h;
-                *reinterpret_cast<uint4*>(stg + 2560 + (8 * i + r8) * 80 + q4 * 16) = l;
-              }
-              __syncwarp();
+              const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + obase + c0);
+              const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + obase + c0);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint4 h = *reinterpret_cast<const uint4*>(stg + lane * 80 + q * 16);
-                const uint4 l = *reinterpret_cast<const uint4*>(stg + 2560 + lane * 80 + q * 16);
+                const uint4 h = __ldg(rh + q), l = __ldg(rl + q);
                 const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -283,52 +267,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                   y[q * 8 + e * 2 + 1] += f16hi_to_f(hw[e]) + f16hi_to_f(lw[e]);
                 }
               }
-              __syncwarp();
             }
             if (p.relu) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
             }
             if (p.out_f32) {
+              float4* o = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(stg + lane * 144 + q * 16) = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
-              __syncwarp();
-              const int r4 = lane >> 3, q8 = lane & 7;    // fp32: 4 rows x 8 pieces per instruction
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const long long mr = m0w + 4 * i + r4;
-                if (mr < p.m_total)
-                  *reinterpret_cast<float4*>(p.out_f32 + (size_t)mr * p.cout + (size_t)nt * BN + c0 + q8 * 4) =
-                      *reinterpret_cast<const float4*>(stg + (4 * i + r4) * 144 + q8 * 16);
-              }
-              __syncwarp();
+              for (int q = 0; q < 8; ++q) o[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
             } else {
+              uint32_t ph[16], pl[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                __half h0, l0, h1, l1;
+                split_f16(y[2 * i], h0, l0);
+                split_f16(y[2 * i + 1], h1, l1);
+                ph[i] = pack_f16(h0, h1);
+                pl[i] = pack_f16(l0, l1);
+              }
+              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
+              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                uint32_t ph[4], pl[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  __half h0, l0, h1, l1;
-                  split_f16(y[q * 8 + 2 * e], h0, l0);
-                  split_f16(y[q * 8 + 2 * e + 1], h1, l1);
-                  ph[e] = pack_f16(h0, h1);
-                  pl[e] = pack_f16(l0, l1);
-                }
-                *reinterpret_cast<uint4*>(stg + lane * 80 + q * 16) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                *reinterpret_cast<uint4*>(stg + 2560 + lane * 80 + q * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
+                ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
               }
-              __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const long long mr = m0w + 8 * i + r8;
-                if (mr < p.m_total) {
-                  const size_t o = (size_t)mr * p.cout + (size_t)nt * BN + c0 + q4 * 8;
-                  *reinterpret_cast<uint4*>(p.out_hi + o) = *reinterpret_cast<const uint4*>(stg + (8 * i + r8) * 80 + q4 * 16);
-                  *reinterpret_cast<uint4*>(p.out_lo + o) = *reinterpret_cast<const uint4*>(stg + 2560 + (8 * i + r8) * 80 + q4 * 16);
-                }
-              }
-              __syncwarp();
             }
           }
         }
