@@ -245,6 +245,34 @@ def run_gpu(args):
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
+        # ---- extra: the proxy representation is synthesised ON THE DEVICE from what a caller really has on
+        # the host -- part-segmentation labels and 2-D joints (reference train/...:178-182) -- so only 16.8 MB + 8.7 KB cross PCIe.
+        ms_kp = None
+        if C in (17, 18):
+            from utils.label_conversions import convert_2Djoints_to_gaussian_heatmaps_torch, convert_multiclass_to_binary_labels_torch
+            rng = np.random.RandomState(7 + rank)
+            seg_host = torch.from_numpy((x_host[:, 0].numpy() * rng.randint(1, 7, (B, 1, 1))).astype(np.float32)).pin_memory()
+            j2d_host = torch.from_numpy(rng.uniform(8, 247, (B, C - 1, 2)).astype(np.float32)).pin_memory()
+            seg_dev, j2d_dev = torch.empty_like(seg_host, device=dev), torch.empty_like(j2d_host, device=dev)
+
+            def kp_step():
+                seg_dev.copy_(seg_host, non_blocking=True)
+                j2d_dev.copy_(j2d_host, non_blocking=True)
+                x_in = torch.cat([convert_multiclass_to_binary_labels_torch(seg_dev).unsqueeze(1),
+                                  convert_2Djoints_to_gaussian_heatmaps_torch(j2d_dev, 256)], dim=1)
+                res = hot_path(x_in)
+                for h, d in zip(out_host, res):
+                    h.copy_(d, non_blocking=True)
+            for _ in range(3):
+                kp_step()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                kp_step()
+            e1.record()
+            barrier()
+            ms_kp = max_over_ranks(e0.elapsed_time(e1))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -271,6 +299,10 @@ def run_gpu(args):
                        'l2': 'inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush'},
             'e2e': {'value': e2e, 'unit': 'bodies/s', 'h2d_bytes_per_step': int(x_host.numel() * 4),
                     'd2h_bytes_per_step': int(sum(h.numel() for h in out_host) * 4)},
+            'e2e_from_keypoints': None if ms_kp is None else {
+                'value': world * B / (ms_kp / args.steps * 1e-3), 'unit': 'bodies/s',
+                'h2d_bytes_per_step': int(B * 256 * 256 * 4 + B * (C - 1) * 2 * 4), 'd2h_bytes_per_step': int(sum(h.numel() for h in out_host) * 4),
+                'note': 'input synthesised on device from host segmentation labels + 2-D joints (utils/label_conversions drop-in, SURVEY 8f N1)'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': achieved_tf / peak_tf, 'traffic': None, 'peak_kind': peak_kind + ' (sustained cuBLAS bf16)',

@@ -224,75 +224,91 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ================= epilogue warps 2..5 =================
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
+    constexpr int NCHUNK = MT * (BN / 32);       // 32-column chunks per work item
     uint32_t ti = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
       const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
       const uint32_t as = ti % Cfg::TSTAGES;
+      // The residual (identity) tile does not depend on the accumulator: its loads are software-pipelined one chunk ahead, and
+      // the first chunk is requested BEFORE waiting for the MMAs -- the in-situ experiment (profiles/r01_conv_experiments.txt)
+      // showed the un-pipelined residual latency exposed on the short-K layers.
+      uint4 rh[4], rl[4];
+      auto fetch_residual = [&](int chunk) {
+        const int t = chunk / (BN / 32), c0 = (chunk % (BN / 32)) * 32;
+        const long long m = (long long)(mg * MT + t) * BM_TC + row;
+        if (p.res_hi && chunk < NCHUNK && m < p.m_total && p.debug != 3) {
+          const size_t o = (size_t)m * p.cout + (size_t)nt * BN + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o) + q);
+            rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o) + q);
+          }
+        }
+      };
+      fetch_residual(0);
       mbar_wait(&tfull[as], (ti / Cfg::TSTAGES) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int t = 0; t < MT; ++t) {
+      for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+        const int t = chunk / (BN / 32), c0 = (chunk % (BN / 32)) * 32;
         const long long m = (long long)(mg * MT + t) * BM_TC + row;
         const bool valid = m < p.m_total;
         const size_t obase = (size_t)m * p.cout + (size_t)nt * BN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32], vl[32];
-          const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + as * Cfg::ACC_COLS + t * Cfg::TILE_COLS + c0;
-          tmem_ld_32x32(tacc, v);
-          tmem_ld_32x32(tacc + BN, vl);
-          tmem_ld_wait();
-          float y[32];
-          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + nt * BN + c0);
-          const float4* us4 = reinterpret_cast<const float4*>(p.unscale + nt * BN + c0);
+        uint32_t v[32], vl[32];
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + as * Cfg::ACC_COLS + t * Cfg::TILE_COLS + c0;
+        tmem_ld_32x32(tacc, v);
+        tmem_ld_32x32(tacc + BN, vl);
+        tmem_ld_wait();
+        float y[32];
+        const float4* sh4 = reinterpret_cast<const float4*>(p.shift + nt * BN + c0);
+        const float4* us4 = reinterpret_cast<const float4*>(p.unscale + nt * BN + c0);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
-            y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
-            y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
-            y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
-            y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
+          y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
+          y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
+          y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
+          y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+        }
+        if (valid && p.debug != 3) {
+          if (p.res_hi) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t hw[4] = {rh[q].x, rh[q].y, rh[q].z, rh[q].w}, lw[4] = {rl[q].x, rl[q].y, rl[q].z, rl[q].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                y[q * 8 + e * 2 + 0] += f16lo_to_f(hw[e]) + f16lo_to_f(lw[e]);
+                y[q * 8 + e * 2 + 1] += f16hi_to_f(hw[e]) + f16hi_to_f(lw[e]);
+              }
+            }
           }
-          if (valid && p.debug != 3) {
-            if (p.res_hi) {
-              const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + obase + c0);
-              const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + obase + c0);
+        }
+        fetch_residual(chunk + 1);        // in flight while this chunk is split and stored
+        if (valid && p.debug != 3) {
+          if (p.relu) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 h = __ldg(rh + q), l = __ldg(rl + q);
-                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+            for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
+          }
+          if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  y[q * 8 + e * 2 + 0] += f16lo_to_f(hw[e]) + f16lo_to_f(lw[e]);
-                  y[q * 8 + e * 2 + 1] += f16hi_to_f(hw[e]) + f16hi_to_f(lw[e]);
-                }
-              }
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+          } else {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              __half h0, l0, h1, l1;
+              split_f16(y[2 * i], h0, l0);
+              split_f16(y[2 * i + 1], h1, l1);
+              ph[i] = pack_f16(h0, h1);
+              pl[i] = pack_f16(l0, l1);
             }
-            if (p.relu) {
+            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
+            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
-            }
-            if (p.out_f32) {
-              float4* o = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) o[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
-            } else {
-              uint32_t ph[16], pl[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                __half h0, l0, h1, l1;
-                split_f16(y[2 * i], h0, l0);
-                split_f16(y[2 * i + 1], h1, l1);
-                ph[i] = pack_f16(h0, h1);
-                pl[i] = pack_f16(l0, l1);
-              }
-              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
-              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
-                ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
-              }
+            for (int q = 0; q < 4; ++q) {
+              oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
+              ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
             }
           }
         }
