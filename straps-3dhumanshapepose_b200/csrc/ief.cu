@@ -84,9 +84,20 @@ ief_kernel(const float* __restrict__ feat, const float* __restrict__ init, const
     bulk_g2s(&s.w3[0][0], wts.w3 + (size_t)rank * IEF_H * OPAD, IEF_H * OPAD * 4, &s.bar[2]);
   }
   // state: feat (transposed into k-major) + initial estimate
-  for (int i = tid; i < STRAPS_FEAT_DIM * TBI; i += IEF_THREADS) {
-    const int b = i / STRAPS_FEAT_DIM, k = i % STRAPS_FEAT_DIM;
-    s.xs[k][b] = (b0 + b < B) ? feat[(size_t)(b0 + b) * STRAPS_FEAT_DIM + k] : 0.f;
+  {
+    // 16 independent loads per thread are issued before the first store (ncu: the naive loop serialised 16 L2 round trips)
+    constexpr int PER = STRAPS_FEAT_DIM * TBI / IEF_THREADS;
+    float fv[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = tid + j * IEF_THREADS, b = i / STRAPS_FEAT_DIM, k = i % STRAPS_FEAT_DIM;
+      fv[j] = (b0 + b < B) ? __ldg(feat + (size_t)(b0 + b) * STRAPS_FEAT_DIM + k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = tid + j * IEF_THREADS;
+      s.xs[i % STRAPS_FEAT_DIM][i / STRAPS_FEAT_DIM] = fv[j];
+    }
   }
   for (int i = tid; i < STRAPS_IEF_PARAMS * TBI; i += IEF_THREADS) {
     const int k = i / TBI, b = i % TBI;
