@@ -44,6 +44,14 @@ def algorithmic_mflop(c):
     return MFLOP_PER_BODY.get(c, 4429.1 + 2 * 64 * 128 * 128 * 49 * c / 1e6 + 4.11)
 
 
+def conv_traffic(batch, channels):
+    """DRAM bytes per conv_tc_kernel launch from the committed `ncu --set full` capture of this command (B=64, C=17 only)."""
+    p = os.path.join(REPO, 'profiles', 'r01_conv_traffic.json')
+    if batch == 64 and channels == 17 and os.path.exists(p):
+        return json.load(open(p))['dram_bytes_per_launch']
+    return None
+
+
 def measured_peaks():
     p = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -305,9 +313,10 @@ def run_gpu(args):
                 'note': 'input synthesised on device from host segmentation labels + 2-D joints (utils/label_conversions drop-in, SURVEY 8f N1)'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': achieved_tf / peak_tf, 'traffic': None, 'peak_kind': peak_kind + ' (sustained cuBLAS bf16)',
+                         'frac': achieved_tf / peak_tf, 'traffic': conv_traffic(B, C), 'peak_kind': peak_kind + ' (sustained cuBLAS bf16)',
                          'kernel': 'conv_tc_kernel (20 launches/step) + input pack/pools = encoder', 'encoder_ms': enc_ms,
                          'algorithmic_gflop_per_step': flops / 1e9,
+                         'traffic_unit': 'DRAM bytes per conv_tc_kernel launch (dram__bytes_read+write, mean of the 20 launches of a step)',
                          'note': 'algorithmic FLOPs (1 pass); the f16x3 mode issues 3 MMA passes'},
             'cpu_baseline': cpu, 'clocks': clocks, 'torch': torch.__version__}
     print(json.dumps(line))

@@ -175,6 +175,16 @@ int straps_ief_backward(straps_regressor_t* r, const float* feat, const float* s
 int straps_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int step,
                      float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* Fused multi-task loss, forward + backward seeds -- losses/multi_task_loss.py:73-119 (+ utils/joints2d_utils.py:23-33 as the
+ * joints2D row mask).  preds / targets / grads: 5 dev pointers each in the order verts, joints2D [rows,2], joints3D, shape_params,
+ * pose rotmats (preds[t] == NULL switches task t off; grads[t] may be NULL).  counts[5] = element counts.  vis: optional dev uint8
+ * [rows] visibility mask (NULL + use_vis=1: computed from the pixel label exactly as the reference does; use_vis=0: all rows).
+ * log_vars dev [5] in the same task order.  scratch dev 128 bytes.  out dev [6] = (total, 5 weighted task losses);
+ * d_log_vars dev [5]; g_total dev [1] or NULL (= 1) scales the prediction gradients. */
+int straps_multitask_loss(const float* const* preds, const float* const* targets, float* const* grads, const int64_t* counts,
+                          const unsigned char* vis, int use_vis, float img_wh, const float* log_vars, int sum_reduction,
+                          const float* g_total, void* scratch, float* out, float* d_log_vars, void* stream);
+
 /* Debug/parity hook: copy a named intermediate activation (as NCHW fp32) of the last forward into
  * out (dev).  Names: "stem", "pool", "layer1.0" ... "layer4.1".  Returns element count via *n. */
 int straps_encoder_read_activation(straps_regressor_t* r, const char* name, int batch, float* out,

@@ -98,6 +98,51 @@ class DataParallelAdam(object):
         b.bump_versions()
 
 
+    # ---- checkpoint format of torch.optim.Adam (reference train/...:365-377, run_train.py:204-209) ----
+    def state_dict(self):
+        """The dict torch.optim.Adam.state_dict() would give for the same parameter list (per-parameter exp_avg / exp_avg_sq
+        views of the flat moments), so `checkpoint['optimiser_state_dict']` interchanges with the reference's files."""
+        b = self.bucket
+        state = {}
+        if self.step_count > 0:
+            for i, (p, o) in enumerate(zip(b.plist, b.offsets)):
+                n = p.numel()
+                state[i] = {'step': torch.tensor(float(self.step_count)),
+                            'exp_avg': self.exp_avg[o:o + n].view(p.shape).clone(),
+                            'exp_avg_sq': self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {'lr': self.lr, 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': 0, 'amsgrad': False, 'maximize': False,
+                 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None, 'decoupled_weight_decay': False,
+                 'params': list(range(len(b.plist)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_state_dict(self, sd):
+        b = self.bucket
+        groups = sd['param_groups']
+        if len(groups) != 1 or len(groups[0]['params']) != len(b.plist):
+            raise ValueError('optimiser state has %d parameter groups / %d parameters, expected 1 / %d'
+                             % (len(groups), len(groups[0]['params']) if groups else 0, len(b.plist)))
+        g = groups[0]
+        if g.get('weight_decay', 0) or g.get('amsgrad', False):
+            raise ValueError('weight decay / amsgrad are not part of the reference configuration (run_train.py:200-201)')
+        self.lr, self.betas, self.eps = g['lr'], tuple(g['betas']), g['eps']
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for i, (p, o) in enumerate(zip(b.plist, b.offsets)):
+            st = sd['state'].get(i, sd['state'].get(str(i)))
+            if st is None:
+                continue
+            n = p.numel()
+            if tuple(st['exp_avg'].shape) != tuple(p.shape):
+                raise ValueError('optimiser state %d has shape %s, parameter has %s' % (i, tuple(st['exp_avg'].shape), tuple(p.shape)))
+            self.exp_avg[o:o + n].copy_(st['exp_avg'].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st['exp_avg_sq'].reshape(-1))
+            steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise ValueError('per-parameter step counts differ (%s): not a plain Adam run' % sorted(steps))
+        self.step_count = steps.pop() if steps else 0
+
+
 def shard(batch_tensor, rank, world):
     """Contiguous batch shard of rank `rank`."""
     n = batch_tensor.shape[0]

@@ -260,3 +260,58 @@ def test_fused_adam_matches_torch_adam():
         opt.step()
         ops.adam_step(p, (2.0 * grad).to(DEV), m, v, step, lr=1e-4, grad_scale=0.5)
     assert rel_err(p.cpu().numpy(), pc.detach().numpy()) < 1e-6
+
+
+def _loss_inputs(B, seed):
+    rng = np.random.RandomState(seed)
+    mk = lambda *s: torch.from_numpy(rng.normal(0, 1, s).astype(np.float32))
+    outputs = {'verts': mk(B, 6890, 3), 'joints2D': mk(B, 17, 2), 'joints3D': mk(B, 14, 3), 'shape_params': mk(B, 10),
+               'pose_params_rot_matrices': mk(B, 24, 3, 3)}
+    labels = {'verts': mk(B, 6890, 3), 'joints2D': torch.from_numpy(rng.uniform(-40, 300, (B, 17, 2)).astype(np.float32)),
+              'joints3D': mk(B, 14, 3), 'shape_params': mk(B, 10), 'pose_params_rot_matrices': mk(B, 24, 3, 3)}
+    return outputs, labels
+
+
+def test_fused_loss_against_reference_fixture_and_oracle_autograd():
+    from losses.multi_task_loss import HomoscedasticUncertaintyWeightedMultiTaskLoss as Loss
+    from utils.joints2d_utils import check_joints2d_visibility_torch
+    from conftest import golden
+    W = {'verts': 1.0, 'joints2D': 0.1, 'pose_params': 0.1, 'shape_params': 0.1, 'joints3D': 1.0}
+    tasks = ['verts', 'joints2D', 'joints3D', 'shape_params', 'pose_params']
+    g = golden('loss_b3.npz')
+    outputs, labels = _loss_inputs(3, 21)            # the generator of oracle/gen_golden.py
+    labels['vis'] = O.joints2d_visibility(labels['joints2D'])
+    # oracle with autograd
+    oo = {k: v.clone().requires_grad_(True) for k, v in outputs.items()}
+    lv = {k: v.clone().requires_grad_(True) for k, v in O.init_log_vars(W).items()}
+    total_o, parts_o = O.multi_task_loss(labels, oo, lv)
+    total_o.backward()
+    # product on the GPU
+    crit = Loss(tasks, init_loss_weights=W).to(DEV)
+    og = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+    lg = {k: v.to(DEV) for k, v in labels.items()}
+    lg['vis'] = check_joints2d_visibility_torch(lg['joints2D'], 256)
+    assert torch.equal(lg['vis'].cpu(), labels['vis'])
+    total, parts = crit(lg, og)
+    total.backward()
+    assert rel_err(total.detach().cpu().numpy(), g['total']) < 1e-5
+    assert list(parts.keys()) == ['verts', 'joints2D', 'joints3D', 'shape_params', 'pose_params']
+    for k, v in parts.items():
+        assert rel_err(v.detach().cpu().numpy(), g['part_' + k]) < 1e-5, k
+    for k in outputs:
+        assert rel_err(og[k].grad.cpu().numpy(), oo[k].grad.numpy()) < 1e-5, k
+    for t in tasks:
+        assert rel_err(getattr(crit, t + '_log_var').grad.cpu().numpy(), lv[t].grad.numpy()) < 1e-5, t
+    # variants: no visibility mask, 'sum' reduction, a subset of tasks, an all-invisible batch (NaN like the reference)
+    lab2 = {k: v for k, v in lg.items() if k != 'vis'}
+    lab2o = {k: v for k, v in labels.items() if k != 'vis'}
+    crit_sum = Loss(['verts', 'joints2D', 'shape_params'], init_loss_weights=None, reduction='sum').to(DEV)
+    t2, p2 = crit_sum(lab2, {k: v.detach() for k, v in og.items()})
+    t2o, p2o = O.multi_task_loss(lab2o, outputs, O.init_log_vars(None), losses_on=('verts', 'joints2D', 'shape_params'), reduction='sum')
+    assert rel_err(t2.detach().cpu().numpy(), t2o.numpy()) < 1e-5 and set(p2.keys()) == {'verts', 'joints2D', 'shape_params'}
+    lg['vis'] = torch.zeros_like(lg['vis'])
+    t3, _ = crit(lg, {k: v.detach() for k, v in og.items()})
+    assert torch.isnan(t3)
+    from straps_b200._lib import StrapsError
+    with pytest.raises(StrapsError):
+        crit(labels, outputs)
