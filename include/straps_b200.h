@@ -152,15 +152,21 @@ int straps_regressor_forward(straps_regressor_t* r, const float* x, int batch, i
 /* ---- training path of the regressor (BASELINE config 3; reference train/...:186,230-233) ----
  * Train-mode forward of the encoder: BatchNorm uses batch statistics (biased variance), and -- when
  * update_running_stats != 0 -- updates the PyTorch-owned running_mean / running_var tensors given to
- * straps_regressor_load in place (momentum 0.1, unbiased variance).  fp32 CUDA-core kernels.  Keeps every
- * activation and pre-BN convolution output in the handle's training workspace for straps_encoder_backward. */
+ * straps_regressor_load in place (momentum 0.1, unbiased variance).  Keeps every activation and pre-BN
+ * convolution output in the handle's training workspace for straps_encoder_backward.
+ * conv_mode: STRAPS_CONV_FP32_SIMT = fp32 CUDA-core convolutions (forward, data and weight gradients);
+ *            STRAPS_CONV_F16X3_TC = forward convolutions, data gradients and weight gradients on the tensor cores
+ *            (3-pass fp16 split, fp32-equivalent). */
 int straps_encoder_train_forward(straps_regressor_t* r, const float* x, int batch, int update_running_stats,
-                                 float* feat, void* stream);
+                                 int conv_mode, float* feat, void* stream);
 /* Backward of the last straps_encoder_train_forward: dfeat dev [B,512] ->
  *   d_conv_w[20] : OIHW fp32 weight gradients (same order as straps_regressor_load's conv_w), overwritten;
- *   d_bn[40]     : (d_weight, d_bias) of the 20 BatchNorms, overwritten. */
-int straps_encoder_backward(straps_regressor_t* r, const float* dfeat, int batch, float* const* d_conv_w,
-                            float* const* d_bn, void* stream);
+ *   d_bn[40]     : (d_weight, d_bias) of the 20 BatchNorms, overwritten.
+ * conv_mode: -1 = the mode of the forward; STRAPS_CONV_FP32_SIMT after a tensor-core forward runs the fp32 CUDA-core
+ * gradients on the SAME saved activations (the parity tests use this to compare the two arithmetic paths without
+ * ReLU / max-pool flip noise); the tensor-core backward needs a tensor-core forward.  May be called repeatedly. */
+int straps_encoder_backward(straps_regressor_t* r, const float* dfeat, int batch, int conv_mode,
+                            float* const* d_conv_w, float* const* d_bn, void* stream);
 /* IEF forward that also saves, per iteration, { p_k [B,157] | h1_k [B,512] | h2_k [B,512] } into
  * saved dev [iters * B * 1181] for straps_ief_backward. */
 int straps_ief_forward_train(straps_regressor_t* r, const float* feat, int batch, int iters, float* params,

@@ -234,6 +234,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                          // SWIZZLE_128B   [61,64)
   return d;
 }
+// MN-major operand (the reduction index is the SLOW one in shared memory), SWIZZLE_128B: each K row is one 128-byte line of 64
+// fp16 along M/N (exactly what a TMA box {64, rows} writes); 8 rows form a 1024-byte swizzle atom (SBO = stride between
+// 8-row groups along K), and LBO is the stride between consecutive 64-element chunks along M/N.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptors for kind::f16 (fp32 accumulate, both operands K-major).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4)            // c_format = F32
@@ -247,6 +259,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
          | ((N >> 3) << 17)   // n_dim
          | ((M >> 4) << 24);  // m_dim
 }
+// kind::f16, both operands MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_mn(uint32_t M, uint32_t N) { return umma_idesc_f16(M, N) | (1u << 15) | (1u << 16); }
 #endif  // __CUDACC__
 
 }  // namespace straps

@@ -29,7 +29,6 @@
 //   ring of 3-4 stages, two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Roofline: tensor pipe; algorithmic FLOPs 6,180.1 MFLOP/body (C=17), issued = 3 passes (+ conv1 K padding).
 #include "regressor.h"
-#include <cuda_fp16.h>
 #include <map>
 #include <cstdlib>
 
@@ -59,6 +58,7 @@ struct TcConvParams {
   __half* out_lo;
   const __half* res_hi;     // residual (identity) planes or null
   const __half* res_lo;
+  const float* res_f32;     // fp32 NHWC tensor added to the result (data-gradient accumulation) or null
   int relu;
   int debug;        // timing experiments only (STRAPS_TC_DEBUG): 1 = no TMA traffic, 2 = no MMAs, 3 = no epilogue stores
 };
@@ -85,16 +85,6 @@ struct TcCfg {
   static constexpr int TMEM_COLS = TSTAGES * ACC_COLS;
   static_assert(STAGES >= 2 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "bad tile configuration");
 };
-
-__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
-  hi = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
-  lo = __float2half_rn(v - __half2float(hi));
-}
-__device__ __forceinline__ uint32_t pack_f16(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
-__device__ __forceinline__ float f16lo_to_f(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
-__device__ __forceinline__ float f16hi_to_f(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
 template <int BN, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -285,6 +275,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         fetch_residual(chunk + 1);        // in flight while this chunk is split and stored
         if (valid && p.debug != 3) {
+          if (p.res_f32) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.res_f32 + obase + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 a = r4[q];
+              y[q * 4 + 0] += a.x; y[q * 4 + 1] += a.y; y[q * 4 + 2] += a.z; y[q * 4 + 3] += a.w;
+            }
+          }
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
@@ -696,6 +694,7 @@ struct TcState {
   float* unscale;               // [sum cout] their inverses
   size_t ch_off[NCONV];         // offset of each conv in the two arrays above
   std::map<int, std::vector<TcLayerMaps>> maps;   // per batch size
+  struct TcTrain* train;        // training-path state, allocated on first use
 };
 
 static inline __half* plane_hi(const straps_regressor* r, int buf) {
@@ -712,7 +711,7 @@ static inline bool out_is_f32(const straps_regressor* r, int ci) {
 int tc_create(straps_regressor* r) {
   TcState* t = new TcState();
   r->tc = t;
-  t->xp = nullptr; t->wpool = nullptr; t->encode = nullptr; t->num_sms = 148;
+  t->xp = nullptr; t->wpool = nullptr; t->encode = nullptr; t->num_sms = 148; t->train = nullptr;
   // The driver entry point is resolved at first use (no GPU / driver in the build container).
   t->xp_plane = (size_t)r->max_batch * XP_H * XP_W * XP_C;
   size_t welts = 0, nch = 0;
@@ -744,9 +743,12 @@ int tc_create(straps_regressor* r) {
   return 0;
 }
 
+static void tc_train_free(TcState* t);
+
 void tc_destroy(straps_regressor* r) {
   TcState* t = static_cast<TcState*>(r->tc);
   if (!t) return;
+  tc_train_free(t);
   if (t->xp) cudaFree(t->xp);
   if (t->wpool) cudaFree(t->wpool);
   if (t->rowscale) cudaFree(t->rowscale);
@@ -784,60 +786,89 @@ static int encode(TcState* t, CUtensorMap* m, void* base, int rank, const cuuint
   return 0;
 }
 
+// geometry of one implicit-GEMM convolution as the kernel sees it (a forward conv, or a data gradient recast as one)
+struct TcGeom {
+  int cin, cout, ksize, stride, pad, hin, win, hout, wout, k_eff, conv1;
+};
+static TcGeom geom_fwd(const ConvSpec& c, int ci) {
+  TcGeom g;
+  g.cin = c.cin; g.cout = c.cout; g.ksize = c.ksize; g.stride = c.stride; g.pad = c.pad;
+  g.hin = c.hin; g.win = c.win; g.hout = c.hout; g.wout = c.wout; g.k_eff = c.k_eff; g.conv1 = (ci == 0);
+  return g;
+}
+// dX = conv(dY [zero-upsampled x2 when the forward conv has stride 2], taps flipped, Cin <-> Cout), stride 1, pad ks-1-pad
+static TcGeom geom_dgrad(const ConvSpec& c) {
+  TcGeom g;
+  g.cin = c.cout; g.cout = c.cin; g.ksize = c.ksize; g.stride = 1; g.pad = c.ksize - 1 - c.pad;
+  g.hin = c.hin; g.win = c.win; g.hout = c.hin; g.wout = c.win; g.k_eff = c.ksize * c.ksize * c.cout; g.conv1 = 0;
+  return g;
+}
+
 // tile configuration per layer (see TcCfg): BN, MT
-static void tile_cfg(const ConvSpec& c, int* bn, int* mt) {
+static void tile_cfg(int cout, int* bn, int* mt) {
   const char* e = getenv("STRAPS_TC_TILES");      // "wide" selects the experimental (64,2)/(128,2)/(256,1) shapes
   const bool wide = e && e[0] == 'w';
-  if (c.cout == 64) { *bn = 64; *mt = wide ? 2 : 1; }
-  else if (c.cout == 128) { *bn = 128; *mt = wide ? 2 : 1; }
-  else if (c.cout == 256 && wide) { *bn = 256; *mt = 1; }
+  if (cout == 64) { *bn = 64; *mt = wide ? 2 : 1; }
+  else if (cout == 128) { *bn = 128; *mt = wide ? 2 : 1; }
+  else if (cout == 256 && wide) { *bn = 256; *mt = 1; }
   else { *bn = 128; *mt = 1; }
 }
-static int tile_bn(const ConvSpec& c) { int bn, mt; tile_cfg(c, &bn, &mt); return bn; }
+static int tile_bn(int cout) { int bn, mt; tile_cfg(cout, &bn, &mt); return bn; }
+
+static int ensure_encode(TcState* t) {
+  if (t->encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  STRAPS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  STRAPS_CHECK(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from this driver");
+  t->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+// tensor maps of one convolution: A over the split activation planes, W over [Cout][K_eff]
+static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __half* a_lo, void* w_hi, void* w_lo, TcLayerMaps& out) {
+  const int bn = tile_bn(c.cout);
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)c.k_eff, (cuuint64_t)c.cout};
+    cuuint64_t str[1] = {(cuuint64_t)c.k_eff * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    cuuint32_t es[2] = {1, 1};
+    if (encode(t, &out.w_hi, w_hi, 2, dims, str, box, es)) return 1;
+    if (encode(t, &out.w_lo, w_lo, 2, dims, str, box, es)) return 1;
+    cuuint32_t box2[2] = {64, (cuuint32_t)((c.cout == 64 ? 64 : 128) / 2)};
+    if (encode(t, &out.w2_hi, w_hi, 2, dims, str, box2, es)) return 1;
+    if (encode(t, &out.w2_lo, w_lo, 2, dims, str, box2, es)) return 1;
+  }
+  if (c.conv1) {
+    // conv1: (flattened kw,c run | ow | oh | b) over the padded input, strides bake in the stride-2 sampling
+    cuuint64_t dims[4] = {(cuuint64_t)6 * XP_W * XP_C + C1_KROW, 128, 128, (cuuint64_t)B};
+    cuuint64_t str[3] = {2 * XP_C * 2, (cuuint64_t)2 * XP_W * XP_C * 2, (cuuint64_t)XP_H * XP_W * XP_C * 2};
+    cuuint32_t box[4] = {64, 128, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (encode(t, &out.a_hi, a_hi, 4, dims, str, box, es)) return 1;
+    if (encode(t, &out.a_lo, a_lo, 4, dims, str, box, es)) return 1;
+  } else {
+    const int th = (c.hout * c.wout >= BM_TC) ? BM_TC / c.wout : c.hout;
+    const int nb = BM_TC / (c.wout * th);
+    cuuint64_t dims[4] = {(cuuint64_t)c.cin, (cuuint64_t)c.win, (cuuint64_t)c.hin, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)c.cin * 2, (cuuint64_t)c.win * c.cin * 2, (cuuint64_t)c.hin * c.win * c.cin * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(c.wout * c.stride), (cuuint32_t)(th * c.stride), (cuuint32_t)nb};
+    cuuint32_t es[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
+    if (encode(t, &out.a_hi, a_hi, 4, dims, str, box, es)) return 1;
+    if (encode(t, &out.a_lo, a_lo, 4, dims, str, box, es)) return 1;
+  }
+  return 0;
+}
 
 static int build_maps(straps_regressor* r, int B, std::vector<TcLayerMaps>& out) {
   TcState* t = static_cast<TcState*>(r->tc);
-  if (!t->encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    STRAPS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    STRAPS_CHECK(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from this driver");
-    t->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  }
+  if (ensure_encode(t)) return 1;
   out.resize(NCONV);
   for (int i = 0; i < NCONV; ++i) {
     const ConvSpec& c = r->conv[i];
-    const int bn = tile_bn(c);
-    // weights: [Cout][K_eff]
-    {
-      cuuint64_t dims[2] = {(cuuint64_t)c.k_eff, (cuuint64_t)c.cout};
-      cuuint64_t str[1] = {(cuuint64_t)c.k_eff * 2};
-      cuuint32_t box[2] = {64, (cuuint32_t)bn};
-      cuuint32_t es[2] = {1, 1};
-      if (encode(t, &out[i].w_hi, c.w_hi, 2, dims, str, box, es)) return 1;
-      if (encode(t, &out[i].w_lo, c.w_lo, 2, dims, str, box, es)) return 1;
-      cuuint32_t box2[2] = {64, (cuuint32_t)((c.cout == 64 ? 64 : 128) / 2)};
-      if (encode(t, &out[i].w2_hi, c.w_hi, 2, dims, str, box2, es)) return 1;
-      if (encode(t, &out[i].w2_lo, c.w_lo, 2, dims, str, box2, es)) return 1;
-    }
-    if (i == 0) {
-      // conv1: (flattened kw,c run | ow | oh | b) over the padded input, strides bake in the stride-2 sampling
-      cuuint64_t dims[4] = {(cuuint64_t)6 * XP_W * XP_C + C1_KROW, 128, 128, (cuuint64_t)B};
-      cuuint64_t str[3] = {2 * XP_C * 2, (cuuint64_t)2 * XP_W * XP_C * 2, (cuuint64_t)XP_H * XP_W * XP_C * 2};
-      cuuint32_t box[4] = {64, 128, 1, 1};
-      cuuint32_t es[4] = {1, 1, 1, 1};
-      if (encode(t, &out[i].a_hi, t->xp, 4, dims, str, box, es)) return 1;
-      if (encode(t, &out[i].a_lo, t->xp + t->xp_plane, 4, dims, str, box, es)) return 1;
-    } else {
-      const int th = (c.hout * c.wout >= BM_TC) ? BM_TC / c.wout : c.hout;
-      const int nb = BM_TC / (c.wout * th);
-      cuuint64_t dims[4] = {(cuuint64_t)c.cin, (cuuint64_t)c.win, (cuuint64_t)c.hin, (cuuint64_t)B};
-      cuuint64_t str[3] = {(cuuint64_t)c.cin * 2, (cuuint64_t)c.win * c.cin * 2, (cuuint64_t)c.hin * c.win * c.cin * 2};
-      cuuint32_t box[4] = {64, (cuuint32_t)(c.wout * c.stride), (cuuint32_t)(th * c.stride), (cuuint32_t)nb};
-      cuuint32_t es[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
-      if (encode(t, &out[i].a_hi, plane_hi(r, c.in_buf), 4, dims, str, box, es)) return 1;
-      if (encode(t, &out[i].a_lo, plane_lo(r, c.in_buf), 4, dims, str, box, es)) return 1;
-    }
+    __half* a_hi = (i == 0) ? t->xp : plane_hi(r, c.in_buf);
+    __half* a_lo = (i == 0) ? t->xp + t->xp_plane : plane_lo(r, c.in_buf);
+    if (build_layer_maps(t, geom_fwd(c, i), B, a_hi, a_lo, c.w_hi, c.w_lo, out[i])) return 1;
   }
   return 0;
 }
@@ -872,16 +903,13 @@ static int launch_conv_tc2(const TcLayerMaps& m, const TcConvParams& p, int num_
   return 0;
 }
 
-static int run_conv_tc(straps_regressor* r, const std::vector<TcLayerMaps>& maps, int ci, int B, cudaStream_t st) {
-  TcState* t = static_cast<TcState*>(r->tc);
-  const ConvSpec& c = r->conv[ci];
-  const int bn = tile_bn(c);
-  TcConvParams p;
-  memset(&p, 0, sizeof(p));
+// p carries the pointers (shift, unscale, outputs, residuals, relu); the geometry fields are filled here
+static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParams p, int B, cudaStream_t st) {
+  const int bn = tile_bn(c.cout);
   p.m_total = (long long)B * c.hout * c.wout;
   p.n_mtiles = (int)((p.m_total + BM_TC - 1) / BM_TC);
   p.n_ntiles = c.cout / bn;
-  p.conv1 = (ci == 0);
+  p.conv1 = c.conv1;
   p.n_kblocks = c.k_eff / BK_TC;
   p.cchunks = c.cin / 64;
   p.kw_count = c.ksize;
@@ -889,10 +917,30 @@ static int run_conv_tc(straps_regressor* r, const std::vector<TcLayerMaps>& maps
   p.hw_out = c.hout * c.wout; p.wout = c.wout;
   p.th = (c.hout * c.wout >= BM_TC) ? BM_TC / c.wout : c.hout;
   p.cout = c.cout;
+  { const char* d = getenv("STRAPS_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
+  int mt;
+  { int bn2; tile_cfg(c.cout, &bn2, &mt); }
+  {
+    // STRAPS_TC_PAIR: "128" = CTA pairs for the Cout >= 128 layers, "all" = every layer, unset/"0" = single-CTA kernels
+    const char* e = getenv("STRAPS_TC_PAIR");
+    const bool pair = e && ((e[0] == 'a') || (e[0] == '1' && c.cout >= 128));
+    if (pair && mt == 1 && bn <= 128 && !p.res_f32)
+      return bn == 64 ? launch_conv_tc2<64>(m, p, t->num_sms, st) : launch_conv_tc2<128>(m, p, t->num_sms, st);
+  }
+  if (bn == 64) return mt == 2 ? launch_conv_tc<64, 2>(m, p, t->num_sms, st) : launch_conv_tc<64, 1>(m, p, t->num_sms, st);
+  if (bn == 256) return launch_conv_tc<256, 1>(m, p, t->num_sms, st);
+  if (mt == 2) return launch_conv_tc<128, 2>(m, p, t->num_sms, st);
+  return launch_conv_tc<128, 1>(m, p, t->num_sms, st);
+}
+
+static int run_conv_tc(straps_regressor* r, const std::vector<TcLayerMaps>& maps, int ci, int B, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  const ConvSpec& c = r->conv[ci];
+  TcConvParams p;
+  memset(&p, 0, sizeof(p));
   p.shift = c.shift;
   p.unscale = t->unscale + t->ch_off[ci];
   p.relu = c.relu;
-  { const char* d = getenv("STRAPS_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
   if (out_is_f32(r, ci)) {
     p.out_f32 = act_ptr(r, c.out_buf);
   } else {
@@ -903,19 +951,7 @@ static int run_conv_tc(straps_regressor* r, const std::vector<TcLayerMaps>& maps
     p.res_hi = plane_hi(r, c.res_buf);
     p.res_lo = plane_lo(r, c.res_buf);
   }
-  int mt;
-  { int bn2; tile_cfg(c, &bn2, &mt); }
-  {
-    // STRAPS_TC_PAIR: "128" = CTA pairs for the Cout >= 128 layers, "all" = every layer, unset/"0" = single-CTA kernels
-    const char* e = getenv("STRAPS_TC_PAIR");
-    const bool pair = e && ((e[0] == 'a') || (e[0] == '1' && c.cout >= 128));
-    if (pair && mt == 1 && bn <= 128)
-      return bn == 64 ? launch_conv_tc2<64>(maps[ci], p, t->num_sms, st) : launch_conv_tc2<128>(maps[ci], p, t->num_sms, st);
-  }
-  if (bn == 64) return mt == 2 ? launch_conv_tc<64, 2>(maps[ci], p, t->num_sms, st) : launch_conv_tc<64, 1>(maps[ci], p, t->num_sms, st);
-  if (bn == 256) return launch_conv_tc<256, 1>(maps[ci], p, t->num_sms, st);
-  if (mt == 2) return launch_conv_tc<128, 2>(maps[ci], p, t->num_sms, st);
-  return launch_conv_tc<128, 1>(maps[ci], p, t->num_sms, st);
+  return run_tc(t, geom_fwd(c, ci), maps[ci], p, B, st);
 }
 
 int tc_encoder_forward(straps_regressor* r, const float* x, int B, float* feat, cudaStream_t st) {
@@ -957,6 +993,600 @@ int tc_read_activation(straps_regressor* r, int buf, int batch, float* out, cuda
     f32_nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(act_ptr(r, buf), b.c, b.h, b.w, out, total);
   else
     split_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(plane_hi(r, buf), plane_lo(r, buf), b.c, b.h, b.w, out, total);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient on the tensor cores
+//   dW[co][(tap,ci)] = sum over output pixels of  X[pixel @ tap][ci] * dY[pixel][co]
+// Both operands are read exactly as they lie in HBM -- NHWC, i.e. the reduction index (the pixel) is the SLOW one -- so both
+// are MN-major UMMA operands: a TMA box {64 channels, 64 pixels} lands as 64 rows of 128 bytes, which IS the canonical
+// SWIZZLE_128B MN-major atom layout (no transposes anywhere).  A = X patches (M = 128 = two 64-wide (tap, ci-chunk) columns of
+// the weight matrix, the same 4-D boxes the forward uses, 64 pixels deep), B = dY (N = BN output channels), D = dW^T tile.
+// 3-pass fp16 split as in the forward:  X_hi.[dY_hi | dY_lo]  (one MMA of width 2 BN)  +  X_lo.dY_hi , separate accumulators.
+// dY is pre-scaled by a power of two (split_scaled_kernel); the inverse is applied by unpack_dw_tc_kernel.
+// Split-K: an item = (M-tile, N-tile, range of <= 128 K-tiles of 64 pixels); partial tiles are added to dW[cout][k_eff] with
+// coalesced fp32 reductions (a warp = 32 consecutive ci of one co).  Short K ranges also bound the truncation bias of the
+// tensor-core accumulator (-1e-8 relative per MMA).
+struct WgParams {
+  int n_mtiles, n_ntiles, splits, ktiles, kt_per;
+  int nchunks;         // 64-wide columns (tap, ci-chunk) of the weight matrix
+  int conv1, cchunks, kw_count, stride, pad;
+  int hw_out, wout;
+  int k_eff;
+  float* dw;           // [cout][k_eff], accumulated
+};
+
+template <int BN>
+struct WgCfg {
+  static constexpr int CHUNK_BYTES = 64 * 128;                      // 64 pixels x 64 channels fp16
+  static constexpr int A_BYTES = 2 * CHUNK_BYTES;                   // per plane
+  static constexpr int B_BYTES = (BN / 64) * CHUNK_BYTES;           // per plane
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;     // 48 KB (BN 64) / 64 KB (BN 128)
+  static constexpr int STAGES = (BN == 64) ? 4 : 3;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int ACC_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;                    // two accumulator stages
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                const __grid_constant__ CUtensorMap map_dy_hi, const __grid_constant__ CUtensorMap map_dy_lo, const WgParams p) {
+  using Cfg = WgCfg<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.n_mtiles * p.n_ntiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x_hi); tma_prefetch_desc(&map_x_lo); tma_prefetch_desc(&map_dy_hi); tma_prefetch_desc(&map_dy_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (split, nt, mt): consecutive CTAs share the K range (dY and X tiles hit in L2)
+  auto decode = [&](int item, int& mt, int& nt, int& kt0, int& kt1) {
+    mt = item % p.n_mtiles;
+    const int r = item / p.n_mtiles;
+    nt = r % p.n_ntiles;
+    const int sp = r / p.n_ntiles;
+    kt0 = sp * p.kt_per;
+    kt1 = min(p.ktiles, kt0 + p.kt_per);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int mt, nt, kt0, kt1;
+        decode(item, mt, nt, kt0, kt1);
+        int c0[2], c1o[2], c2o[2];        // per chunk: channel / flattened-run coordinate and the tap offsets
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int q = min(2 * mt + j, p.nchunks - 1);
+          if (p.conv1) {
+            const int kh = q / 3, jj = q % 3;
+            c0[j] = kh * (XP_W * XP_C) + jj * 64; c1o[j] = 0; c2o[j] = 0;
+          } else {
+            const int tap = q / p.cchunks, cc = q % p.cchunks;
+            c0[j] = cc * 64; c1o[j] = tap % p.kw_count - p.pad; c2o[j] = tap / p.kw_count - p.pad;
+          }
+        }
+        for (int kt = kt0; kt < kt1; ++kt, ++it) {
+          const int st = it % Cfg::STAGES;
+          mbar_wait(&empty[st], ((it / Cfg::STAGES) & 1) ^ 1);
+          unsigned char* sa = smem + st * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
+          const long long pix0 = (long long)kt * 64;
+          const int b0 = (int)(pix0 / p.hw_out), rem = (int)(pix0 % p.hw_out);
+          const int oh0 = rem / p.wout, ow0 = rem % p.wout;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c1 = p.conv1 ? ow0 : ow0 * p.stride + c1o[j];
+            const int c2 = p.conv1 ? oh0 : oh0 * p.stride + c2o[j];
+            tma_load_4d(sa + j * Cfg::CHUNK_BYTES, &map_x_hi, &full[st], c0[j], c1, c2, b0);
+            tma_load_4d(sa + Cfg::A_BYTES + j * Cfg::CHUNK_BYTES, &map_x_lo, &full[st], c0[j], c1, c2, b0);
+          }
+          unsigned char* sb = sa + 2 * Cfg::A_BYTES;
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) {
+            tma_load_2d(sb + c * Cfg::CHUNK_BYTES, &map_dy_hi, &full[st], nt * BN + c * 64, kt * 64);
+            tma_load_2d(sb + Cfg::B_BYTES + c * Cfg::CHUNK_BYTES, &map_dy_lo, &full[st], nt * BN + c * 64, kt * 64);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16_mn(128, BN);
+      constexpr uint32_t idesc_wide = umma_idesc_f16_mn(128, 2 * BN);
+      constexpr uint32_t lbo = Cfg::CHUNK_BYTES, sbo = 1024;     // chunk stride along M/N, 8-pixel atom stride along K
+      uint32_t it = 0, ti = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+        int mt, nt, kt0, kt1;
+        decode(item, mt, nt, kt0, kt1);
+        const uint32_t as = ti & 1;
+        mbar_wait(&tempty[as], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_hi = tmem_base + as * Cfg::ACC_COLS, d_lo = d_hi + BN;
+        for (int kt = kt0; kt < kt1; ++kt, ++it) {
+          const int st = it % Cfg::STAGES;
+          mbar_wait(&full[st], (it / Cfg::STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
+          const uint64_t x_hi = umma_desc_mn_sw128(sa, lbo, sbo);
+          const uint64_t x_lo = umma_desc_mn_sw128(sa + Cfg::A_BYTES, lbo, sbo);
+          const uint64_t dy = umma_desc_mn_sw128(sa + 2 * Cfg::A_BYTES, lbo, sbo);     // [dY_hi chunks | dY_lo chunks]
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2048 >> 4);       // 16 pixels = two 8-row swizzle atoms
+            umma_f16(d_hi, x_hi + ko, dy + ko, idesc_wide, (kt != kt0) || (k != 0));
+            umma_f16(d_lo, x_lo + ko, dy + ko, idesc, 1);
+          }
+          umma_commit(&empty[st]);
+        }
+        umma_commit(&tfull[as]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;            // = chunk_local * 64 + ci_local
+    uint32_t ti = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+      int mt, nt, kt0, kt1;
+      decode(item, mt, nt, kt0, kt1);
+      const uint32_t as = ti & 1;
+      mbar_wait(&tfull[as], (ti >> 1) & 1);
+      tc_fence_after();
+      const int q = 2 * mt + (row >> 6);
+      const bool valid = q < p.nchunks;
+      float* dst = p.dw + (size_t)(nt * BN) * p.k_eff + (size_t)q * 64 + (row & 63);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32], vl[32];
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + as * Cfg::ACC_COLS + c0;
+        tmem_ld_32x32(tacc, v);
+        tmem_ld_32x32(tacc + BN, vl);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            atomicAdd(dst + (size_t)(c0 + j) * p.k_eff, __uint_as_float(v[j]) + __uint_as_float(vl[j]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// dW[cout][k_eff] (x dY scale) -> OIHW fp32
+__global__ void unpack_dw_tc_kernel(const float* __restrict__ dw, const unsigned* __restrict__ maxbits, int cout, int cin, int ks, int conv1,
+                                    int k_eff, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)cout * cin * ks * ks) return;
+  int e = 0;
+  const float mx = __uint_as_float(*maxbits);
+  if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); e = max(-100, min(100, 14 - e)); }
+  const int kw = (int)(i % ks);
+  size_t t = i / ks;
+  const int kh = (int)(t % ks); t /= ks;
+  const int c = (int)(t % cin);
+  const int n = (int)(t / cin);
+  const int k = conv1 ? kh * C1_KROW + kw * XP_C + c : (kh * ks + kw) * cin + c;
+  out[i] = dw[(size_t)n * k_eff + k] * ldexpf(1.f, -e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// training path on the tensor cores (called from train.cu)
+//
+// forward       : the same conv_tc_kernel with the BatchNorm scale NOT folded (train-mode BN needs the raw conv output for its
+//                 batch statistics): weights re-split every step, output = fp32 NHWC `raw`, no shift / residual / ReLU.
+// data gradient : dX = conv(dY, W') with W'[ci][(kh',kw',co)] = W[co][ci][ks-1-kh'][ks-1-kw'], stride 1, pad ks-1-pad -- again the
+//                 same kernel.  A stride-2 forward conv becomes a stride-1 conv over dY zero-upsampled by 2 (4x redundant MMAs on
+//                 6 small layers, 9 % of the data-gradient FLOPs, instead of a second kernel).  dY has no natural scale (1e-2 ..
+//                 1e-8), so it is multiplied by the power of two that puts max|dY| into [2^13, 2^14) before the fp16 split; the
+//                 exact inverse is folded into the per-channel epilogue scale.  The other branch's gradient (`add`) is summed in
+//                 fp32 in the epilogue.
+// ------------------------------------------------------------------------------------------------
+struct TcTrain {
+  __half* pool;
+  std::vector<__half*> plane_hi, plane_lo;     // split planes per activation buffer (null: never a conv input)
+  __half *wf_hi[NCONV], *wf_lo[NCONV];         // forward weights [cout][k_eff]
+  __half *wd_hi[NCONV], *wd_lo[NCONV];         // data-gradient weights [cin][ks*ks*cout]
+  float *wf_scale, *wf_unscale;                // [sum cout]
+  float *wd_scale, *wd_unscale;                // [sum cin]
+  size_t wd_off[NCONV];
+  float* dg_unscale;                           // [512] wd_unscale / dY scale of the current data gradient
+  float* ones; float* zeros;                   // [512]
+  unsigned* dy_max;                            // bits of max |dY| (atomicMax target of bn_bwd_apply_kernel)
+  __half *dy_hi, *dy_lo;                       // split (scaled, optionally zero-upsampled) dY of the current layer
+  size_t dy_plane;                             // elements per plane
+  float* dw_packed;                            // [cout][k_eff] fp32 accumulation target of the weight gradient (largest conv)
+  size_t dw_elems;
+  std::map<int, std::vector<TcLayerMaps>> fwd_maps, dg_maps;
+  std::map<int, std::vector<TcLayerMaps>> wg_maps;   // a_* = X with 64-pixel boxes, w_* = dY [pixels][cout] boxes {64, 64}
+};
+
+static void tc_train_free(TcState* t) {
+  if (!t->train) return;
+  if (t->train->pool) cudaFree(t->train->pool);
+  delete t->train;
+  t->train = nullptr;
+}
+
+// per INPUT channel of the forward conv: power-of-two scale for the rows of the data-gradient weight matrix
+__global__ void w_colscale_kernel(const float* __restrict__ w, int cout, int cin, int kk, float* __restrict__ pscale,
+                                  float* __restrict__ unscale) {
+  __shared__ float red[256];
+  const int ci = blockIdx.x;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < cout * kk; i += blockDim.x) m = fmaxf(m, fabsf(w[((size_t)(i / kk) * cin + ci) * kk + (i % kk)]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float mx = red[0];
+    int e = 0;
+    if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); e = max(-60, min(60, 14 - e)); }
+    pscale[ci] = ldexpf(1.f, e);
+    unscale[ci] = ldexpf(1.f, -e);
+  }
+}
+// OIHW fp32 -> [Cin][(kh',kw',co)] fp16 hi/lo with the taps flipped
+__global__ void pack_w_dgrad_tc_kernel(const float* __restrict__ w, const float* __restrict__ pscale, int cout, int cin, int ks,
+                                       __half* __restrict__ hi, __half* __restrict__ lo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k_eff = ks * ks * cout;
+  if (i >= (size_t)cin * k_eff) return;
+  const int ci = (int)(i / k_eff), k = (int)(i % k_eff);
+  const int tap = k / cout, co = k % cout, kh = ks - 1 - tap / ks, kw = ks - 1 - tap % ks;
+  const float v = w[(((size_t)co * cin + ci) * ks + kh) * ks + kw] * pscale[ci];
+  __half h, l;
+  split_f16(v, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+// fp32 NHWC -> split planes, scaled by the power of two derived from *maxbits (null: no scaling); up = 1 writes pixel (h, w) to
+// (2h, 2w) of a [B, 2H, 2W, C] tensor (zeroed beforehand).  Block 0 also publishes the epilogue scales of the data gradient.
+__global__ void split_scaled_kernel(const float* __restrict__ src, const unsigned* __restrict__ maxbits, long long n4, int C, int H, int W,
+                                    int up, __half* __restrict__ hi, __half* __restrict__ lo, const float* __restrict__ w_unscale,
+                                    int n_unscale, float* __restrict__ out_unscale) {
+  int e = 0;
+  if (maxbits) {
+    const float mx = __uint_as_float(*maxbits);
+    if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); e = max(-100, min(100, 14 - e)); }
+  }
+  const float sc = ldexpf(1.f, e);
+  if (blockIdx.x == 0 && out_unscale) {
+    const float inv = ldexpf(1.f, -e);
+    for (int c = threadIdx.x; c < n_unscale; c += blockDim.x) out_unscale[c] = w_unscale[c] * inv;
+  }
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(src)[i];
+  __half h[4], l[4];
+  split_f16(v.x * sc, h[0], l[0]); split_f16(v.y * sc, h[1], l[1]); split_f16(v.z * sc, h[2], l[2]); split_f16(v.w * sc, h[3], l[3]);
+  long long o = i * 4;
+  if (up) {
+    const int c = (int)(o % C);
+    long long t = o / C;
+    const int w = (int)(t % W); t /= W;
+    const int hh = (int)(t % H);
+    const long long b = t / H;
+    o = (((b * 2 * H + 2 * hh) * 2 * W) + 2 * w) * C + c;
+  }
+  *reinterpret_cast<uint2*>(hi + o) = make_uint2(pack_f16(h[0], h[1]), pack_f16(h[2], h[3]));
+  *reinterpret_cast<uint2*>(lo + o) = make_uint2(pack_f16(l[0], l[1]), pack_f16(l[2], l[3]));
+}
+
+static bool buf_is_conv_input(const straps_regressor* r, int buf) {
+  for (int i = 1; i < NCONV; ++i)
+    if (r->conv[i].in_buf == buf) return true;
+  return false;
+}
+
+int tc_train_begin(straps_regressor* r, int B, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  STRAPS_CHECK(t, "tc_train_begin: tensor-core state missing");
+  if (ensure_encode(t)) return 1;
+  if (!t->train) {
+    TcTrain* tt = new TcTrain();
+    size_t el = 0;   // fp16 elements
+    auto take = [&](size_t n) { size_t o = el; el += (n + 511) & ~(size_t)511; return o; };   // 1 KB granules
+    const size_t nb = r->bufs.size();
+    std::vector<size_t> off_p(nb, (size_t)-1);
+    for (size_t b = 0; b < nb; ++b)
+      if ((int)b != r->buf_xin && buf_is_conv_input(r, (int)b)) off_p[b] = take(2 * (size_t)r->max_batch * r->bufs[b].h * r->bufs[b].w * r->bufs[b].c);
+    size_t off_wf[NCONV], off_wd[NCONV], nco = 0, nci = 0, dy_el = 0, dw_el = 0;
+    for (int i = 0; i < NCONV; ++i) {
+      const ConvSpec& c = r->conv[i];
+      off_wf[i] = take(2 * (size_t)c.cout * c.k_eff);
+      off_wd[i] = (i == 0) ? 0 : take(2 * (size_t)c.cin * c.ksize * c.ksize * c.cout);
+      tt->wd_off[i] = nci;
+      nco += c.cout; nci += (i == 0) ? 0 : c.cin;
+      dy_el = std::max(dy_el, (size_t)r->max_batch * c.hout * c.wout * c.cout);
+      if (i > 0) dy_el = std::max(dy_el, (size_t)r->max_batch * c.hin * c.win * c.cout);   // (upsampled) dY of this layer
+      dw_el = std::max(dw_el, (size_t)c.cout * c.k_eff);
+    }
+    tt->dy_plane = dy_el;
+    const size_t off_dy = take(2 * dy_el);
+    const size_t n_f32 = 2 * nco + 2 * nci + 512 * 3 + 64 + dw_el;
+    const size_t off_f = take(2 * n_f32);
+    if (cudaMalloc(&tt->pool, el * sizeof(__half)) != cudaSuccess) {
+      set_error("tc_train_begin: cudaMalloc of %zu bytes failed: %s", el * sizeof(__half), cudaGetErrorString(cudaGetLastError()));
+      delete tt;
+      return 1;
+    }
+    tt->plane_hi.assign(nb, nullptr); tt->plane_lo.assign(nb, nullptr);
+    for (size_t b = 0; b < nb; ++b)
+      if (off_p[b] != (size_t)-1) {
+        tt->plane_hi[b] = tt->pool + off_p[b];
+        tt->plane_lo[b] = tt->plane_hi[b] + (size_t)r->max_batch * r->bufs[b].h * r->bufs[b].w * r->bufs[b].c;
+      }
+    for (int i = 0; i < NCONV; ++i) {
+      const ConvSpec& c = r->conv[i];
+      tt->wf_hi[i] = tt->pool + off_wf[i]; tt->wf_lo[i] = tt->wf_hi[i] + (size_t)c.cout * c.k_eff;
+      tt->wd_hi[i] = (i == 0) ? nullptr : tt->pool + off_wd[i];
+      tt->wd_lo[i] = (i == 0) ? nullptr : tt->wd_hi[i] + (size_t)c.cin * c.ksize * c.ksize * c.cout;
+    }
+    tt->dy_hi = tt->pool + off_dy; tt->dy_lo = tt->dy_hi + dy_el;
+    float* f = reinterpret_cast<float*>(tt->pool + off_f);
+    tt->wf_scale = f; f += nco; tt->wf_unscale = f; f += nco;
+    tt->wd_scale = f; f += nci; tt->wd_unscale = f; f += nci;
+    tt->dg_unscale = f; f += 512; tt->ones = f; f += 512; tt->zeros = f; f += 512;
+    tt->dy_max = reinterpret_cast<unsigned*>(f); f += 64;
+    tt->dw_packed = f; tt->dw_elems = dw_el;
+    std::vector<float> one(512, 1.f);
+    STRAPS_CUDA(cudaMemcpy(tt->ones, one.data(), 512 * sizeof(float), cudaMemcpyHostToDevice));
+    STRAPS_CUDA(cudaMemset(tt->zeros, 0, 512 * sizeof(float)));
+    STRAPS_CUDA(cudaMemset(tt->dy_max, 0, sizeof(unsigned)));
+    t->train = tt;
+  }
+  TcTrain* tt = t->train;
+  // forward weights of this step (the optimiser has changed them): BN scale not folded
+  for (int i = 0; i < NCONV; ++i) {
+    const ConvSpec& c = r->conv[i];
+    const size_t total = (size_t)c.cout * c.k_eff;
+    w_rowscale_kernel<<<c.cout, 256, 0, st>>>(c.w_oihw, tt->ones, c.cin * c.ksize * c.ksize, tt->wf_scale + t->ch_off[i],
+                                             tt->wf_unscale + t->ch_off[i]);
+    STRAPS_LAUNCH_CHECK();
+    pack_w_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c.w_oihw, tt->ones, tt->wf_scale + t->ch_off[i], c.cout, c.cin, c.ksize,
+                                                                     i == 0, c.k_eff, tt->wf_hi[i], tt->wf_lo[i]);
+    STRAPS_LAUNCH_CHECK();
+  }
+  if (tt->fwd_maps.find(B) == tt->fwd_maps.end()) {
+    std::vector<TcLayerMaps> fm(NCONV), dm(NCONV);
+    for (int i = 0; i < NCONV; ++i) {
+      const ConvSpec& c = r->conv[i];
+      __half* a_hi = (i == 0) ? t->xp : tt->plane_hi[c.in_buf];
+      __half* a_lo = (i == 0) ? t->xp + t->xp_plane : tt->plane_lo[c.in_buf];
+      STRAPS_CHECK(a_hi && a_lo, "tc_train_begin: conv %d has no input planes", i);
+      if (build_layer_maps(t, geom_fwd(c, i), B, a_hi, a_lo, tt->wf_hi[i], tt->wf_lo[i], fm[i])) return 1;
+      if (i > 0 && build_layer_maps(t, geom_dgrad(c), B, tt->dy_hi, tt->dy_lo, tt->wd_hi[i], tt->wd_lo[i], dm[i])) return 1;
+    }
+    std::vector<TcLayerMaps> wm(NCONV);
+    for (int i = 0; i < NCONV; ++i) {
+      const ConvSpec& c = r->conv[i];
+      __half* x_hi = (i == 0) ? t->xp : tt->plane_hi[c.in_buf];
+      __half* x_lo = (i == 0) ? t->xp + t->xp_plane : tt->plane_lo[c.in_buf];
+      cuuint32_t es1[4] = {1, 1, 1, 1};
+      if (i == 0) {
+        cuuint64_t dims[4] = {(cuuint64_t)6 * XP_W * XP_C + C1_KROW, 128, 128, (cuuint64_t)B};
+        cuuint64_t str[3] = {2 * XP_C * 2, (cuuint64_t)2 * XP_W * XP_C * 2, (cuuint64_t)XP_H * XP_W * XP_C * 2};
+        cuuint32_t box[4] = {64, 64, 1, 1};
+        if (encode(t, &wm[i].a_hi, x_hi, 4, dims, str, box, es1)) return 1;
+        if (encode(t, &wm[i].a_lo, x_lo, 4, dims, str, box, es1)) return 1;
+      } else {
+        const int wb = c.wout < 64 ? c.wout : 64, hb = 64 / wb;      // 64 output pixels = hb rows of wb
+        STRAPS_CHECK(hb <= c.hout && (c.hout * c.wout) % 64 == 0, "weight-gradient tiling: unsupported output size %dx%d", c.hout, c.wout);
+        cuuint64_t dims[4] = {(cuuint64_t)c.cin, (cuuint64_t)c.win, (cuuint64_t)c.hin, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)c.cin * 2, (cuuint64_t)c.win * c.cin * 2, (cuuint64_t)c.hin * c.win * c.cin * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(wb * c.stride), (cuuint32_t)(hb * c.stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
+        if (encode(t, &wm[i].a_hi, x_hi, 4, dims, str, box, es)) return 1;
+        if (encode(t, &wm[i].a_lo, x_lo, 4, dims, str, box, es)) return 1;
+      }
+      cuuint64_t ddims[2] = {(cuuint64_t)c.cout, (cuuint64_t)B * c.hout * c.wout};
+      cuuint64_t dstr[1] = {(cuuint64_t)c.cout * 2};
+      cuuint32_t dbox[2] = {64, 64};
+      if (encode(t, &wm[i].w_hi, tt->dy_hi, 2, ddims, dstr, dbox, es1)) return 1;
+      if (encode(t, &wm[i].w_lo, tt->dy_lo, 2, ddims, dstr, dbox, es1)) return 1;
+    }
+    tt->fwd_maps.emplace(B, std::move(fm));
+    tt->dg_maps.emplace(B, std::move(dm));
+    tt->wg_maps.emplace(B, std::move(wm));
+  }
+  return 0;
+}
+
+int tc_train_pack_input(straps_regressor* r, const float* x, int B, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  pack_input_tc_kernel<<<dim3(IMG, B), 256, 0, st>>>(x, r->c_in, t->xp, t->xp + t->xp_plane);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+// padded split planes of the conv1 input -> fp32 NHWC [B,256,256,c_in_pad] (what the fp32 CUDA-core conv1 weight gradient reads);
+// only used when fp32 gradients are requested after a tensor-core forward
+__global__ void unsplit_input_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int c_pad, float* __restrict__ out, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % c_pad);
+  size_t t = i / c_pad;
+  const int w = (int)(t % IMG); t /= IMG;
+  const int h = (int)(t % IMG);
+  const size_t b = t / IMG;
+  float v = 0.f;
+  if (c < XP_C) {
+    const size_t s = ((b * XP_H + h + 3) * XP_W + w + 3) * XP_C + c;
+    v = __half2float(hi[s]) + __half2float(lo[s]);
+  }
+  out[i] = v;
+}
+int tc_train_unpack_input(straps_regressor* r, int B, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  const size_t total = (size_t)B * IMG * IMG * r->c_in_pad;
+  unsplit_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t->xp, t->xp + t->xp_plane, r->c_in_pad, act_ptr(r, r->buf_xin), total);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+__half* tc_train_plane(straps_regressor* r, int buf, int lo) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  if (!t || !t->train || buf < 0) return nullptr;
+  return lo ? t->train->plane_lo[buf] : t->train->plane_hi[buf];
+}
+
+int tc_train_split_act(straps_regressor* r, int buf, int B, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  TcTrain* tt = t->train;
+  STRAPS_CHECK(tt && tt->plane_hi[buf], "tc_train_split_act: buffer %d has no planes", buf);
+  const ActBuf& b = r->bufs[buf];
+  const long long n4 = (long long)B * b.h * b.w * b.c / 4;
+  split_scaled_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(act_ptr(r, buf), nullptr, n4, b.c, b.h, b.w, 0, tt->plane_hi[buf],
+                                                                  tt->plane_lo[buf], nullptr, 0, nullptr);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc_train_conv_fwd(straps_regressor* r, int ci, int B, float* raw, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  TcTrain* tt = t->train;
+  const ConvSpec& c = r->conv[ci];
+  TcConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.shift = tt->zeros;
+  p.unscale = tt->wf_unscale + t->ch_off[ci];
+  p.out_f32 = raw;
+  return run_tc(t, geom_fwd(c, ci), tt->fwd_maps.at(B)[ci], p, B, st);
+}
+
+int tc_train_pack_dgrad(straps_regressor* r, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  TcTrain* tt = t->train;
+  STRAPS_CHECK(tt, "tc_train_pack_dgrad: no tensor-core training forward before this backward");
+  for (int i = 1; i < NCONV; ++i) {
+    const ConvSpec& c = r->conv[i];
+    const int kk = c.ksize * c.ksize;
+    w_colscale_kernel<<<c.cin, 256, 0, st>>>(c.w_oihw, c.cout, c.cin, kk, tt->wd_scale + tt->wd_off[i], tt->wd_unscale + tt->wd_off[i]);
+    STRAPS_LAUNCH_CHECK();
+    const size_t total = (size_t)c.cin * kk * c.cout;
+    pack_w_dgrad_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c.w_oihw, tt->wd_scale + tt->wd_off[i], c.cout, c.cin, c.ksize,
+                                                                           tt->wd_hi[i], tt->wd_lo[i]);
+    STRAPS_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+unsigned* tc_train_dy_max(straps_regressor* r) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  return (t && t->train) ? t->train->dy_max : nullptr;
+}
+
+// dy: fp32 NHWC [B,hout,wout,cout] whose max |.| bits are in *dy_max  ->  scaled split planes (plain, or zero-upsampled x2 for the
+// data gradient of a stride-2 conv); also publishes the data gradient's epilogue scales
+int tc_train_split_dy(straps_regressor* r, int ci, int B, const float* dy, int up, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  TcTrain* tt = t->train;
+  const ConvSpec& c = r->conv[ci];
+  if (up) {
+    STRAPS_CHECK(c.stride == 2 && c.hin == 2 * c.hout && c.win == 2 * c.wout, "tc_train_split_dy: unsupported stride");
+    const size_t n = (size_t)B * c.hin * c.win * c.cout;
+    STRAPS_CUDA(cudaMemsetAsync(tt->dy_hi, 0, n * sizeof(__half), st));
+    STRAPS_CUDA(cudaMemsetAsync(tt->dy_lo, 0, n * sizeof(__half), st));
+  }
+  const long long n4 = (long long)B * c.hout * c.wout * c.cout / 4;
+  split_scaled_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dy, tt->dy_max, n4, c.cout, c.hout, c.wout, up, tt->dy_hi, tt->dy_lo,
+                                                                  ci > 0 ? tt->wd_unscale + tt->wd_off[ci] : nullptr, ci > 0 ? c.cin : 0,
+                                                                  ci > 0 ? tt->dg_unscale : nullptr);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+// gin = dgrad(split dY) (+ add)
+int tc_train_conv_dgrad(straps_regressor* r, int ci, int B, const float* add, float* gin, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  TcTrain* tt = t->train;
+  const ConvSpec& c = r->conv[ci];
+  TcConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.shift = tt->zeros;
+  p.unscale = tt->dg_unscale;
+  p.out_f32 = gin;
+  p.res_f32 = add;
+  return run_tc(t, geom_dgrad(c), tt->dg_maps.at(B)[ci], p, B, st);
+}
+
+template <int BN>
+static int launch_wgrad_tc(const TcLayerMaps& m, const WgParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = WgCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    STRAPS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int items = p.n_mtiles * p.n_ntiles * p.splits;
+  wgrad_tc_kernel<BN><<<items < num_sms ? items : num_sms, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w_hi, m.w_lo, p);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+// dw_oihw = wgrad(X planes of the forward, plain split dY of tc_train_split_dy)
+int tc_train_conv_wgrad(straps_regressor* r, int ci, int B, float* dw_oihw, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  TcTrain* tt = t->train;
+  const ConvSpec& c = r->conv[ci];
+  const int bn = c.cout == 64 ? 64 : 128;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.nchunks = c.k_eff / 64;
+  p.n_mtiles = (p.nchunks + 1) / 2;
+  p.n_ntiles = c.cout / bn;
+  p.ktiles = (int)((long long)B * c.hout * c.wout / 64);
+  const int tiles = p.n_mtiles * p.n_ntiles;
+  int splits = std::min(std::max(1, p.ktiles / 4), (2 * t->num_sms + tiles - 1) / tiles);
+  int kt_max = 32;     // <= 128 MMAs per TMEM accumulation chain (the accumulator truncates); longer chains measured no faster
+  { const char* e = getenv("STRAPS_WG_KT"); if (e && atoi(e) > 0) kt_max = atoi(e); }
+  splits = std::max(splits, (p.ktiles + kt_max - 1) / kt_max);
+  p.kt_per = (p.ktiles + splits - 1) / splits;
+  p.splits = (p.ktiles + p.kt_per - 1) / p.kt_per;
+  p.conv1 = (ci == 0);
+  p.cchunks = c.cin / 64; p.kw_count = c.ksize; p.stride = c.stride; p.pad = c.pad;
+  p.hw_out = c.hout * c.wout; p.wout = c.wout;
+  p.k_eff = c.k_eff;
+  p.dw = tt->dw_packed;
+  STRAPS_CUDA(cudaMemsetAsync(tt->dw_packed, 0, (size_t)c.cout * c.k_eff * sizeof(float), st));
+  const TcLayerMaps& m = tt->wg_maps.at(B)[ci];
+  if (bn == 64 ? launch_wgrad_tc<64>(m, p, t->num_sms, st) : launch_wgrad_tc<128>(m, p, t->num_sms, st)) return 1;
+  const size_t total = (size_t)c.cout * c.cin * c.ksize * c.ksize;
+  unpack_dw_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tt->dw_packed, tt->dy_max, c.cout, c.cin, c.ksize, ci == 0, c.k_eff, dw_oihw);
   STRAPS_LAUNCH_CHECK();
   return 0;
 }

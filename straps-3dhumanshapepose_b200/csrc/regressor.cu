@@ -237,7 +237,7 @@ extern "C" int straps_regressor_create(straps_regressor_t** out, int c_in, int m
   STRAPS_CHECK(max_batch >= 1 && max_batch <= 4096, "straps_regressor_create: max_batch=%d outside [1,4096]", max_batch);
   straps_regressor* r = new straps_regressor();
   r->c_in = c_in; r->c_in_pad = (c_in + 7) / 8 * 8; r->max_batch = max_batch;
-  r->ws = nullptr; r->ws_bytes = 0; r->wpool = nullptr; r->tc = nullptr; r->loaded = 0; r->last_mode = -1;
+  r->ws = nullptr; r->ws_bytes = 0; r->wpool = nullptr; r->tc = nullptr; r->loaded = 0; r->last_mode = -1; r->dirty_bn = r->dirty_simt = r->dirty_tc = 1;
   r->train = nullptr; r->ief = nullptr;
   // activation buffers (NHWC)
   r->buf_xin = add_buf(r, "", IMG, IMG, 32);        // sized for the widest packed-input layout either mode uses
@@ -334,22 +334,49 @@ extern "C" int straps_regressor_load(straps_regressor_t* r, const float* const* 
     ConvSpec& c = r->conv[i];
     STRAPS_CHECK(conv_w[i] && bn[4 * i] && bn[4 * i + 1] && bn[4 * i + 2] && bn[4 * i + 3],
                  "straps_regressor_load: null tensor for conv %d (%s)", i, c.name.c_str());
-    const int total = c.ksize * c.ksize * c.cin_pad * c.cout;
-    pack_w_simt_kernel<<<ceil_div(total, 256), 256, 0, st>>>(conv_w[i], c.cout, c.cin, c.cin_pad, c.ksize, c.w_simt);
-    STRAPS_LAUNCH_CHECK();
-    fold_bn_kernel<<<ceil_div(c.cout, 128), 128, 0, st>>>(bn[4 * i], bn[4 * i + 1], bn[4 * i + 2], bn[4 * i + 3], c.cout,
-                                                         c.scale, c.shift);
-    STRAPS_LAUNCH_CHECK();
     c.w_oihw = conv_w[i];
     c.gamma = bn[4 * i]; c.beta = bn[4 * i + 1];
     c.rmean = const_cast<float*>(bn[4 * i + 2]); c.rvar = const_cast<float*>(bn[4 * i + 3]);
   }
   for (int i = 0; i < 3; ++i) { r->fc_w[i] = fc_w[i]; r->fc_b[i] = fc_b[i]; }
   if (ief_pack(r, fc_w, fc_b, init_params, st)) return 1;
-  if (tc_pack(r, conv_w, st)) return 1;
+  // The convolution weights are only REFERENCED here: the packed inference copies (folded BatchNorm, fp32 / fp16-split layouts)
+  // are rebuilt by the first forward that needs them, so a training loop -- which reloads after every optimiser step and packs
+  // its own un-folded copies -- does not pay for them.  The tensors must stay alive and in place until the next load.
+  r->dirty_bn = r->dirty_simt = r->dirty_tc = 1;
   r->loaded = 1;
   return 0;
 }
+
+namespace straps {
+int ensure_packed(straps_regressor* r, int conv_mode, int need_folded_bn, cudaStream_t st) {
+  if (need_folded_bn && r->dirty_bn) {
+    for (int i = 0; i < NCONV; ++i) {
+      ConvSpec& c = r->conv[i];
+      fold_bn_kernel<<<ceil_div(c.cout, 128), 128, 0, st>>>(c.gamma, c.beta, c.rmean, c.rvar, c.cout, c.scale, c.shift);
+      STRAPS_LAUNCH_CHECK();
+    }
+    r->dirty_bn = 0;
+    r->dirty_tc = 1;      // the tensor-core copy folds the BN scale into the weights
+  }
+  if (conv_mode == STRAPS_CONV_FP32_SIMT && r->dirty_simt) {
+    for (int i = 0; i < NCONV; ++i) {
+      ConvSpec& c = r->conv[i];
+      const int total = c.ksize * c.ksize * c.cin_pad * c.cout;
+      pack_w_simt_kernel<<<ceil_div(total, 256), 256, 0, st>>>(c.w_oihw, c.cout, c.cin, c.cin_pad, c.ksize, c.w_simt);
+      STRAPS_LAUNCH_CHECK();
+    }
+    r->dirty_simt = 0;
+  }
+  if (conv_mode == STRAPS_CONV_F16X3_TC && need_folded_bn && r->dirty_tc) {
+    const float* w[NCONV];
+    for (int i = 0; i < NCONV; ++i) w[i] = r->conv[i].w_oihw;
+    if (tc_pack(r, w, st)) return 1;
+    r->dirty_tc = 0;
+  }
+  return 0;
+}
+}  // namespace straps
 
 namespace straps {
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
@@ -413,6 +440,8 @@ extern "C" int straps_encoder_forward(straps_regressor_t* r, const float* x, int
   STRAPS_CHECK(batch >= 1 && batch <= r->max_batch, "straps_encoder_forward: batch %d outside [1,%d]", batch, r->max_batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   r->last_mode = conv_mode;
+  STRAPS_CHECK(conv_mode == STRAPS_CONV_FP32_SIMT || conv_mode == STRAPS_CONV_F16X3_TC, "straps_encoder_forward: unknown conv_mode %d", conv_mode);
+  if (ensure_packed(r, conv_mode, 1, st)) return 1;
   if (conv_mode == STRAPS_CONV_FP32_SIMT) return encoder_forward_simt(r, x, batch, feat, st);
   if (conv_mode == STRAPS_CONV_F16X3_TC) return tc_encoder_forward(r, x, batch, feat, st);
   STRAPS_CHECK(false, "straps_encoder_forward: unknown conv_mode %d", conv_mode);
@@ -446,6 +475,15 @@ extern "C" int straps_regressor_forward(straps_regressor_t* r, const float* x, i
 extern "C" int straps_encoder_read_activation(straps_regressor_t* r, const char* name, int batch, float* out, int64_t* n,
                                               void* stream) {
   STRAPS_CHECK(r && name && out, "straps_encoder_read_activation: null argument");
+  if (std::string(name) == "grad:conv1") {   // parity hook: dY of conv1 (the last raw-output gradient the encoder backward produced)
+    const float* g = train_last_draw(r);
+    STRAPS_CHECK(g, "straps_encoder_read_activation: no encoder backward has run");
+    const size_t total = (size_t)batch * 64 * 128 * 128;
+    if (n) *n = (int64_t)total;
+    nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, 64, 128, 128, out, total);
+    STRAPS_LAUNCH_CHECK();
+    return 0;
+  }
   int id = -1;
   for (size_t i = 0; i < r->bufs.size(); ++i)
     if (!r->bufs[i].name.empty() && r->bufs[i].name == name) id = (int)i;

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "../../include/straps_b200.h"
+#include <cuda_fp16.h>
 #include <vector>
 #include <string>
 
@@ -48,6 +49,17 @@ struct ConvArgs {
   int transposed;      // 1 = data-gradient gather (rows are input pixels, `in` is dY)
 };
 
+// 2-term fp16 split used by the tensor-core path (conv_tc.cu): x = hi + lo
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  lo = __float2half_rn(v - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t pack_f16(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+__device__ __forceinline__ float f16lo_to_f(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
+__device__ __forceinline__ float f16hi_to_f(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
 struct ActBuf {
   std::string name;   // "" = internal
   int h, w, c;        // NHWC per body
@@ -76,6 +88,7 @@ struct straps_regressor {
   const float* fc_b[3];
   int loaded;
   int last_mode;
+  int dirty_bn, dirty_simt, dirty_tc;   // inference copies (folded BN, packed conv weights) are rebuilt lazily after a load
 };
 
 namespace straps {
@@ -84,16 +97,30 @@ int ief_create(straps_regressor* r);
 void ief_destroy(straps_regressor* r);
 int ief_pack(straps_regressor* r, const float* const* fc_w, const float* const* fc_b, const float* init, cudaStream_t st);
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+int ensure_packed(straps_regressor* r, int conv_mode, int need_folded_bn, cudaStream_t st);   // lazy repack of the inference weight copies
 int launch_nchw_to_nhwc(straps_regressor* r, const float* x, int B, cudaStream_t st);
 int launch_maxpool(straps_regressor* r, int B, cudaStream_t st);
 int launch_avgpool(straps_regressor* r, int B, float* feat, cudaStream_t st);
 int ief_launch_train(const straps_regressor* r, const float* feat, int batch, int iters, float* params, float* saved, cudaStream_t st);
 void train_destroy(straps_regressor* r);
+const float* train_last_draw(const straps_regressor* r);   // scratch holding the last d(raw conv output) of the backward (conv1's)
 // tensor-core encoder (conv_tc.cu)
 int tc_create(straps_regressor* r);
 void tc_destroy(straps_regressor* r);
 int tc_pack(straps_regressor* r, const float* const* conv_w, cudaStream_t st);
 int tc_encoder_forward(straps_regressor* r, const float* x, int batch, float* feat, cudaStream_t st);
 int tc_read_activation(straps_regressor* r, int buf, int batch, float* out, cudaStream_t st);
+// tensor-core training path (conv_tc.cu): forward convs with un-folded weights and data gradients as flipped-tap convolutions
+int tc_train_begin(straps_regressor* r, int batch, cudaStream_t st);                      // workspace, forward weight pack, tensor maps
+int tc_train_pack_input(straps_regressor* r, const float* x, int batch, cudaStream_t st);
+int tc_train_unpack_input(straps_regressor* r, int batch, cudaStream_t st);               // conv1 input planes -> fp32 NHWC input buffer
+__half* tc_train_plane(straps_regressor* r, int buf, int lo);                              // split planes of an activation buffer (or null)
+int tc_train_split_act(straps_regressor* r, int buf, int batch, cudaStream_t st);         // fp32 activation buffer -> its split planes
+int tc_train_conv_fwd(straps_regressor* r, int ci, int batch, float* raw, cudaStream_t st);
+int tc_train_pack_dgrad(straps_regressor* r, cudaStream_t st);
+int tc_train_split_dy(straps_regressor* r, int ci, int batch, const float* dy, int upsample, cudaStream_t st);   // scaled split of dY
+int tc_train_conv_wgrad(straps_regressor* r, int ci, int batch, float* dw_oihw, cudaStream_t st);                // needs the plain split
+unsigned* tc_train_dy_max(straps_regressor* r);                                            // device word: bits of max |dY| (atomicMax target)
+int tc_train_conv_dgrad(straps_regressor* r, int ci, int batch, const float* add, float* gin, cudaStream_t st);  // needs the split
 inline float* act_ptr(const straps_regressor* r, int buf) { return reinterpret_cast<float*>(r->ws + r->bufs[buf].offset); }
 }  // namespace straps

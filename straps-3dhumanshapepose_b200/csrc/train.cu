@@ -16,6 +16,7 @@
 //   IEF backward                  : generic 32x32 SIMT GEMM (all four transpose combinations) + ReLU masks + column sums
 // HBM layout: NHWC fp32 activations (regressor.cu); every conv keeps its pre-BN output `raw` for the backward.
 #include "regressor.h"
+#include <cstdlib>
 
 namespace straps {
 
@@ -35,6 +36,8 @@ struct TrainState {
   float* w_dgrad[NCONV];       // [(kh,kw,co)][ci]
   float* dw_packed;            // [(kh,kw,ci_pad)][cout] scratch for the weight gradient (largest conv)
   int last_batch;
+  int mode;                    // STRAPS_CONV_* of the last training forward (the backward follows it)
+  int xin_valid;               // the fp32 NHWC copy of the input (CUDA-core conv1 weight gradient) matches the last forward
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -74,7 +77,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc2, long long np
 // y = (x - mean) * invstd * gamma + beta (+ res) (ReLU)
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ res,
-                                int relu, long long n4, int C, float* __restrict__ y) {
+                                int relu, long long n4, int C, float* __restrict__ y, __half* __restrict__ y_hi,
+                                __half* __restrict__ y_lo) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const int c = (int)((i * 4) % C);
@@ -86,6 +90,12 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
   if (res) { const float4 r = reinterpret_cast<const float4*>(res)[i]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
   if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
   reinterpret_cast<float4*>(y)[i] = o;
+  if (y_hi) {   // tensor-core training path: the next conv reads the 2-term fp16 split
+    __half h[4], l[4];
+    split_f16(o.x, h[0], l[0]); split_f16(o.y, h[1], l[1]); split_f16(o.z, h[2], l[2]); split_f16(o.w, h[3], l[3]);
+    reinterpret_cast<uint2*>(y_hi)[i] = make_uint2(pack_f16(h[0], h[1]), pack_f16(h[2], h[3]));
+    reinterpret_cast<uint2*>(y_lo)[i] = make_uint2(pack_f16(l[0], l[1]), pack_f16(l[2], l[3]));
+  }
 }
 // sums over pixels of dy and dy * xhat, with dy = gout * (act > 0) when act != null.  acc[0..C) = sum dy, acc[C..2C) = sum dy xhat
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ gout, const float* __restrict__ act,
@@ -111,21 +121,54 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     atomicAdd(&acc[C + c], (red[1][0][t] + red[1][1][t]) + (red[1][2][t] + red[1][3][t]));
   }
 }
-// dx = gamma * invstd * (dy - sum_dy/N - xhat * sum_dy_xhat/N);   optionally also writes the masked dy
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ gout, const float* __restrict__ act, const float* __restrict__ x,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ acc, long long npix, int C, float* __restrict__ dx,
-                                    float* __restrict__ masked_out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix * C) return;
-  const int c = (int)(i % C);
-  float dy = gout[i];
-  if (act && !(act[i] > 0.f)) dy = 0.f;
-  if (masked_out) masked_out[i] = dy;
-  const float is = invstd[c];
-  const float xhat = (x[i] - mean[c]) * is;
+// dx = gamma * invstd * (dy - sum_dy/N - xhat * sum_dy_xhat/N);   optionally also writes the masked dy and the max |dx|.
+// 4 float4 per thread; n4 = npix * C / 4
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ gout, const float* __restrict__ act,
+                                                           const float* __restrict__ x, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ acc, long long npix, int C, float* __restrict__ dx,
+                                                           float* __restrict__ masked_out, unsigned* __restrict__ maxbits) {
+  __shared__ unsigned smax[8];
+  const long long n4 = npix * C / 4;
   const float inv_n = 1.f / (float)npix;
-  dx[i] = gamma[c] * is * (dy - acc[c] * inv_n - xhat * acc[C + c] * inv_n);
+  float m = 0.f;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const long long i = ((long long)blockIdx.x * 4 + it) * 256 + threadIdx.x;
+    if (i >= n4) break;
+    const int c = (int)((i * 4) % C);
+    float4 dy = reinterpret_cast<const float4*>(gout)[i];
+    if (act) {
+      const float4 a = reinterpret_cast<const float4*>(act)[i];
+      if (!(a.x > 0.f)) dy.x = 0.f;
+      if (!(a.y > 0.f)) dy.y = 0.f;
+      if (!(a.z > 0.f)) dy.z = 0.f;
+      if (!(a.w > 0.f)) dy.w = 0.f;
+    }
+    if (masked_out) reinterpret_cast<float4*>(masked_out)[i] = dy;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 s0 = *reinterpret_cast<const float4*>(acc + c), s1 = *reinterpret_cast<const float4*>(acc + C + c);
+    float4 r;
+    r.x = ga.x * is.x * (dy.x - s0.x * inv_n - ((xv.x - mu.x) * is.x) * s1.x * inv_n);
+    r.y = ga.y * is.y * (dy.y - s0.y * inv_n - ((xv.y - mu.y) * is.y) * s1.y * inv_n);
+    r.z = ga.z * is.z * (dy.z - s0.z * inv_n - ((xv.z - mu.z) * is.z) * s1.z * inv_n);
+    r.w = ga.w * is.w * (dy.w - s0.w * inv_n - ((xv.w - mu.w) * is.w) * s1.w * inv_n);
+    reinterpret_cast<float4*>(dx)[i] = r;
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(r.x), fabsf(r.y))), fmaxf(fabsf(r.z), fabsf(r.w)));
+  }
+  if (maxbits) {   // max |dx| for the power-of-two scale of the tensor-core gradients (non-negative floats order like their bits)
+    const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned t = smax[0];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) t = max(t, smax[k]);
+      if (t) atomicMax(maxbits, t);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -382,6 +425,11 @@ static int train_ensure(straps_regressor* r) {
   return 0;
 }
 
+const float* train_last_draw(const straps_regressor* r) {
+  const TrainState* t = static_cast<const TrainState*>(r->train);
+  return t ? t->draw : nullptr;
+}
+
 void train_destroy(straps_regressor* r) {
   TrainState* t = static_cast<TrainState*>(r->train);
   if (!t) return;
@@ -391,6 +439,7 @@ void train_destroy(straps_regressor* r) {
 }
 
 static int conv_raw(straps_regressor* r, TrainState* t, int ci, int B, cudaStream_t st) {
+  if (t->mode == STRAPS_CONV_F16X3_TC) return tc_train_conv_fwd(r, ci, B, t->raw[ci], st);
   const ConvSpec& c = r->conv[ci];
   ConvArgs a;
   a.in = act_ptr(r, c.in_buf); a.w = c.w_simt; a.scale = t->ones; a.shift = t->zeros; a.res = nullptr; a.out = t->raw[ci];
@@ -399,9 +448,13 @@ static int conv_raw(straps_regressor* r, TrainState* t, int ci, int B, cudaStrea
   return launch_conv_simt(a, st);
 }
 
-static int bn_forward(straps_regressor* r, TrainState* t, int ci, int B, const float* res, int relu, float* out, int update_running,
+static int bn_forward(straps_regressor* r, TrainState* t, int ci, int B, const float* res, int relu, int out_buf, int update_running,
                       cudaStream_t st) {
   const ConvSpec& c = r->conv[ci];
+  float* out = act_ptr(r, out_buf);
+  const bool tc = t->mode == STRAPS_CONV_F16X3_TC;
+  __half* out_hi = tc ? tc_train_plane(r, out_buf, 0) : nullptr;
+  __half* out_lo = tc ? tc_train_plane(r, out_buf, 1) : nullptr;
   const long long npix = (long long)B * c.hout * c.wout;
   const int chunks = (int)std::min<long long>(1024, (npix + 63) / 64);
   STRAPS_CUDA(cudaMemsetAsync(t->dstat, 0, 1024 * sizeof(double), st));
@@ -416,7 +469,7 @@ static int bn_forward(straps_regressor* r, TrainState* t, int ci, int B, const f
   STRAPS_LAUNCH_CHECK();
   const long long n4 = npix * c.cout / 4;
   bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(t->raw[ci], t->mean[ci], t->invstd[ci], c.gamma, c.beta, res, relu, n4,
-                                                              c.cout, out);
+                                                              c.cout, out, out_hi, out_lo);
   STRAPS_LAUNCH_CHECK();
   return 0;
 }
@@ -429,18 +482,30 @@ static int bn_backward(straps_regressor* r, TrainState* t, int ci, int B, const 
   const long long npix = (long long)B * c.hout * c.wout;
   const int chunks = (int)std::min<long long>(1024, (npix + 63) / 64);
   STRAPS_CUDA(cudaMemsetAsync(t->fstat, 0, 1024 * sizeof(float), st));
+  unsigned* maxbits = (t->mode == STRAPS_CONV_F16X3_TC) ? tc_train_dy_max(r) : nullptr;
+  if (maxbits) STRAPS_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(unsigned), st));
   bn_bwd_reduce_kernel<<<dim3(chunks, c.cout / 64), 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], npix, c.cout, t->fstat);
   STRAPS_LAUNCH_CHECK();
-  const long long n = npix * c.cout;
-  bn_bwd_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], c.gamma, t->fstat, npix,
-                                                                 c.cout, t->draw, masked_out);
+  const long long n4 = npix * c.cout / 4;
+  bn_bwd_apply_kernel<<<(unsigned)((n4 + 1023) / 1024), 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], c.gamma, t->fstat, npix,
+                                                                 c.cout, t->draw, masked_out, maxbits);
   STRAPS_LAUNCH_CHECK();
   STRAPS_CUDA(cudaMemcpyAsync(dbeta, t->fstat, c.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
   STRAPS_CUDA(cudaMemcpyAsync(dgamma, t->fstat + c.cout, c.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
+static bool wgrad_on_tc() {
+  const char* e = getenv("STRAPS_WGRAD");      // "simt" keeps the fp32 CUDA-core weight gradient in tensor-core mode (debugging)
+  return !(e && e[0] == 's');
+}
+
 static int conv_wgrad(straps_regressor* r, TrainState* t, int ci, int B, float* dw_oihw, cudaStream_t st) {
+  if (t->mode == STRAPS_CONV_F16X3_TC) {
+    // the plain split of dY serves the weight gradient and (stride-1 convs) the data gradient that follows
+    if (tc_train_split_dy(r, ci, B, t->draw, 0, st)) return 1;
+    if (wgrad_on_tc()) return tc_train_conv_wgrad(r, ci, B, dw_oihw, st);
+  }
   const ConvSpec& c = r->conv[ci];
   const size_t nw = (size_t)c.ksize * c.ksize * c.cin_pad * c.cout;
   STRAPS_CUDA(cudaMemsetAsync(t->dw_packed, 0, nw * sizeof(float), st));
@@ -462,6 +527,10 @@ static int conv_wgrad(straps_regressor* r, TrainState* t, int ci, int B, float* 
 
 // gin[in_buf] (+)= dgrad(t->draw);  add != null -> that tensor is added (identity / other-branch gradient)
 static int conv_dgrad(straps_regressor* r, TrainState* t, int ci, int B, const float* add, float* gin, cudaStream_t st) {
+  if (t->mode == STRAPS_CONV_F16X3_TC) {   // always preceded by conv_wgrad of the same conv (same dY)
+    if (r->conv[ci].stride == 2 && tc_train_split_dy(r, ci, B, t->draw, 1, st)) return 1;
+    return tc_train_conv_dgrad(r, ci, B, add, gin, st);
+  }
   const ConvSpec& c = r->conv[ci];
   ConvArgs a;
   a.in = t->draw; a.w = t->w_dgrad[ci]; a.scale = t->ones; a.shift = t->zeros; a.res = add; a.out = gin;
@@ -474,46 +543,69 @@ static int conv_dgrad(straps_regressor* r, TrainState* t, int ci, int B, const f
 
 using namespace straps;
 
-extern "C" int straps_encoder_train_forward(straps_regressor_t* r, const float* x, int batch, int update_running_stats, float* feat,
-                                            void* stream) {
+extern "C" int straps_encoder_train_forward(straps_regressor_t* r, const float* x, int batch, int update_running_stats, int conv_mode,
+                                            float* feat, void* stream) {
   STRAPS_CHECK(r && x && feat, "straps_encoder_train_forward: null argument");
   STRAPS_CHECK(r->loaded, "straps_encoder_train_forward: weights not loaded");
   STRAPS_CHECK(batch >= 2 && batch <= r->max_batch, "straps_encoder_train_forward: batch %d outside [2,%d]", batch, r->max_batch);
   if (train_ensure(r)) return 1;
   TrainState* t = static_cast<TrainState*>(r->train);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  STRAPS_CHECK(conv_mode == STRAPS_CONV_FP32_SIMT || conv_mode == STRAPS_CONV_F16X3_TC, "straps_encoder_train_forward: unknown conv_mode %d",
+               conv_mode);
   t->last_batch = batch;
-  r->last_mode = STRAPS_CONV_FP32_SIMT;
-  if (straps::launch_nchw_to_nhwc(r, x, batch, st)) return 1;
+  t->mode = conv_mode;
+  r->last_mode = STRAPS_CONV_FP32_SIMT;   // the activation buffers hold fp32 NHWC in both training modes
+  if (conv_mode == STRAPS_CONV_F16X3_TC) {
+    if (straps::tc_train_begin(r, batch, st)) return 1;
+    if (straps::tc_train_pack_input(r, x, batch, st)) return 1;
+    t->xin_valid = 0;      // rebuilt from the split planes if a CUDA-core weight gradient is requested
+  } else {
+    if (straps::ensure_packed(r, STRAPS_CONV_FP32_SIMT, 0, st)) return 1;
+    if (straps::launch_nchw_to_nhwc(r, x, batch, st)) return 1;
+    t->xin_valid = 1;
+  }
   // stem: conv1 -> bn1 -> relu -> maxpool
   if (conv_raw(r, t, 0, batch, st)) return 1;
-  if (bn_forward(r, t, 0, batch, nullptr, 1, act_ptr(r, r->buf_stem), update_running_stats, st)) return 1;
+  if (bn_forward(r, t, 0, batch, nullptr, 1, r->buf_stem, update_running_stats, st)) return 1;
   if (straps::launch_maxpool(r, batch, st)) return 1;
+  if (conv_mode == STRAPS_CONV_F16X3_TC && straps::tc_train_split_act(r, r->buf_pool, batch, st)) return 1;
   int i = 1;
   while (i < NCONV) {
     const bool ds = (i + 2 < NCONV) && r->conv[i + 2].ksize == 1;
     const ConvSpec &c1 = r->conv[i], &c2 = r->conv[i + 1];
     if (conv_raw(r, t, i, batch, st)) return 1;
-    if (bn_forward(r, t, i, batch, nullptr, 1, act_ptr(r, c1.out_buf), update_running_stats, st)) return 1;
+    if (bn_forward(r, t, i, batch, nullptr, 1, c1.out_buf, update_running_stats, st)) return 1;
     if (ds) {
       if (conv_raw(r, t, i + 2, batch, st)) return 1;
-      if (bn_forward(r, t, i + 2, batch, nullptr, 0, act_ptr(r, r->conv[i + 2].out_buf), update_running_stats, st)) return 1;
+      if (bn_forward(r, t, i + 2, batch, nullptr, 0, r->conv[i + 2].out_buf, update_running_stats, st)) return 1;
     }
     if (conv_raw(r, t, i + 1, batch, st)) return 1;
-    if (bn_forward(r, t, i + 1, batch, act_ptr(r, c2.res_buf), 1, act_ptr(r, c2.out_buf), update_running_stats, st)) return 1;
+    if (bn_forward(r, t, i + 1, batch, act_ptr(r, c2.res_buf), 1, c2.out_buf, update_running_stats, st)) return 1;
     i += ds ? 3 : 2;
   }
   return straps::launch_avgpool(r, batch, feat, st);
 }
 
 // d_conv_w[20]: OIHW gradients (state_dict order); d_bn[40]: (dgamma, dbeta) per BatchNorm.  All PyTorch-owned, overwritten.
-extern "C" int straps_encoder_backward(straps_regressor_t* r, const float* dfeat, int batch, float* const* d_conv_w, float* const* d_bn,
-                                       void* stream) {
+extern "C" int straps_encoder_backward(straps_regressor_t* r, const float* dfeat, int batch, int conv_mode, float* const* d_conv_w,
+                                       float* const* d_bn, void* stream) {
   STRAPS_CHECK(r && dfeat && d_conv_w && d_bn, "straps_encoder_backward: null argument");
   TrainState* t = static_cast<TrainState*>(r->train);
   STRAPS_CHECK(t && t->last_batch == batch, "straps_encoder_backward: no matching straps_encoder_train_forward (batch %d)", batch);
+  STRAPS_CHECK(conv_mode == -1 || conv_mode == t->mode || (conv_mode == STRAPS_CONV_FP32_SIMT && t->mode == STRAPS_CONV_F16X3_TC),
+               "straps_encoder_backward: conv_mode %d is not available after a forward in mode %d", conv_mode, t->mode);
+  // the fp32 CUDA-core gradients can run on the activations a tensor-core forward saved (they are fp32 in both modes)
+  struct ModeGuard { TrainState* t; int saved; ~ModeGuard() { t->mode = saved; } } guard{t, t->mode};
+  if (conv_mode != -1) t->mode = conv_mode;
+  const bool fp32_wgrad = t->mode == STRAPS_CONV_FP32_SIMT || !wgrad_on_tc();
+  if (fp32_wgrad && !t->xin_valid) {   // the tensor-core forward did not write the fp32 NHWC input the CUDA-core conv1 weight gradient reads
+    if (straps::tc_train_unpack_input(r, batch, static_cast<cudaStream_t>(stream))) return 1;
+    t->xin_valid = 1;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (int i = 1; i < NCONV; ++i) {   // data-gradient weight layout (conv1 needs none)
+  if (t->mode == STRAPS_CONV_F16X3_TC && straps::tc_train_pack_dgrad(r, st)) return 1;
+  for (int i = 1; i < NCONV && t->mode != STRAPS_CONV_F16X3_TC; ++i) {   // data-gradient weight layout (conv1 needs none)
     const ConvSpec& c = r->conv[i];
     const int total = c.ksize * c.ksize * c.cout * c.cin;
     pack_w_dgrad_kernel<<<ceil_div(total, 256), 256, 0, st>>>(c.w_oihw, c.cout, c.cin, c.ksize, t->w_dgrad[i]);

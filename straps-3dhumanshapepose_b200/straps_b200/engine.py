@@ -114,7 +114,7 @@ class RegressorEngine(object):
 class _RegressorTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, handle, x, iters, want, *params):
-        feat = handle.encoder_train_forward(x, update_running_stats=True)
+        feat = handle.encoder_train_forward(x, update_running_stats=True, mode=engine.conv_mode)
         ctx.handle, ctx.iters, ctx.want = handle, iters, want
         ctx.conv_shapes = [tuple(p.shape) for p in params[:20]]
         ctx.bn_channels = [p.shape[0] for p in params[20:40]]

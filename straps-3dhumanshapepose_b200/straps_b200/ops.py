@@ -270,7 +270,7 @@ class RegressorHandle(object):
         return params
 
     # ---- training path ----
-    def encoder_train_forward(self, x, update_running_stats=True):
+    def encoder_train_forward(self, x, update_running_stats=True, mode=DEFAULT_CONV_MODE):
         _need_cuda(x, 'input')
         x = x.contiguous()
         B = x.shape[0]
@@ -278,12 +278,12 @@ class RegressorHandle(object):
             raise StrapsError('encoder input must be [B,%d,256,256], got %s' % (self.c_in, tuple(x.shape)))
         feat = torch.empty((B, 512), dtype=torch.float32, device=x.device)
         with torch.cuda.device(self.device):
-            check(_lib.lib().straps_encoder_train_forward(self._h, _p(x), B, 1 if update_running_stats else 0, _p(feat),
+            check(_lib.lib().straps_encoder_train_forward(self._h, _p(x), B, 1 if update_running_stats else 0, conv_mode_id(mode), _p(feat),
                                                           _stream(self.device)), 'straps_encoder_train_forward')
         return feat
 
-    def encoder_backward(self, dfeat, conv_shapes, bn_channels):
-        """-> (list of 20 OIHW weight gradients, list of 20 (d_weight, d_bias))."""
+    def encoder_backward(self, dfeat, conv_shapes, bn_channels, mode=None):
+        """-> (list of 20 OIHW weight gradients, list of 20 (d_weight, d_bias)).  mode None = the mode of the forward."""
         dfeat = dfeat.contiguous()
         B = dfeat.shape[0]
         dws = [torch.empty(s, dtype=torch.float32, device=self.device) for s in conv_shapes]
@@ -292,7 +292,8 @@ class RegressorHandle(object):
         flat_bn = [t for pair in dbn for t in pair]
         arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         with torch.cuda.device(self.device):
-            check(_lib.lib().straps_encoder_backward(self._h, _p(dfeat), B, arr(dws), arr(flat_bn), _stream(self.device)),
+            check(_lib.lib().straps_encoder_backward(self._h, _p(dfeat), B, -1 if mode is None else conv_mode_id(mode), arr(dws), arr(flat_bn),
+                                                     _stream(self.device)),
                   'straps_encoder_backward')
         return dws, dbn
 
@@ -320,7 +321,7 @@ class RegressorHandle(object):
         return d_feat, dw, db
 
     def read_activation(self, name, batch):
-        shapes = {'stem': (64, 128, 128), 'pool': (64, 64, 64)}
+        shapes = {'stem': (64, 128, 128), 'pool': (64, 64, 64), 'grad:conv1': (64, 128, 128)}
         for L, (c, hw) in enumerate(((64, 64), (128, 32), (256, 16), (512, 8))):
             for blk in range(2):
                 for suffix in ('', '.a', '.ds'):

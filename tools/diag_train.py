@@ -21,7 +21,8 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-for C, B in [(17, 4), (17, 16)]:
+import itertools
+for (C, B), MODE in itertools.product([(17, 4), (17, 16)], os.environ.get('DIAG_MODES', 'fp32_simt,f16x3_tc').split(',')):
     sd = O.make_regressor_state(C, seed=7)
     sdg = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float32 and 'running' not in k else v.clone()) for k, v in sd.items()}
     x = torch.from_numpy(synthetic_inputs.make_proxy_batch(B, C, seed=13))
@@ -31,17 +32,18 @@ for C, B in [(17, 4), (17, 16)]:
     for t in taps.values():
         t.retain_grad()
     (feat_o * g).sum().backward()
-    reg = SingleInputRegressor(C, 18, 3, conv_mode='fp32_simt')
+    reg = SingleInputRegressor(C, 18, 3, conv_mode=MODE)
     reg.load_state_dict(sd)
     reg = reg.to('cuda:0').train()
     feat = reg.image_encoder(x.cuda())
     (feat * g.cuda()).sum().backward()
     torch.cuda.synchronize()
-    print('=== C=%d B=%d  feat fwd err %.2e' % (C, B, rel(feat.detach().cpu(), feat_o.detach())))
+    print('=== %s C=%d B=%d  feat fwd err %.2e' % (MODE, C, B, rel(feat.detach().cpu(), feat_o.detach())))
     eng = reg._engine
     for name, ref in taps.items():
         got = eng.read_activation(name, B).cpu().numpy()
-        print('  act  %-12s %.2e' % (name, rel(got, ref.detach().numpy())))
+        rn = ref.detach().numpy()
+        print('  act  %-12s %.2e   zero-mask mismatches %d of %d' % (name, rel(got, rn), int(((got > 0) != (rn > 0)).sum()), rn.size))
     new = reg.state_dict()
     worst = max(rel(new['image_encoder.' + k].cpu(), v) for k, v in stats.items())
     print('  running stats worst err %.2e' % worst)

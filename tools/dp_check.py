@@ -43,6 +43,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--channels', type=int, default=17)
     ap.add_argument('--oracle-batch', type=int, default=0)
+    ap.add_argument('--conv-mode', default='f16x3_tc', choices=['fp32_simt', 'f16x3_tc'])
     args = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -67,7 +68,7 @@ def main():
     smpl_oracle = O.SmplOracle(add, batch_size=args.batch)
     B, C = args.batch, args.channels
     torch.manual_seed(1234 + rank)          # deliberately different: the broadcast in DataParallelAdam must equalise the replicas
-    reg = SingleInputRegressor(C, 18, 3, conv_mode='fp32_simt').to(dev).train()
+    reg = SingleInputRegressor(C, 18, 3, conv_mode=args.conv_mode).to(dev).train()
     crit = Loss(TASKS, init_loss_weights=W).to(dev)
     smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(dev)
     params = [p for n, p in reg.named_parameters()] + list(crit.parameters())
@@ -133,8 +134,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     if rank == 0:
-        print(json.dumps({'config': 'BASELINE config %d: training step (encoder+IEF+SMPL+multi-task loss, fp32 CUDA-core kernels), '
-                                    'B=%d/GPU, %d GPU(s), one all-reduce of %d fp32 + fused Adam' % (4 if world > 1 else 3, B, world, opt.bucket.numel),
+        print(json.dumps({'config': 'BASELINE config %d: training step (encoder+IEF+SMPL+multi-task loss, conv mode %s), '
+                                    'B=%d/GPU, %d GPU(s), one all-reduce of %d fp32 + fused Adam' % (4 if world > 1 else 3, args.conv_mode, B, world, opt.bucket.numel),
                           'ms_per_step': ms, 'bodies_per_s': world * B / (ms * 1e-3), 'loss0': float(loss), 'checks': ok}))
     if world > 1:
         dist.destroy_process_group()
