@@ -134,7 +134,10 @@ const char* straps_regressor_conv_name(const straps_regressor_t* r, int i);
  *   bn[20*4]    : for each conv's BatchNorm: weight, bias, running_mean, running_var (fp32 [Cout]).
  *   fc_w[3], fc_b[3] : IEF fc1 [512,669], fc2 [512,512], fc3 [157,512] and biases.
  *   init_params : dev [157] initial estimate (models/ief_module.py:31).
- * Eval-mode BN is folded into per-channel scale/shift here.  Asynchronous on `stream`. */
+ * The IEF weights are packed here; the convolution / BatchNorm tensors are REFERENCED, and their inference copies
+ * (eval-mode BN folded into per-channel scale/shift, fp32 or fp16-split weight layouts) are built by the first forward
+ * that needs them -- so every tensor must stay alive and in place until the next straps_regressor_load (the training
+ * path reads and, for running_mean / running_var, writes them directly).  Asynchronous on `stream`. */
 int straps_regressor_load(straps_regressor_t* r, const float* const* conv_w, const float* const* bn,
                           const float* const* fc_w, const float* const* fc_b, const float* init_params,
                           void* stream);
