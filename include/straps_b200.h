@@ -109,6 +109,35 @@ int straps_joints2d_to_heatmaps(const float* joints2d, int batch, int num_joints
 /* utils/label_conversions.py:48-55 -- out[i] = (labels[i] != 0) ? 1 : 0  (fp32 in, fp32 out). */
 int straps_multiclass_to_binary(const float* labels, int64_t n, float* out, void* stream);
 
+/* ---- target side of the synthetic training loop (train/train_synthetic_otf_rendering.py:121-145) ----
+ * smplx.lbs.batch_rodrigues (augmentation/smpl_augmentation.py:55-58, train/...:190,301,322, predict/predict_3D.py:134):
+ * rot_vecs dev [n,3] axis-angle -> R dev [n,3,3]; angle = ||r + 1e-8||. */
+int straps_batch_rodrigues(const float* rot_vecs, int64_t n, float* R, void* stream);
+/* utils/cam_utils.py:40-71 perspective_project_torch: points dev [B,N,3], rotation dev [B,3,3], translation dev [B,3],
+ * cam_K dev [B,3,3] -> out dev [B,N,2] = (K ((R p + t) / (R p + t).z))[:2]. */
+int straps_perspective_project(const float* points, const float* rotation, const float* translation, const float* cam_K,
+                               int batch, int npoints, float* out, void* stream);
+/* The affine part of augmentation/smpl_augmentation.py:6-24 and augmentation/cam_augmentation.py:4-14:
+ * out[r,c] = (noise[r,c] * mul[c] + add[c]) + base[r*base_stride + c], every operation rounded separately (no FMA), i.e.
+ * bit-identical to the reference's torch ops on the same draws.  add may be NULL; base_stride 0 broadcasts one row. */
+int straps_scale_shift(const float* noise, const float* mul, const float* add, const float* base, int64_t base_stride,
+                       int rows, int width, float* out, void* stream);
+
+/* ---- evaluation metrics on the device (metrics/train_loss_and_metrics_tracker.py:102-213,
+ * utils/eval_utils.py:7-85) ----
+ * Per body b: pred/target dev [B,N,3].  `which` selects (bit 0) sum_i ||p_i - t_i||, (bit 1) the same after the scale-and-
+ * translation correction of eval_utils.py:63-85, (bit 2) after the similarity (Procrustes) alignment of eval_utils.py:7-52.
+ * sums: dev double[3] ACCUMULATED into (fp64 atomics; slots of unselected metrics untouched) or NULL; pred_sc / pred_pa:
+ * optional dev [B,N,3] outputs of the corrected / aligned points (what the reference's functions return). */
+int straps_points_metrics(const float* pred, const float* target, int batch, int npoints, int which, double* sums,
+                          float* pred_sc, float* pred_pa, void* stream);
+/* *sum += sum over rows of ||(pred + pred_add) * pred_mul - target||_2 (squared == 0; rows of `dim` floats) or of the squared
+ * differences (squared != 0): joints2D L2 error with utils/joints2d_utils.py:5-10 un-normalisation, pose / shape MSE sums. */
+int straps_rows_metric(const float* pred, const float* target, int64_t rows, int dim, float pred_add, float pred_mul,
+                       int squared, double* sum, void* stream);
+/* dst[i] += scale * src[i], i < n (dev double accumulator; loss sums of the tracker without .item()). */
+int straps_accumulate(const float* src, int n, double scale, double* dst, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Regressor -- replaces models/regressor.py:43-47 = ResNet.forward (models/resnet.py:201-216) +
  * IEFModule.forward (models/ief_module.py:48-64).

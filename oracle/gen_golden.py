@@ -19,6 +19,8 @@ sys.path.insert(0, os.path.join(REPO, 'straps-3dhumanshapepose_b200'))
 
 import ref_harness                      # noqa: E402
 import straps_oracle as O               # noqa: E402
+from golden_inputs import (synth_inputs, metrics_inputs, SYNTH_STD, SYNTH_RANGE, SYNTH_XY_STD, SYNTH_Z_RANGE,   # noqa: E402
+                           ALL_METRICS, ALL_TASKS)
 from straps_b200 import synthetic_assets, synthetic_inputs   # noqa: E402
 
 GOLDEN = os.path.join(REPO, 'tests', 'golden')
@@ -37,6 +39,53 @@ def smpl_inputs(batch, seed):
 
 def checksum(a):
     return float(np.asarray(a, dtype=np.float64).sum())
+
+
+def synth_fixture(ref):
+    I = {k: torch.from_numpy(v) for k, v in synth_inputs().items()}
+    B = I['pose_aa'].shape[0]
+    out = {'in_checksum': np.array([checksum(v.numpy()) for v in I.values()])}
+    std_vec = torch.tensor([SYNTH_STD] * 10)
+    for dist, seed in (('normal', 5), ('uniform', 6)):
+        params = {'augment_shape': True, 'delta_betas_distribution': dist, 'delta_betas_range': SYNTH_RANGE,
+                  'delta_betas_std_vector': std_vec}
+        torch.manual_seed(seed)
+        shape, pose_rm, glob_rm = ref.smpl_augmentation.augment_smpl(I['orig_shape'], I['pose_aa'][:, 3:], I['pose_aa'][:, :3],
+                                                                     I['mean_shape'], params)
+        torch.manual_seed(seed)            # the draw the call above consumed
+        noise = torch.randn(B, 10) if dist == 'normal' else torch.rand(B, 10)
+        out.update({'shape_%s' % dist: shape.numpy(), 'noise_%s' % dist: noise.numpy()})
+    out.update(pose_rotmats=pose_rm.numpy(), glob_rotmats=glob_rm.numpy())
+    torch.manual_seed(7)
+    cam_t = ref.cam_augmentation.augment_cam_t(I['mean_cam_t'], xy_std=SYNTH_XY_STD, delta_z_range=SYNTH_Z_RANGE)
+    torch.manual_seed(7)
+    out.update(aug_cam_t=cam_t.numpy(), noise_xy=torch.randn(B, 2).numpy(), noise_z=torch.rand(B).numpy())
+    K = torch.from_numpy(ref.get_intrinsics_matrix(256, 256, 5000.).astype(np.float32))[None].expand(B, -1, -1)
+    out['proj'] = ref.perspective_project_torch(I['points'], I['cam_R'], I['cam_t'], cam_K=K).numpy()
+    out['proj_default_K'] = ref.perspective_project_torch(I['points'], I['cam_R'], I['cam_t'], focal_length=5000., img_wh=256).numpy()
+    return out
+
+
+def metrics_fixture(ref):
+    pred, target, pr, tr_, losses = metrics_inputs()
+    B = pred['verts'].shape[0]
+    tracker = ref.Tracker(ALL_TASKS, ALL_METRICS, 256, os.path.join(REPO, 'tests', '_scratch', 'ref_tracker_log.pkl'))
+    tracker.initialise_loss_metric_sums()
+    t = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    for split in ('train', 'val'):
+        tracker.update_per_batch(split, torch.tensor(losses['total']), {k: torch.tensor(losses[k]) for k in ALL_TASKS}, t(pred), t(target),
+                                 B, pred_reposed_vertices=torch.from_numpy(pr), target_reposed_vertices=torch.from_numpy(tr_))
+    sums = dict(tracker.loss_metric_sums)
+    tracker.update_per_epoch()
+    out = {'in_checksum': np.array([checksum(pred['verts']), checksum(target['verts']), checksum(pr), checksum(tr_),
+                                    checksum(pred['joints3D']), checksum(target['joints3D'])]),
+           'sum_keys': np.array(sorted(sums)), 'sum_values': np.array([float(sums[k]) for k in sorted(sums)], dtype=np.float64),
+           'history_keys': np.array(sorted(tracker.history)),
+           'history_values': np.array([tracker.history[k][-1] if tracker.history[k] else np.nan for k in sorted(tracker.history)])}
+    out['joints3D_pa'] = ref.eval_utils.procrustes_analysis_batch(pred['joints3D'], target['joints3D'])
+    out['joints3D_sc'] = ref.eval_utils.scale_and_translation_transform_batch(pred['joints3D'], target['joints3D'])
+    out['verts0_pa_first32'] = ref.eval_utils.compute_similarity_transform(pred['verts'][0], target['verts'][0])[:32]
+    return out
 
 
 def main():
@@ -106,6 +155,10 @@ def main():
     j[0, 0] = [0., 0.]; j[0, 1] = [255., 255.]; j[0, 2] = [-7.9, 262.9]; j[0, 3] = [-8., 100.]; j[0, 4] = [263., 5.]
     j[0, 5] = [247.5, 8.2]; j[0, 6] = [254.99, 0.5]
     np.savez_compressed(os.path.join(GOLDEN, 'heatmaps_b4.npz'), joints2d=j, heatmaps=ref.heatmaps(torch.from_numpy(j), 256).numpy())
+    # ---- N2: SMPL / camera augmentation + perspective projection (augmentation/*.py, utils/cam_utils.py:40-71) ----------
+    np.savez_compressed(os.path.join(GOLDEN, 'synth_b4.npz'), **synth_fixture(ref))
+    # ---- N4: metric sums of the tracker + aligned point sets (metrics/..tracker.py:102-213, utils/eval_utils.py) --------
+    np.savez_compressed(os.path.join(GOLDEN, 'metrics_b4.npz'), **metrics_fixture(ref))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

@@ -61,6 +61,13 @@ def load_reference(assets_root):
         ns.Loss = importlib.import_module('losses.multi_task_loss').HomoscedasticUncertaintyWeightedMultiTaskLoss
         ns.SyntheticTrainingDataset = importlib.import_module('data.synthetic_training_dataset').SyntheticTrainingDataset
         ns.heatmaps = importlib.import_module('utils.label_conversions').convert_2Djoints_to_gaussian_heatmaps_torch
+        # SURVEY 8f rows N2 / N4
+        ns.smpl_augmentation = importlib.import_module('augmentation.smpl_augmentation')
+        ns.cam_augmentation = importlib.import_module('augmentation.cam_augmentation')
+        ns.perspective_project_torch = importlib.import_module('utils.cam_utils').perspective_project_torch
+        ns.get_intrinsics_matrix = importlib.import_module('utils.cam_utils').get_intrinsics_matrix
+        ns.eval_utils = importlib.import_module('utils.eval_utils')
+        ns.Tracker = importlib.import_module('metrics.train_loss_and_metrics_tracker').TrainingLossesAndMetricsTracker
     ns.assets_root = assets_root
 
     @contextlib.contextmanager

@@ -314,3 +314,89 @@ def joints2d_to_heatmaps(joints2d, img_wh, std=4):
                 gsy, gey = max(0, size - cy), min(2 * size, 2 * size - (size + cy - (img_wh - 1)))
                 hm[i, j, hsy:hey, hsx:hex_] = g[gsy:gey, gsx:gex]
     return hm
+
+
+# ----------------------------------------------------------------------------------------------
+# target side of the synthetic loop
+# ----------------------------------------------------------------------------------------------
+def batch_rodrigues(rot_vecs):
+    """smplx.lbs.batch_rodrigues (restated in oracle/smplx_shim): [n,3] -> [n,3,3]."""
+    if _SHIM not in sys.path:
+        sys.path.insert(0, _SHIM)
+    from smplx.lbs import batch_rodrigues as br
+    return br(rot_vecs)
+
+
+def perspective_project(points, rotation, translation, cam_K):
+    """utils/cam_utils.py:56-71: rotate + translate, divide by depth, apply the intrinsics, drop the last coordinate."""
+    q = torch.einsum('bij,bkj->bki', rotation, points) + translation.unsqueeze(1)
+    q = q / q[:, :, -1].unsqueeze(-1)
+    return torch.einsum('bij,bkj->bki', cam_K, q)[:, :, :-1]
+
+
+def sample_shape_from_noise(noise, mean_shape, distribution, delta_betas_range=None, std_vector=None):
+    """augmentation/smpl_augmentation.py:6-24 with the random draw passed in (`noise` = the rand / randn tensor)."""
+    if distribution == 'uniform':
+        l, h = delta_betas_range
+        return ((h - l) * noise + l) + mean_shape
+    return noise * std_vector + mean_shape
+
+
+def cam_t_from_noise(mean_cam_t, noise_xy, noise_z, xy_std, delta_z_range):
+    """augmentation/cam_augmentation.py:4-14 with the two draws (randn [bs,2], rand [bs]) passed in."""
+    out = mean_cam_t.clone()
+    out[:, :2] = mean_cam_t[:, :2] + noise_xy * xy_std
+    l, h = delta_z_range
+    out[:, 2] = mean_cam_t[:, 2] + ((h - l) * noise_z + l)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# SURVEY.md 8f row N4: evaluation metrics (utils/eval_utils.py, metrics/train_loss_and_metrics_tracker.py:102-213)
+# numpy float32 like the reference; the batch loop of the reference is vectorised with numpy's stacked SVD
+# ----------------------------------------------------------------------------------------------
+def procrustes_batch(S1, S2):
+    """utils/eval_utils.py:7-60 for [B,N,3] arrays: S1 after the best similarity transform onto S2."""
+    S1, S2 = np.asarray(S1), np.asarray(S2)
+    A, Bm = np.swapaxes(S1, 1, 2), np.swapaxes(S2, 1, 2)                 # [B,3,N] as the reference works
+    mu1, mu2 = A.mean(axis=2, keepdims=True), Bm.mean(axis=2, keepdims=True)
+    X1, X2 = A - mu1, Bm - mu2
+    var1 = np.sum(X1 ** 2, axis=(1, 2))
+    K = X1 @ np.swapaxes(X2, 1, 2)
+    U, s, Vh = np.linalg.svd(K)
+    V = np.swapaxes(Vh, 1, 2)
+    Z = np.tile(np.eye(3, dtype=K.dtype), (K.shape[0], 1, 1))
+    Z[:, 2, 2] *= np.sign(np.linalg.det(U @ np.swapaxes(V, 1, 2)))
+    R = V @ (Z @ np.swapaxes(U, 1, 2))
+    scale = np.trace(R @ K, axis1=1, axis2=2) / var1
+    t = mu2 - scale[:, None, None] * (R @ mu1)
+    return np.swapaxes(scale[:, None, None] * (R @ A) + t, 1, 2)
+
+
+def scale_translation_batch(P, T):
+    """utils/eval_utils.py:63-85."""
+    P, T = np.asarray(P), np.asarray(T)
+    Pc = P - P.mean(axis=1, keepdims=True)
+    p_scale = np.sqrt(np.sum(Pc ** 2, axis=(1, 2), keepdims=True) / P.shape[1])
+    t_mean = T.mean(axis=1, keepdims=True)
+    t_scale = np.sqrt(np.sum((T - t_mean) ** 2, axis=(1, 2), keepdims=True) / T.shape[1])
+    return Pc / p_scale * t_scale + t_mean
+
+
+def metric_sums(pred, target, img_wh=REGRESSOR_IMG_WH, pred_reposed=None, target_reposed=None):
+    """The per-batch metric SUMS of metrics/train_loss_and_metrics_tracker.py:121-213 (all of them), as a dict of floats.
+    pred / target: dicts of numpy arrays with the tracker's keys (verts, joints3D, joints2D, shape_params,
+    pose_params_rot_matrices)."""
+    l2 = lambda a, b: float(np.sum(np.linalg.norm(a - b, axis=-1)))
+    out = {}
+    for name, p, t in (('pves', pred['verts'], target['verts']), ('pve-ts', pred_reposed, target_reposed),
+                       ('mpjpes', pred['joints3D'], target['joints3D'])):
+        if p is None:
+            continue
+        out[name] = l2(p, t)
+        out[name + '_sc'] = l2(scale_translation_batch(p, t), t)
+        out[name + '_pa'] = l2(procrustes_batch(p, t), t)
+    out['pose_mses'] = float(np.sum((pred['pose_params_rot_matrices'] - target['pose_params_rot_matrices']) ** 2))
+    out['shape_mses'] = float(np.sum((pred['shape_params'] - target['shape_params']) ** 2))
+    out['joints2D_l2es'] = l2((pred['joints2D'] + 1) * (img_wh / 2.0), target['joints2D'])
+    return out

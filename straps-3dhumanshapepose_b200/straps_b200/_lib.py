@@ -29,6 +29,12 @@ SIGNATURES = {
     'straps_orthographic_project': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     'straps_joints2d_to_heatmaps': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     'straps_multiclass_to_binary': (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp]),
+    'straps_batch_rodrigues': (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp]),
+    'straps_perspective_project': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    'straps_scale_shift': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    'straps_points_metrics': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    'straps_rows_metric': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, _vp, _vp]),
+    'straps_accumulate': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, _vp, _vp]),
     'straps_regressor_create': (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int]),
     'straps_regressor_destroy': (None, [_vp]),
     'straps_regressor_workspace_bytes': (ctypes.c_size_t, [_vp]),

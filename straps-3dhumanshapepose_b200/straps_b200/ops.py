@@ -99,6 +99,107 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-3, betas=(0.9, 0.9
               'straps_adam_step')
 
 
+# ---- SURVEY 8f N2: target side of the synthetic loop ----
+def batch_rodrigues(rot_vecs):
+    """[n,3] axis-angle -> [n,3,3]  (smplx.lbs.batch_rodrigues; reference call sites augmentation/smpl_augmentation.py:55-58)."""
+    _need_cuda(rot_vecs, 'rot_vecs')
+    if rot_vecs.dim() != 2 or rot_vecs.shape[1] != 3:
+        raise StrapsError('batch_rodrigues expects [n,3], got %s' % (tuple(rot_vecs.shape),))
+    r = rot_vecs.contiguous()
+    out = torch.empty((r.shape[0], 3, 3), dtype=torch.float32, device=r.device)
+    with torch.cuda.device(r.device):
+        check(_lib.lib().straps_batch_rodrigues(_p(r), r.shape[0], _p(out), _stream(r.device)), 'straps_batch_rodrigues')
+    return out
+
+
+def perspective_project(points, rotation, translation, cam_K):
+    """[B,N,3], [B,3,3], [B,3], [B,3,3] -> [B,N,2]  (reference utils/cam_utils.py:40-71)."""
+    for n, t in (('points', points), ('rotation', rotation), ('translation', translation), ('cam_K', cam_K)):
+        _need_cuda(t, n)
+    B, N = points.shape[0], points.shape[1]
+    if rotation.shape != (B, 3, 3) or translation.shape != (B, 3) or cam_K.shape != (B, 3, 3):
+        raise StrapsError('perspective_project: expected rotation [B,3,3], translation [B,3], cam_K [B,3,3] for B=%d' % B)
+    points, rotation, translation, cam_K = points.contiguous(), rotation.contiguous(), translation.contiguous(), cam_K.contiguous()
+    out = torch.empty((B, N, 2), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().straps_perspective_project(_p(points), _p(rotation), _p(translation), _p(cam_K), B, N, _p(out),
+                                                    _stream(points.device)), 'straps_perspective_project')
+    return out
+
+
+def scale_shift(noise, mul, add, base):
+    """out[r,c] = (noise[r,c]*mul[c] + add[c]) + base[r or 0, c], each op rounded separately like the reference's torch ops.
+    noise [R,W]; mul / add: [W] tensors or python scalars (add may be None); base [R,W] or [W]."""
+    _need_cuda(noise, 'noise')
+    noise = noise.contiguous()
+    R, W = noise.shape
+    dev = noise.device
+
+    def vec(v):
+        if v is None:
+            return None
+        if torch.is_tensor(v):
+            v = v.to(device=dev, dtype=torch.float32).reshape(-1)
+            return (v.expand(W) if v.numel() == 1 else v).contiguous()
+        return torch.full((W,), float(v), dtype=torch.float32, device=dev)
+    mul_t, add_t = vec(mul), vec(add)
+    _need_cuda(base, 'base')
+    base2 = base.reshape(-1, W)
+    if base2.shape[0] not in (1, R):
+        raise StrapsError('scale_shift: base has %d rows, expected 1 or %d' % (base2.shape[0], R))
+    if base2.stride(1) != 1:
+        base2 = base2.contiguous()
+    stride = 0 if base2.shape[0] == 1 else base2.stride(0)
+    out = torch.empty((R, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().straps_scale_shift(_p(noise), _p(mul_t), _p(add_t) if add_t is not None else None, _p(base2), stride, R, W,
+                                            _p(out), _stream(dev)), 'straps_scale_shift')
+    return out
+
+
+# ---- SURVEY 8f N4: evaluation metrics on the device ----
+METRIC_PLAIN, METRIC_SC, METRIC_PA = 1, 2, 4
+
+
+def points_metrics(pred, target, which, sums=None, want_sc=False, want_pa=False):
+    """pred/target [B,N,3].  Accumulates the selected error sums into `sums` (CUDA float64 [3]: plain, scale-corrected,
+    Procrustes-aligned) and/or returns the corrected / aligned copies of pred (reference utils/eval_utils.py:7-85)."""
+    _need_cuda(pred, 'pred')
+    _need_cuda(target, 'target')
+    if pred.shape != target.shape or pred.dim() != 3 or pred.shape[2] != 3:
+        raise StrapsError('points_metrics expects two [B,N,3] tensors, got %s and %s' % (tuple(pred.shape), tuple(target.shape)))
+    pred, target = pred.contiguous(), target.contiguous()
+    if sums is not None and (not sums.is_cuda or sums.dtype != torch.float64 or sums.numel() < 3 or not sums.is_contiguous()):
+        raise StrapsError('points_metrics: sums must be a contiguous CUDA float64 tensor with >= 3 elements')
+    out_sc = torch.empty_like(pred) if want_sc else None
+    out_pa = torch.empty_like(pred) if want_pa else None
+    with torch.cuda.device(pred.device):
+        check(_lib.lib().straps_points_metrics(_p(pred), _p(target), pred.shape[0], pred.shape[1], int(which),
+                                               _p(sums) if sums is not None else None, _p(out_sc) if want_sc else None,
+                                               _p(out_pa) if want_pa else None, _stream(pred.device)), 'straps_points_metrics')
+    return out_sc, out_pa
+
+
+def rows_metric(pred, target, sum_slot, dim, pred_add=0.0, pred_mul=1.0, squared=False):
+    """sum_slot (CUDA float64, 1 element view) += sum over rows of ||(pred+add)*mul - target|| (or squared differences)."""
+    _need_cuda(pred, 'pred')
+    _need_cuda(target, 'target')
+    if pred.numel() != target.numel() or pred.numel() % dim:
+        raise StrapsError('rows_metric: shapes %s / %s do not form rows of %d' % (tuple(pred.shape), tuple(target.shape), dim))
+    pred, target = pred.contiguous(), target.contiguous()
+    with torch.cuda.device(pred.device):
+        check(_lib.lib().straps_rows_metric(_p(pred), _p(target), pred.numel() // dim, dim, float(pred_add), float(pred_mul),
+                                            1 if squared else 0, _p(sum_slot), _stream(pred.device)), 'straps_rows_metric')
+
+
+def accumulate(src, scale, dst):
+    """dst[:n] += scale * src  (src CUDA float32 [n], dst CUDA float64)."""
+    _need_cuda(src, 'src')
+    src = src.contiguous()
+    with torch.cuda.device(src.device):
+        check(_lib.lib().straps_accumulate(_p(src), src.numel(), float(scale), _p(dst), _stream(src.device)), 'straps_accumulate')
+
+
 class SmplHandle(object):
     """Owns the device-resident packed SMPL constants of one CUDA device."""
 
