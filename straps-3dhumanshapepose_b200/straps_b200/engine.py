@@ -21,6 +21,17 @@ class RegressorEngine(object):
         self._sig = None
         self._train_steps = 0      # running statistics are updated through raw pointers: force a repack afterwards
 
+    def _initial_estimate(self, device):
+        """Device copy of `ief.initial_params_estimate` (a plain attribute, normally a CPU tensor: models/ief_module.py:31), cached by
+        the source tensor's identity / version so that a forward neither copies nor synchronises (the previous per-call
+        `.cpu()` comparison drained the stream once per step and made the forward impossible to capture in a CUDA graph)."""
+        src = self.ief.initial_params_estimate
+        key = (id(src), src.data_ptr(), src._version, str(device))
+        if getattr(self, '_init_key', None) != key:
+            self._init_dev = src.detach().to(device=device, dtype=torch.float32).contiguous().clone()
+            self._init_key = key
+        return self._init_dev
+
     # -- tensors in the order the C ABI expects
     def _tensors(self, device):
         h = self._handle
@@ -45,7 +56,7 @@ class RegressorEngine(object):
         if self.ief is not None:
             fc_w = [self.ief.fc1.weight, self.ief.fc2.weight, self.ief.fc3.weight]
             fc_b = [self.ief.fc1.bias, self.ief.fc2.bias, self.ief.fc3.bias]
-            init = self.ief.initial_params_estimate.to(device=device, dtype=torch.float32)
+            init = self._initial_estimate(device)
         else:
             fc_w = [torch.zeros(512, 669, device=device), torch.zeros(512, 512, device=device), torch.zeros(157, 512, device=device)]
             fc_b = [torch.zeros(512, device=device), torch.zeros(512, device=device), torch.zeros(157, device=device)]
@@ -65,7 +76,7 @@ class RegressorEngine(object):
         for t in flat:
             if t.device != device:
                 raise StrapsError('regressor parameters live on %s but the input is on %s' % (t.device, device))
-        sig = tuple((t.data_ptr(), t._version) for t in flat) + (init.cpu().numpy().tobytes(), self._train_steps)
+        sig = tuple((t.data_ptr(), t._version) for t in flat) + (init.data_ptr(), self._train_steps)
         if sig != self._sig:
             self._handle.load([t.detach() for t in conv_w], [[t.detach() for t in q] for q in bn],
                               [t.detach() for t in fc_w], [t.detach() for t in fc_b], init)
