@@ -37,6 +37,13 @@ namespace straps {
 constexpr int XP_H = 262, XP_W = 264, XP_C = 24;   // padded conv1 input
 constexpr int C1_KROW = 192;                       // K elements per filter row of conv1 (3 chunks of 64)
 constexpr int TC_THREADS = 192;
+// STRAPS_TC_EXPERIMENTS builds keep the in-situ timing switches of profiles/r01_conv_experiments.txt (p.debug); normal builds have
+// no trace of them in the hot loops
+#ifdef STRAPS_TC_EXPERIMENTS
+#define TC_EPI_IO(p) ((p).debug != 3)
+#else
+#define TC_EPI_IO(p) true
+#endif
 constexpr int BM_TC = 128;
 constexpr int BK_TC = 64;
 
@@ -119,48 +126,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The two issue roles are ONE thread each, so their cost is instruction LATENCY, not throughput: the first version of these
+  // loops (div/mod per K-block, 64-bit descriptor arithmetic, `lane == 0` divergence that made the compiler wrap every
+  // UTMALDG / UTCHMMA in an ELECT + BRA.U.ANY loop) ran ~125-150 dependent SASS instructions per K-block -- about as long as the
+  // 448 tensor-pipe cycles of the K-block itself (in-situ: MMAs alone 810 cycles per K-block, TMA alone 870).  Both loops now
+  // keep incremental counters, 32-bit shared addresses and descriptor words, and run under elect.sync.
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // ================= TMA producer =================
-      uint32_t it = 0;
+      uint32_t st = 0, ph = 1;                       // ring stage and the parity to wait for on empty[st]
+      const int nkb = p.n_kblocks, cchunks = p.cchunks, kwc = p.kw_count, pad = p.pad, stride = p.stride;
+      const bool conv1 = p.conv1 != 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
-        int b0[MT], oh0[MT];
+        const int mg = item / p.n_ntiles, nt = item - mg * p.n_ntiles;
+        int b0[MT], row0[MT];
 #pragma unroll
         for (int t = 0; t < MT; ++t) {
           const long long pix0 = (long long)(mg * MT + t) * BM_TC;   // tiles past the end land out of bounds -> zeros
           b0[t] = (int)(pix0 / p.hw_out);
-          oh0[t] = (int)((pix0 % p.hw_out) / p.wout);
+          const int oh0 = (int)((pix0 % p.hw_out) / p.wout);
+          row0[t] = conv1 ? oh0 : oh0 * stride - pad;
         }
-        for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
-          const int st = it % Cfg::STAGES;
-          mbar_wait(&empty[st], ((it / Cfg::STAGES) & 1) ^ 1);
-          unsigned char* sa = smem + st * Cfg::STAGE_BYTES;
-          if (p.debug == 1) { mbar_arrive(&full[st]); continue; }      // timing experiment: stale operands, no TMA traffic
-          mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
-          int c0, c1, dh;
-          if (p.conv1) {
-            const int kh = kb / 3, j = kb % 3;
-            c0 = kh * (XP_W * XP_C) + j * 64; c1 = 0; dh = 0;
-          } else {
-            const int tap = kb / p.cchunks, cc = kb % p.cchunks;
-            const int kh = tap / p.kw_count, kw = tap % p.kw_count;
-            c0 = cc * 64; c1 = kw - p.pad; dh = kh - p.pad;
-          }
+        const int wrow = nt * BN;
+        // K-block coordinates, advanced incrementally: conv1 (c0 = kh * row pitch + j * 64, j = 0..2), others (cc, kw, kh)
+        int c0 = 0, c1 = conv1 ? 0 : -pad, dh = 0, sub = 0, kwi = 0, wk = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t sa = smem0 + st * Cfg::STAGE_BYTES;
+          const uint32_t fb = full0 + st * 8;
+          mbar_wait_u32(empty0 + st * 8, ph);
+#ifdef STRAPS_TC_EXPERIMENTS
+          if (p.debug == 1) { mbar_arrive(&full[st]); if (++st == Cfg::STAGES) { st = 0; ph ^= 1; } continue; }
+#endif
+          mbar_expect_tx_u32(fb, Cfg::STAGE_BYTES);
 #pragma unroll
           for (int t = 0; t < MT; ++t) {
-            const int c2 = p.conv1 ? oh0[t] : oh0[t] * p.stride + dh;
-            tma_load_4d(sa + (2 * t) * Cfg::A_BYTES, &map_a_hi, &full[st], c0, c1, c2, b0[t]);
-            tma_load_4d(sa + (2 * t + 1) * Cfg::A_BYTES, &map_a_lo, &full[st], c0, c1, c2, b0[t]);
+            tma_load_4d_u32(sa + (2 * t) * Cfg::A_BYTES, &map_a_hi, fb, c0, c1, row0[t] + dh, b0[t]);
+            tma_load_4d_u32(sa + (2 * t + 1) * Cfg::A_BYTES, &map_a_lo, fb, c0, c1, row0[t] + dh, b0[t]);
           }
-          unsigned char* sw = sa + MT * 2 * Cfg::A_BYTES;
-          tma_load_2d(sw, &map_w_hi, &full[st], kb * BK_TC, nt * BN);
-          tma_load_2d(sw + Cfg::W_BYTES, &map_w_lo, &full[st], kb * BK_TC, nt * BN);
+          tma_load_2d_u32(sa + MT * 2 * Cfg::A_BYTES, &map_w_hi, fb, wk, wrow);
+          tma_load_2d_u32(sa + MT * 2 * Cfg::A_BYTES + Cfg::W_BYTES, &map_w_lo, fb, wk, wrow);
+          wk += BK_TC;
+          if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
+          if (conv1) {
+            c0 += 64;
+            if (++sub == 3) { sub = 0; c0 += XP_W * XP_C - 3 * 64; }     // next filter row of the padded input
+          } else {
+            c0 += 64;
+            if (++sub == cchunks) {
+              sub = 0; c0 = 0; ++c1;
+              if (++kwi == kwc) { kwi = 0; c1 = -pad; ++dh; }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // ================= MMA issuer =================
       // W_hi and W_lo are adjacent in the stage, so for BN <= 128 ONE MMA of width 2*BN computes
       // A_hi.[W_hi ; W_lo] into [acc_hi | acc_lo] (A_hi is read from shared memory once instead of twice).
@@ -169,45 +192,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       // K/16 additions happen at full magnitude; the two are summed in fp32 in the epilogue.
       constexpr uint32_t idesc = umma_idesc_f16(BM_TC, BN);
       constexpr uint32_t idesc_wide = umma_idesc_f16(BM_TC, (2 * BN <= 256) ? 2 * BN : BN);
-      uint32_t it = 0, ti = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
-        const uint32_t as = ti % Cfg::TSTAGES;
-        mbar_wait(&tempty[as], ((ti / Cfg::TSTAGES) & 1) ^ 1);
+      constexpr uint32_t STAGE16 = Cfg::STAGE_BYTES >> 4, A16 = Cfg::A_BYTES >> 4, W16 = Cfg::W_BYTES >> 4;
+      const uint32_t desc0 = umma_desc_sw128_lo(smem0);           // low descriptor word of stage 0, A tile 0, hi plane
+      const uint32_t tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
+      uint32_t st = 0, ph = 0, as = 0, aph = 1;
+      const int nkb = p.n_kblocks;
+      const bool conv1 = p.conv1 != 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait_u32(tempty0 + as * 8, aph);
         tc_fence_after();
-        for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
-          const int st = it % Cfg::STAGES;
-          mbar_wait(&full[st], (it / Cfg::STAGES) & 1);
+        const uint32_t acc = tmem_base + as * Cfg::ACC_COLS;
+        int sub = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_u32(full0 + st * 8, ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
-          const uint64_t w_hi = umma_desc_sw128(sa + MT * 2 * Cfg::A_BYTES);
-          const uint64_t w_lo = umma_desc_sw128(sa + MT * 2 * Cfg::A_BYTES + Cfg::W_BYTES);
+          const uint32_t d0 = desc0 + st * STAGE16;
+          const uint32_t w_hi = d0 + MT * 2 * A16, w_lo = w_hi + W16;
+          // conv1: the third 64-element chunk of a filter row holds taps 5.33..7 = 40 real + 24 zero-weight elements;
+          // its last K=16 step is all padding and is skipped (11 of 12 MMAs per filter row)
+          int ksteps = BK_TC / 16;
+          if (conv1) { if (++sub == 3) { sub = 0; ksteps = 3; } }
+#ifdef STRAPS_TC_EXPERIMENTS
+          if (p.debug == 2) ksteps = 0;                                   // timing experiment: TMA only
+#endif
 #pragma unroll
           for (int t = 0; t < MT; ++t) {
-            if (p.debug == 2) break;                                     // timing experiment: TMA only
-            const uint64_t a_hi = umma_desc_sw128(sa + (2 * t) * Cfg::A_BYTES);
-            const uint64_t a_lo = umma_desc_sw128(sa + (2 * t + 1) * Cfg::A_BYTES);
-            const uint32_t d_hi = tmem_base + as * Cfg::ACC_COLS + t * Cfg::TILE_COLS, d_lo = d_hi + BN;
-            // conv1: the third 64-element chunk of a filter row holds taps 5.33..7 = 40 real + 24 zero-weight elements;
-            // its last K=16 step is all padding and is skipped (11 of 12 MMAs per filter row)
-            const int ksteps = (p.conv1 && (kb % 3) == 2) ? 3 : BK_TC / 16;
+            const uint32_t a_hi = d0 + (2 * t) * A16, a_lo = a_hi + A16;
+            const uint32_t d_hi = acc + t * Cfg::TILE_COLS, d_lo = d_hi + BN;
 #pragma unroll
             for (int k = 0; k < BK_TC / 16; ++k) {
-              if (k >= ksteps) break;
-              const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 bytes along K inside the 128-byte swizzle row
-              const uint32_t first = (kb | k) != 0;
-              if constexpr (2 * BN <= 256) {
-                umma_f16(d_hi, a_hi + ko, w_hi + ko, idesc_wide, first);   // -> [acc_hi | acc_lo]
-                umma_f16(d_lo, a_lo + ko, w_hi + ko, idesc, 1);
-              } else {
-                umma_f16(d_hi, a_hi + ko, w_hi + ko, idesc, first);
-                umma_f16(d_lo, a_hi + ko, w_lo + ko, idesc, first);
-                umma_f16(d_lo, a_lo + ko, w_hi + ko, idesc, 1);
+              if (k < ksteps) {
+                const uint32_t ko = k * 2;                 // +32 bytes along K inside the 128-byte swizzle row
+                const uint32_t accum = (kb | k) != 0;
+                if constexpr (2 * BN <= 256) {
+                  umma_f16_lohi(d_hi, a_hi + ko, w_hi + ko, idesc_wide, accum);   // -> [acc_hi | acc_lo]
+                  umma_f16_lohi(d_lo, a_lo + ko, w_hi + ko, idesc, 1);
+                } else {
+                  umma_f16_lohi(d_hi, a_hi + ko, w_hi + ko, idesc, accum);
+                  umma_f16_lohi(d_lo, a_hi + ko, w_lo + ko, idesc, accum);
+                  umma_f16_lohi(d_lo, a_lo + ko, w_hi + ko, idesc, 1);
+                }
               }
             }
           }
-          umma_commit(&empty[st]);          // frees the smem stage once these MMAs have read it
+          umma_commit_u32(empty0 + st * 8);         // frees the smem stage once these MMAs have read it
+          if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[as]);            // accumulators complete -> epilogue
+        umma_commit_u32(tfull0 + as * 8);           // accumulators complete -> epilogue
+        if (++as == Cfg::TSTAGES) { as = 0; aph ^= 1; }
       }
     }
   } else {
@@ -226,7 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       auto fetch_residual = [&](int chunk) {
         const int t = chunk / (BN / 32), c0 = (chunk % (BN / 32)) * 32;
         const long long m = (long long)(mg * MT + t) * BM_TC + row;
-        if (p.res_hi && chunk < NCHUNK && m < p.m_total && p.debug != 3) {
+        if (p.res_hi && chunk < NCHUNK && m < p.m_total && TC_EPI_IO(p)) {
           const size_t o = (size_t)m * p.cout + (size_t)nt * BN + c0;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -260,7 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
           y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
         }
-        if (valid && p.debug != 3) {
+        if (valid && TC_EPI_IO(p)) {
           if (p.res_hi) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -274,7 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
         fetch_residual(chunk + 1);        // in flight while this chunk is split and stored
-        if (valid && p.debug != 3) {
+        if (valid && TC_EPI_IO(p)) {
           if (p.res_f32) {
             const float4* r4 = reinterpret_cast<const float4*>(p.res_f32 + obase + c0);
 #pragma unroll
@@ -695,6 +727,11 @@ struct TcState {
   size_t ch_off[NCONV];         // offset of each conv in the two arrays above
   std::map<int, std::vector<TcLayerMaps>> maps;   // per batch size
   struct TcTrain* train;        // training-path state, allocated on first use
+  // fork/join for the 1x1 downsample convolutions (independent of the block's first 3x3 convolution): launched on `side`,
+  // their CTAs fill the SMs the 3x3 kernel's last, partial wave leaves idle
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  int ds_overlap;
 };
 
 static inline __half* plane_hi(const straps_regressor* r, int buf) {
@@ -712,6 +749,8 @@ int tc_create(straps_regressor* r) {
   TcState* t = new TcState();
   r->tc = t;
   t->xp = nullptr; t->wpool = nullptr; t->encode = nullptr; t->num_sms = 148; t->train = nullptr;
+  t->side = nullptr; t->ev_fork = t->ev_join = nullptr;
+  { const char* e = getenv("STRAPS_TC_DS_OVERLAP"); t->ds_overlap = e ? atoi(e) : 1; }
   // The driver entry point is resolved at first use (no GPU / driver in the build container).
   t->xp_plane = (size_t)r->max_batch * XP_H * XP_W * XP_C;
   size_t welts = 0, nch = 0;
@@ -740,6 +779,9 @@ int tc_create(straps_regressor* r) {
   int dev = 0;
   STRAPS_CUDA(cudaGetDevice(&dev));
   STRAPS_CUDA(cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  STRAPS_CUDA(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
+  STRAPS_CUDA(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+  STRAPS_CUDA(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
   return 0;
 }
 
@@ -752,6 +794,9 @@ void tc_destroy(straps_regressor* r) {
   if (t->xp) cudaFree(t->xp);
   if (t->wpool) cudaFree(t->wpool);
   if (t->rowscale) cudaFree(t->rowscale);
+  if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+  if (t->ev_join) cudaEventDestroy(t->ev_join);
+  if (t->side) cudaStreamDestroy(t->side);
   delete t;
   r->tc = nullptr;
 }
@@ -976,8 +1021,19 @@ int tc_encoder_forward(straps_regressor* r, const float* x, int B, float* feat, 
   int i = 1;
   while (i < NCONV) {
     const bool ds = (i + 2 < NCONV) && r->conv[i + 2].ksize == 1;
-    if (run_conv_tc(r, maps, i, B, st)) return 1;
-    if (ds && run_conv_tc(r, maps, i + 2, B, st)) return 1;
+    if (ds && t->ds_overlap) {
+      // fork: the 3x3/2 convolution goes first on the caller's stream and takes every SM; the 1x1/2 downsample (same input,
+      // own output buffer) follows on the side stream and starts on the SMs freed by the 3x3 kernel's partial last wave
+      STRAPS_CUDA(cudaEventRecord(t->ev_fork, st));
+      STRAPS_CUDA(cudaStreamWaitEvent(t->side, t->ev_fork, 0));
+      if (run_conv_tc(r, maps, i, B, st)) return 1;
+      if (run_conv_tc(r, maps, i + 2, B, t->side)) return 1;
+      STRAPS_CUDA(cudaEventRecord(t->ev_join, t->side));
+      STRAPS_CUDA(cudaStreamWaitEvent(st, t->ev_join, 0));      // join: conv2 adds the downsample output as its residual
+    } else {
+      if (run_conv_tc(r, maps, i, B, st)) return 1;
+      if (ds && run_conv_tc(r, maps, i + 2, B, st)) return 1;
+    }
     if (run_conv_tc(r, maps, i + 1, B, st)) return 1;
     i += ds ? 3 : 2;
   }
