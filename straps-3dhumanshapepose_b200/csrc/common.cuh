@@ -173,12 +173,17 @@ __device__ __forceinline__ bool elect_one_sync() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-// mbarrier / TMA forms that take 32-bit shared-memory addresses (no generic->shared conversion in the loop)
+// mbarrier / TMA forms that take 32-bit shared-memory addresses (no generic->shared conversion in the loop).
+// The two single-thread issue roles poll with test_wait (returns at once) instead of try_wait (may suspend the thread for a
+// hardware time slice before it re-checks): one spinning thread per role costs nothing and wakes up immediately.
+#ifndef STRAPS_MBAR_POLL
+#define STRAPS_MBAR_POLL "mbarrier.test_wait"
+#endif
 __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      STRAPS_MBAR_POLL ".parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@!p bra WAIT_LOOP;\n\t}" ::"r"(bar), "r"(parity)
       : "memory");
 }
@@ -201,19 +206,36 @@ __device__ __forceinline__ void tma_load_4d_u32(uint32_t dst, const CUtensorMap*
 // SWIZZLE_128B K-major descriptor split into its two words: only the low word (start address >> 4, LBO = 1) moves with the
 // stage / K step; the high word (SBO = 1024 B, version 1, SWIZZLE_128B) is the constant below.
 constexpr uint32_t UMMA_DESC_SW128_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+// same for SWIZZLE_64B tiles (rows of 64 bytes = 32 fp16 along K, 8-row atoms 512 B apart; layout type 4)
+constexpr uint32_t UMMA_DESC_SW64_HI = (512u >> 4) | (1u << 14) | (4u << 29);
 __device__ __forceinline__ uint32_t umma_desc_sw128_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
-__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                              uint32_t desc_hi = UMMA_DESC_SW128_HI) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "mov.b64 da, {%1, %5};\n\t"
       "mov.b64 db, {%2, %5};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_SW128_HI)
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// W-tile multicast inside a cluster (conv_tc_kernel<BN, 1, CL>): one L2 read lands in the shared memory of every CTA in `mask`
+// (same offset in each), completing `bytes` on the barrier at the same offset in each destination CTA.
+__device__ __forceinline__ void tma_load_2d_mc_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask` once this thread's MMAs have completed
+__device__ __forceinline__ void umma_commit_mc_u32(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 
 // ---- thread-block clusters / CTA pairs (cta_group::2) --------------------------------------------

@@ -46,6 +46,7 @@ constexpr int TC_THREADS = 192;
 #endif
 constexpr int BM_TC = 128;
 constexpr int BK_TC = 64;
+constexpr int TC_DEFAULT_BK = 64;   // K elements per stage of conv_tc_kernel unless STRAPS_TC_BK says otherwise
 
 struct TcConvParams {
   int n_mtiles, n_ntiles, n_kblocks;
@@ -79,26 +80,41 @@ struct TcConvParams {
 // Wider tiles -- (128,2), (256,1) -- need fewer bytes per FLOP but only fit 2 ring stages and a single TMEM
 // accumulator stage; they measured 10-25 % SLOWER (profiles/r01_launches_tilecfg.txt) and are kept only as
 // template instantiations for the next round (2-CTA pairs halve the weight bytes per SM).
-template <int BN, int MT>
+// BK = K elements per pipeline stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows).  The ring is LATENCY bound -- measured
+// L2 -> SM throughput = (STAGES - 1) * STAGE_BYTES / ~2600 cycles for every tile shape (profiles/r01_conv_experiments.txt) -- and the
+// stage being consumed carries no load, so half-size stages put more of the same shared memory in flight:
+//   (64,1):  4 x 48 KB -> 144 KB in flight;   9 x 24 KB -> 192 KB        (128,1): 3 x 64 KB -> 128 KB;   7 x 32 KB -> 192 KB
+template <int BN, int MT, int BK = 64>
 struct TcCfg {
-  static constexpr int A_BYTES = BM_TC * 128;           // one plane of one A tile
-  static constexpr int W_BYTES = BN * 128;
+  static_assert(BK == 64 || BK == 32, "BK: one swizzle row of 128 or 64 bytes");
+  static constexpr int A_BYTES = BM_TC * BK * 2;        // one plane of one A tile
+  static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = MT * 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int STAGES = (220 * 1024 / STAGE_BYTES) > 4 ? 4 : (220 * 1024 / STAGE_BYTES);
+  static constexpr int MAX_STAGES = (BK == 64) ? 4 : 10;
+  static constexpr int BUDGET = (BK == 64) ? 220 * 1024 : (232448 - 1024 - 256);
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (BUDGET / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static constexpr int TILE_COLS = 2 * BN;              // per M-tile: [hi.hi | lo terms]
   static constexpr int ACC_COLS = MT * TILE_COLS;       // per accumulator stage
   static constexpr int TSTAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = TSTAGES * ACC_COLS;
+  static constexpr uint32_t DESC_HI = (BK == 64) ? UMMA_DESC_SW128_HI : UMMA_DESC_SW64_HI;
+  static constexpr int C1_CHUNKS = C1_KROW / BK;        // K-blocks per filter row of conv1
+  // conv1: the 168 real elements of a filter row end inside the last chunk; its all-padding K=16 steps are skipped
+  static constexpr int C1_LAST_KSTEPS = (7 * XP_C - (C1_CHUNKS - 1) * BK + 15) / 16;
   static_assert(STAGES >= 2 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "bad tile configuration");
+  static_assert(2 * STAGES * 8 + 40 <= 256, "barrier block too small");
 };
 
-template <int BN, int MT>
+// CL > 1: clusters of CL CTAs along M work on CL consecutive M-tiles of the SAME N-tile in lock step and share the weight tile:
+// each CTA fetches 1/CL of its rows and multicasts them to the whole cluster (L2 -> SM weight traffic / CL).  A stage is reused
+// only after EVERY CTA of the cluster has consumed it (empty barriers count CL arrivals: each issuer's commit is multicast).
+template <int BN, int MT, int CL = 1, int BK = 64>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const TcConvParams p) {
-  using Cfg = TcCfg<BN, MT>;
+  using Cfg = TcCfg<BN, MT, BK>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -108,21 +124,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint64_t* tempty = tfull + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  static_assert(CL == 1 || (MT == 1 && (CL == 2 || CL == 4) && BN / CL >= 8), "cluster variant: one M-tile per CTA");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_groups = (p.n_mtiles + MT - 1) / MT;          // a work item = MT consecutive M-tiles x one N-tile
+  constexpr int GROUP = (CL > 1) ? CL : MT;                 // M-tiles per work item (of the cluster, or of the CTA)
+  const int n_groups = (p.n_mtiles + GROUP - 1) / GROUP;    // a work item = GROUP consecutive M-tiles x one N-tile
   const int n_items = n_groups * p.n_ntiles;
+  const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int item0 = (CL > 1) ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+  const int item_step = (CL > 1) ? (int)(gridDim.x / CL) : (int)gridDim.x;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();      // every CTA's barriers exist before any multicast load / remote commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -139,12 +162,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint32_t st = 0, ph = 1;                       // ring stage and the parity to wait for on empty[st]
       const int nkb = p.n_kblocks, cchunks = p.cchunks, kwc = p.kw_count, pad = p.pad, stride = p.stride;
       const bool conv1 = p.conv1 != 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = item0; item < n_items; item += item_step) {
         const int mg = item / p.n_ntiles, nt = item - mg * p.n_ntiles;
         int b0[MT], row0[MT];
 #pragma unroll
         for (int t = 0; t < MT; ++t) {
-          const long long pix0 = (long long)(mg * MT + t) * BM_TC;   // tiles past the end land out of bounds -> zeros
+          const long long pix0 = (long long)(mg * GROUP + crank + t) * BM_TC;   // tiles past the end land out of bounds -> zeros
           b0[t] = (int)(pix0 / p.hw_out);
           const int oh0 = (int)((pix0 % p.hw_out) / p.wout);
           row0[t] = conv1 ? oh0 : oh0 * stride - pad;
@@ -165,15 +188,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tma_load_4d_u32(sa + (2 * t) * Cfg::A_BYTES, &map_a_hi, fb, c0, c1, row0[t] + dh, b0[t]);
             tma_load_4d_u32(sa + (2 * t + 1) * Cfg::A_BYTES, &map_a_lo, fb, c0, c1, row0[t] + dh, b0[t]);
           }
-          tma_load_2d_u32(sa + MT * 2 * Cfg::A_BYTES, &map_w_hi, fb, wk, wrow);
-          tma_load_2d_u32(sa + MT * 2 * Cfg::A_BYTES + Cfg::W_BYTES, &map_w_lo, fb, wk, wrow);
-          wk += BK_TC;
+          if constexpr (CL > 1) {
+            // this CTA's 1/CL of the weight rows, delivered to every CTA of the cluster (the W maps have BN / CL-row boxes)
+            const uint32_t wo = sa + MT * 2 * Cfg::A_BYTES + crank * (Cfg::W_BYTES / CL);
+            tma_load_2d_mc_u32(wo, &map_w_hi, fb, wk, wrow + crank * (BN / CL), CMASK);
+            tma_load_2d_mc_u32(wo + Cfg::W_BYTES, &map_w_lo, fb, wk, wrow + crank * (BN / CL), CMASK);
+          } else {
+            tma_load_2d_u32(sa + MT * 2 * Cfg::A_BYTES, &map_w_hi, fb, wk, wrow);
+            tma_load_2d_u32(sa + MT * 2 * Cfg::A_BYTES + Cfg::W_BYTES, &map_w_lo, fb, wk, wrow);
+          }
+          wk += BK;
           if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
           if (conv1) {
-            c0 += 64;
-            if (++sub == 3) { sub = 0; c0 += XP_W * XP_C - 3 * 64; }     // next filter row of the padded input
+            c0 += BK;
+            if (++sub == Cfg::C1_CHUNKS) { sub = 0; c0 += XP_W * XP_C - C1_KROW; }     // next filter row of the padded input
           } else {
-            c0 += 64;
+            c0 += BK;
             if (++sub == cchunks) {
               sub = 0; c0 = 0; ++c1;
               if (++kwi == kwc) { kwi = 0; c1 = -pad; ++dh; }
@@ -198,7 +228,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint32_t st = 0, ph = 0, as = 0, aph = 1;
       const int nkb = p.n_kblocks;
       const bool conv1 = p.conv1 != 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = item0; item < n_items; item += item_step) {
         mbar_wait_u32(tempty0 + as * 8, aph);
         tc_fence_after();
         const uint32_t acc = tmem_base + as * Cfg::ACC_COLS;
@@ -208,10 +238,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           tc_fence_after();
           const uint32_t d0 = desc0 + st * STAGE16;
           const uint32_t w_hi = d0 + MT * 2 * A16, w_lo = w_hi + W16;
-          // conv1: the third 64-element chunk of a filter row holds taps 5.33..7 = 40 real + 24 zero-weight elements;
-          // its last K=16 step is all padding and is skipped (11 of 12 MMAs per filter row)
-          int ksteps = BK_TC / 16;
-          if (conv1) { if (++sub == 3) { sub = 0; ksteps = 3; } }
+          // conv1: the last chunk of a filter row (192 elements for 7 taps x 24 channels = 168 real ones) ends in zero-weight
+          // padding; its all-padding K=16 steps are skipped (11 of 12 MMAs per filter row)
+          int ksteps = BK / 16;
+          if (conv1) { if (++sub == Cfg::C1_CHUNKS) { sub = 0; ksteps = Cfg::C1_LAST_KSTEPS; } }
 #ifdef STRAPS_TC_EXPERIMENTS
           if (p.debug == 2) ksteps = 0;                                   // timing experiment: TMA only
 #endif
@@ -220,22 +250,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t a_hi = d0 + (2 * t) * A16, a_lo = a_hi + A16;
             const uint32_t d_hi = acc + t * Cfg::TILE_COLS, d_lo = d_hi + BN;
 #pragma unroll
-            for (int k = 0; k < BK_TC / 16; ++k) {
+            for (int k = 0; k < BK / 16; ++k) {
               if (k < ksteps) {
                 const uint32_t ko = k * 2;                 // +32 bytes along K inside the 128-byte swizzle row
                 const uint32_t accum = (kb | k) != 0;
                 if constexpr (2 * BN <= 256) {
-                  umma_f16_lohi(d_hi, a_hi + ko, w_hi + ko, idesc_wide, accum);   // -> [acc_hi | acc_lo]
-                  umma_f16_lohi(d_lo, a_lo + ko, w_hi + ko, idesc, 1);
+                  umma_f16_lohi(d_hi, a_hi + ko, w_hi + ko, idesc_wide, accum, Cfg::DESC_HI);   // -> [acc_hi | acc_lo]
+                  umma_f16_lohi(d_lo, a_lo + ko, w_hi + ko, idesc, 1, Cfg::DESC_HI);
                 } else {
-                  umma_f16_lohi(d_hi, a_hi + ko, w_hi + ko, idesc, accum);
-                  umma_f16_lohi(d_lo, a_hi + ko, w_lo + ko, idesc, accum);
-                  umma_f16_lohi(d_lo, a_lo + ko, w_hi + ko, idesc, 1);
+                  umma_f16_lohi(d_hi, a_hi + ko, w_hi + ko, idesc, accum, Cfg::DESC_HI);
+                  umma_f16_lohi(d_lo, a_hi + ko, w_lo + ko, idesc, accum, Cfg::DESC_HI);
+                  umma_f16_lohi(d_lo, a_lo + ko, w_hi + ko, idesc, 1, Cfg::DESC_HI);
                 }
               }
             }
           }
-          umma_commit_u32(empty0 + st * 8);         // frees the smem stage once these MMAs have read it
+          // frees the smem stage once these MMAs have read it (in every CTA of the cluster: peers multicast into it)
+          if constexpr (CL > 1) umma_commit_mc_u32(empty0 + st * 8, CMASK);
+          else umma_commit_u32(empty0 + st * 8);
           if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
         }
         umma_commit_u32(tfull0 + as * 8);           // accumulators complete -> epilogue
@@ -248,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int row = quad * 32 + lane;
     constexpr int NCHUNK = MT * (BN / 32);       // 32-column chunks per work item
     uint32_t ti = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+    for (int item = item0; item < n_items; item += item_step, ++ti) {
       const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
       const uint32_t as = ti % Cfg::TSTAGES;
       // The residual (identity) tile does not depend on the accumulator: its loads are software-pipelined one chunk ahead, and
@@ -257,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint4 rh[4], rl[4];
       auto fetch_residual = [&](int chunk) {
         const int t = chunk / (BN / 32), c0 = (chunk % (BN / 32)) * 32;
-        const long long m = (long long)(mg * MT + t) * BM_TC + row;
+        const long long m = (long long)(mg * GROUP + crank + t) * BM_TC + row;
         if (p.res_hi && chunk < NCHUNK && m < p.m_total && TC_EPI_IO(p)) {
           const size_t o = (size_t)m * p.cout + (size_t)nt * BN + c0;
 #pragma unroll
@@ -273,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll 1
       for (int chunk = 0; chunk < NCHUNK; ++chunk) {
         const int t = chunk / (BN / 32), c0 = (chunk % (BN / 32)) * 32;
-        const long long m = (long long)(mg * MT + t) * BM_TC + row;
+        const long long m = (long long)(mg * GROUP + crank + t) * BM_TC + row;
         const bool valid = m < p.m_total;
         const size_t obase = (size_t)m * p.cout + (size_t)nt * BN;
         uint32_t v[32], vl[32];
@@ -349,6 +381,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();      // no CTA leaves while a peer may still multicast into it / commit to it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -713,7 +746,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct TcLayerMaps {
   CUtensorMap a_hi, a_lo, w_hi, w_lo;
-  CUtensorMap w2_hi, w2_lo;     // half-tile (BN/2 rows) boxes for the CTA-pair kernel
+  CUtensorMap w2_hi, w2_lo;     // half-tile (BN/2 rows) boxes for the CTA-pair kernel and the 2-CTA multicast clusters
+  CUtensorMap w4_hi, w4_lo;     // quarter-tile boxes for the 4-CTA multicast clusters
+  // BK = 32 stages: boxes of 32 K elements, SWIZZLE_64B (w32h = half-tile rows for the 2-CTA multicast clusters)
+  CUtensorMap a32_hi, a32_lo, w32_hi, w32_lo, w32h_hi, w32h_lo;
 };
 
 struct TcState {
@@ -818,9 +854,9 @@ int tc_pack(straps_regressor* r, const float* const* conv_w, cudaStream_t st) {
 }
 
 static int encode(TcState* t, CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                  const cuuint32_t* box, const cuuint32_t* estr) {
+                  const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUresult rc = t->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu %llu, box %u %u %u %u)", (int)rc,
@@ -883,6 +919,14 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     cuuint32_t box2[2] = {64, (cuuint32_t)((c.cout == 64 ? 64 : 128) / 2)};
     if (encode(t, &out.w2_hi, w_hi, 2, dims, str, box2, es)) return 1;
     if (encode(t, &out.w2_lo, w_lo, 2, dims, str, box2, es)) return 1;
+    cuuint32_t box4[2] = {64, (cuuint32_t)((c.cout == 64 ? 64 : 128) / 4)};
+    if (encode(t, &out.w4_hi, w_hi, 2, dims, str, box4, es)) return 1;
+    if (encode(t, &out.w4_lo, w_lo, 2, dims, str, box4, es)) return 1;
+    cuuint32_t b32[2] = {32, (cuuint32_t)bn}, b32h[2] = {32, (cuuint32_t)((c.cout == 64 ? 64 : 128) / 2)};
+    if (encode(t, &out.w32_hi, w_hi, 2, dims, str, b32, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (encode(t, &out.w32_lo, w_lo, 2, dims, str, b32, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (encode(t, &out.w32h_hi, w_hi, 2, dims, str, b32h, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (encode(t, &out.w32h_lo, w_lo, 2, dims, str, b32h, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   }
   if (c.conv1) {
     // conv1: (flattened kw,c run | ow | oh | b) over the padded input, strides bake in the stride-2 sampling
@@ -892,6 +936,9 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (encode(t, &out.a_hi, a_hi, 4, dims, str, box, es)) return 1;
     if (encode(t, &out.a_lo, a_lo, 4, dims, str, box, es)) return 1;
+    box[0] = 32;
+    if (encode(t, &out.a32_hi, a_hi, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (encode(t, &out.a32_lo, a_lo, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   } else {
     const int th = (c.hout * c.wout >= BM_TC) ? BM_TC / c.wout : c.hout;
     const int nb = BM_TC / (c.wout * th);
@@ -901,6 +948,9 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     cuuint32_t es[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
     if (encode(t, &out.a_hi, a_hi, 4, dims, str, box, es)) return 1;
     if (encode(t, &out.a_lo, a_lo, 4, dims, str, box, es)) return 1;
+    box[0] = 32;
+    if (encode(t, &out.a32_hi, a_hi, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (encode(t, &out.a32_lo, a_lo, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   }
   return 0;
 }
@@ -918,18 +968,51 @@ static int build_maps(straps_regressor* r, int B, std::vector<TcLayerMaps>& out)
   return 0;
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int BK = 64>
 static int launch_conv_tc(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
-  using Cfg = TcCfg<BN, MT>;
+  using Cfg = TcCfg<BN, MT, BK>;
   static bool attr_set = false;
   if (!attr_set) {
-    STRAPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    STRAPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MT, 1, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int items = ((p.n_mtiles + MT - 1) / MT) * p.n_ntiles;
   const int grid = items < num_sms ? items : num_sms;
-  conv_tc_kernel<BN, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w_hi, m.w_lo, p);
+  if (BK == 64) conv_tc_kernel<BN, MT, 1, BK><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w_hi, m.w_lo, p);
+  else conv_tc_kernel<BN, MT, 1, BK><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a32_hi, m.a32_lo, m.w32_hi, m.w32_lo, p);
   STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+// cluster variant: CL CTAs along M share the weight tile through TMA multicast
+template <int BN, int CL, int BK = 64>
+static int launch_conv_tc_cl(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg<BN, 1, BK>;
+  static_assert(BK == 64 || CL == 2, "BK = 32 has half-tile weight maps only");
+  static bool attr_set = false;
+  if (!attr_set) {
+    STRAPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, CL, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int items = ((p.n_mtiles + CL - 1) / CL) * p.n_ntiles;
+  const int clusters = items < num_sms / CL ? items : num_sms / CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(CL * clusters, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const CUtensorMap& ah = (BK == 64) ? m.a_hi : m.a32_hi;
+  const CUtensorMap& al = (BK == 64) ? m.a_lo : m.a32_lo;
+  const CUtensorMap& wh = (BK == 32) ? m.w32h_hi : (CL == 2) ? m.w2_hi : m.w4_hi;
+  const CUtensorMap& wl = (BK == 32) ? m.w32h_lo : (CL == 2) ? m.w2_lo : m.w4_lo;
+  STRAPS_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 1, CL, BK>, ah, al, wh, wl, p));
+  straps::count_launch();
   return 0;
 }
 
@@ -955,22 +1038,36 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
   p.n_mtiles = (int)((p.m_total + BM_TC - 1) / BM_TC);
   p.n_ntiles = c.cout / bn;
   p.conv1 = c.conv1;
-  p.n_kblocks = c.k_eff / BK_TC;
-  p.cchunks = c.cin / 64;
+  // STRAPS_TC_BK = 32 | 64: K elements per pipeline stage (see TcCfg); STRAPS_TC_MCAST = 2 | 4: clusters of that many CTAs share
+  // each weight tile through TMA multicast
+  static const int bk = [] { const char* e = getenv("STRAPS_TC_BK"); const int v = e ? atoi(e) : TC_DEFAULT_BK; return v == 32 ? 32 : 64; }();
+  static const int mc = [] { const char* e = getenv("STRAPS_TC_MCAST"); return e ? atoi(e) : 0; }();
+  int mt;
+  { int bn2; tile_cfg(c.cout, &bn2, &mt); }
+  const bool k32 = (bk == 32) && mt == 1 && bn <= 128;
+  const int kb_elems = k32 ? 32 : BK_TC;
+  p.n_kblocks = c.k_eff / kb_elems;
+  p.cchunks = c.cin / kb_elems;
   p.kw_count = c.ksize;
   p.stride = c.stride; p.pad = c.pad;
   p.hw_out = c.hout * c.wout; p.wout = c.wout;
   p.th = (c.hout * c.wout >= BM_TC) ? BM_TC / c.wout : c.hout;
   p.cout = c.cout;
   { const char* d = getenv("STRAPS_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
-  int mt;
-  { int bn2; tile_cfg(c.cout, &bn2, &mt); }
   {
     // STRAPS_TC_PAIR: "128" = CTA pairs for the Cout >= 128 layers, "all" = every layer, unset/"0" = single-CTA kernels
     const char* e = getenv("STRAPS_TC_PAIR");
     const bool pair = e && ((e[0] == 'a') || (e[0] == '1' && c.cout >= 128));
-    if (pair && mt == 1 && bn <= 128 && !p.res_f32)
+    if (pair && mt == 1 && bn <= 128 && !p.res_f32 && !k32)
       return bn == 64 ? launch_conv_tc2<64>(m, p, t->num_sms, st) : launch_conv_tc2<128>(m, p, t->num_sms, st);
+  }
+  if (k32) {
+    if (mc == 2) return bn == 64 ? launch_conv_tc_cl<64, 2, 32>(m, p, t->num_sms, st) : launch_conv_tc_cl<128, 2, 32>(m, p, t->num_sms, st);
+    return bn == 64 ? launch_conv_tc<64, 1, 32>(m, p, t->num_sms, st) : launch_conv_tc<128, 1, 32>(m, p, t->num_sms, st);
+  }
+  if ((mc == 2 || mc == 4) && mt == 1 && bn <= 128) {
+    if (bn == 64) return mc == 2 ? launch_conv_tc_cl<64, 2>(m, p, t->num_sms, st) : launch_conv_tc_cl<64, 4>(m, p, t->num_sms, st);
+    return mc == 2 ? launch_conv_tc_cl<128, 2>(m, p, t->num_sms, st) : launch_conv_tc_cl<128, 4>(m, p, t->num_sms, st);
   }
   if (bn == 64) return mt == 2 ? launch_conv_tc<64, 2>(m, p, t->num_sms, st) : launch_conv_tc<64, 1>(m, p, t->num_sms, st);
   if (bn == 256) return launch_conv_tc<256, 1>(m, p, t->num_sms, st);

@@ -4,7 +4,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libstraps_b200.so')
+# STRAPS_B200_LIB selects another build of the same ABI (tools/conv_experiment.sh uses the -DSTRAPS_TC_EXPERIMENTS one)
+LIB_PATH = os.environ.get('STRAPS_B200_LIB') or os.path.join(_HERE, 'libstraps_b200.so')
 CSRC_DIR = os.path.join(os.path.dirname(_HERE), 'csrc')
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
