@@ -122,3 +122,33 @@ def test_two_conv_modes_agree(assets_root):
         f0 = _regressor(C, 'fp32_simt', sd).image_encoder(x)
         f1 = _regressor(C, 'f16x3_tc', sd).image_encoder(x)
     assert rel_l2(f1.cpu().numpy(), f0.cpu().numpy()) < 5e-5   # tensor-core fp32 accumulation truncates
+
+
+def test_cuda_graph_replay_is_bit_identical(assets_root):
+    """The whole hot path (encoder -> IEF -> rot6d -> SMPL) captured once and replayed on new inputs equals the eager calls
+    bit for bit (same kernels, same order); wrong shapes are refused."""
+    import config
+    from models.smpl_official import SMPL
+    from straps_b200.graphs import GraphedCallable
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    from straps_b200._lib import StrapsError
+    C, B = 17, 4
+    reg = _regressor(C, 'f16x3_tc', O.make_regressor_state(C, seed=5))
+    smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(DEV)
+
+    def hot_path(x):
+        cam, pose, shape = reg(x)
+        R = rot6d_to_rotmat(pose.contiguous()).view(-1, 24, 3, 3)
+        out = smpl(body_pose=R[:, 1:], global_orient=R[:, 0].unsqueeze(1), betas=shape, pose2rot=False)
+        return cam, out.vertices, out.joints
+    xs = [torch.from_numpy(synthetic_inputs.make_proxy_batch(B, C, seed=s)).to(DEV) for s in (11, 12)]
+    with torch.no_grad():
+        eager = [[t.clone() for t in hot_path(x)] for x in xs]
+    graphed = GraphedCallable(hot_path, xs[0])
+    for x, ref in zip(xs, eager):
+        got = graphed(x)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(got, ref))
+    assert not torch.equal(eager[0][1], eager[1][1])
+    with pytest.raises(StrapsError):
+        graphed(xs[0][:2])
