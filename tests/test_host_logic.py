@@ -70,3 +70,12 @@ def test_visibility_mask_and_proxy_inputs():
     assert set(np.unique(x[:, 0])) <= {0.0, 1.0}
     assert all(int((x[0, c] != 0).sum()) == 256 for c in range(1, 17))
     assert np.array_equal(x, synthetic_inputs.make_proxy_batch(2, 17, seed=3))
+
+
+def test_round2_halo_scheme_matches_conv2d():
+    """tools/halo_emulation.py: the padded-raster / halo-tile / tap-shift index arithmetic planned for round 2 equals conv2d."""
+    import subprocess
+    import sys
+    from conftest import REPO
+    res = subprocess.run([sys.executable, os.path.join(REPO, 'tools', 'halo_emulation.py')], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and 'halo scheme == conv2d' in res.stdout, res.stdout[-1000:] + res.stderr[-1000:]
