@@ -42,7 +42,7 @@ print(json.dumps(out))
 
 def _run(env_extra):
     env = dict(os.environ)
-    for k in ('STRAPS_TC_MCAST', 'STRAPS_TC_BK', 'STRAPS_TC_TILES', 'STRAPS_TC_PAIR', 'STRAPS_TC_DS_OVERLAP'):
+    for k in ('STRAPS_TC_MCAST', 'STRAPS_TC_BK', 'STRAPS_TC_TILES', 'STRAPS_TC_PAIR', 'STRAPS_TC_DS_OVERLAP', 'STRAPS_TC_EPI_WARPS'):
         env.pop(k, None)
     env.update(env_extra)
     script = _SCRIPT % {'pkg': PKG, 'oracle': ORACLE, 'assets': os.path.join(REPO, 'tests', '_scratch', 'assets')}
@@ -56,8 +56,14 @@ def shipped(assets_root):
     return _run({})
 
 
+# variants written after the round's GPU budget was spent: compiled and reviewed but never run on hardware; they join the list above
+# once a run with STRAPS_TEST_UNVERIFIED=1 has passed
+_UNVERIFIED = pytest.mark.skipif(not os.environ.get('STRAPS_TEST_UNVERIFIED'), reason='not yet run on hardware (set STRAPS_TEST_UNVERIFIED=1)')
+
+
 @pytest.mark.parametrize('env', [{'STRAPS_TC_MCAST': '2'}, {'STRAPS_TC_MCAST': '4'}, {'STRAPS_TC_BK': '32'},
-                                 {'STRAPS_TC_BK': '32', 'STRAPS_TC_MCAST': '2'}, {'STRAPS_TC_DS_OVERLAP': '0'}],
+                                 {'STRAPS_TC_BK': '32', 'STRAPS_TC_MCAST': '2'}, {'STRAPS_TC_DS_OVERLAP': '0'},
+                                 pytest.param({'STRAPS_TC_EPI_WARPS': '8'}, marks=_UNVERIFIED)],
                          ids=lambda e: ','.join('%s=%s' % (k[10:], v) for k, v in e.items()))
 def test_variant_matches_shipped_configuration(env, shipped):
     got = _run(env)
