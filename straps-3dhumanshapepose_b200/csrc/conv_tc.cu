@@ -394,6 +394,524 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Halo variant for the stride-1 3x3 convolutions with Cin = Cout = BN (layer1: 64x64x64, layer2: 32x32x128) -- STRAPS_TC_HALO=1.
+// Run on B200 once, at the very end of round 1 (tools/halo_check.py, profiles/r01_halo_check.json): CORRECT on the first run --
+// layer1 bit-identical to conv_tc_kernel (one channel chunk: same K order), layer2 6e-7 (chunk-major instead of tap-major K order) --
+// but NOT faster: encoder 1.584 ms shipped, 1.604 with layer1 on this kernel, 1.611 with layer2, 1.676 with both.  Halving the bytes
+// TMA brings into the SM therefore does not shorten these layers: their epilogue (16-byte per-thread stores at a 128 / 256-byte
+// stride) is at least an equal limit.  Kept off by default as the vehicle for the round-2 epilogue work.
+//
+// conv_tc_kernel fetches one 128-pixel A tile per filter tap: 9 x 32 KB per 64-channel chunk, and the kernel is paced by the bytes
+// TMA brings INTO the SM.  Here the outputs of an image are enumerated on a virtual zero-padded raster of
+// (H+2) x (W+2) positions, an M-tile is 128 CONSECUTIVE raster positions p0 .. p0+127, and per 64-channel chunk ONE box
+// {64 channels, W+2 pixels, RH rows} is loaded from the UNPADDED NHWC planes, starting at pixel -1 / image row r0-2: TMA's
+// out-of-bounds zero fill materialises the border, so shared memory holds raster rows r0 .. r0+RH-1, one 128-byte line per position.
+// Tap (kh, kw) is the 128-line window starting at line (p0 - r0 (W+2)) + (kh-1)(W+2) + (kw-1): the same UMMA descriptor with a
+// shifted start address.  Border positions are computed and discarded by the epilogue.  Bytes into the SM per image:
+// layer1 13.8 -> 7.7 MB, layer2 9.2 -> 6.3 MB.  Two rings: AS halo stages (hi + lo plane) and WS weight stages (one per tap).
+// ---------------------------------------------------------------------------------------------------------
+struct HaloParams {
+  int n_items;            // batch * tiles_per_image
+  int tiles_per_image;    // tiles that contain at least one interior position
+  int H, W;               // input = output size
+  int cchunks;            // Cin / 64
+  int cout;
+  const float* shift;
+  const float* unscale;
+  __half* out_hi;
+  __half* out_lo;
+  const __half* res_hi;   // residual (identity) planes or null
+  const __half* res_lo;
+  int relu;
+};
+
+template <int BN, int RH, int WP>
+struct HaloCfg {
+  static constexpr int A_LINES = RH * WP;                                    // raster positions held per plane
+  static constexpr int A_BOX_BYTES = A_LINES * 128;                           // what one TMA box delivers
+  static constexpr int A_PLANE = (A_BOX_BYTES + 1023) / 1024 * 1024;          // planes start on swizzle-atom boundaries
+  static constexpr int A_STAGE = 2 * A_PLANE;
+  static constexpr int AS = 2;
+  static constexpr int W_BYTES = BN * 128;
+  static constexpr int W_STAGE = 2 * W_BYTES;                                 // [W_hi ; W_lo] adjacent: one wide MMA reads both
+  static constexpr int WS = 3;
+  static constexpr int W_OFF = AS * A_STAGE;
+  static constexpr int SMEM_BYTES = AS * A_STAGE + WS * W_STAGE + 1024 + 256;
+  static constexpr int TILE_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * TILE_COLS;
+  // every tap window [start, start + 128) lies inside the box: the tile's positions and their 3x3 neighbourhoods span
+  // 128 + 2 WP + 2 consecutive positions, which touch at most ceil(that / WP) + 1 raster rows
+  static_assert(RH * WP >= 128 + 2 * WP + 2 + WP - 1, "halo box too small");
+  static_assert(WP <= 256 && RH <= 256, "TMA box dimensions are limited to 256");
+  static_assert(SMEM_BYTES <= 232448 && TMEM_COLS <= 512, "halo tile configuration does not fit");
+};
+
+template <int BN, int RH, int WP, int EPW = 4>
+__global__ void __launch_bounds__(64 + 32 * EPW, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const HaloParams p) {
+  using Cfg = HaloCfg<BN, RH, WP>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::AS * Cfg::A_STAGE + Cfg::WS * Cfg::W_STAGE);
+  uint64_t* a_full = bars;                          // [AS]
+  uint64_t* a_empty = a_full + Cfg::AS;             // [AS]
+  uint64_t* w_full = a_empty + Cfg::AS;             // [WS]
+  uint64_t* w_empty = w_full + Cfg::WS;             // [WS]
+  uint64_t* tfull = w_empty + Cfg::WS;              // [2]
+  uint64_t* tempty = tfull + 2;                     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::AS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < Cfg::WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * EPW); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty), w_full0 = smem_u32(w_full), w_empty0 = smem_u32(w_empty);
+  const int tpi = p.tiles_per_image, cchunks = p.cchunks;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // ================= TMA producer: per 64-channel chunk one halo box (2 planes), then its 9 weight tiles =================
+      uint32_t as = 0, aph = 1, ws = 0, wph = 1;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int b = item / tpi, t = item - b * tpi;
+        const int p0 = t * BM_TC;
+        const int r0 = (p0 + WP - 1) / WP - 2;            // = floor((p0 - WP - 1) / WP): raster row of box row 0 (-2 for the first tile)
+        for (int cc = 0; cc < cchunks; ++cc) {
+          const uint32_t sa = smem0 + as * Cfg::A_STAGE, fb = a_full0 + as * 8;
+          mbar_wait_u32(a_empty0 + as * 8, aph);
+          mbar_expect_tx_u32(fb, 2 * Cfg::A_BOX_BYTES);
+          // image coordinates of the box origin: pixel -1 (left border), row r0 - 1 (raster row r = image row r - 1)
+          tma_load_4d_u32(sa, &map_a_hi, fb, cc * 64, -1, r0 - 1, b);
+          tma_load_4d_u32(sa + Cfg::A_PLANE, &map_a_lo, fb, cc * 64, -1, r0 - 1, b);
+          if (++as == Cfg::AS) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t sw = smem0 + Cfg::W_OFF + ws * Cfg::W_STAGE, wb = w_full0 + ws * 8;
+            mbar_wait_u32(w_empty0 + ws * 8, wph);
+            mbar_expect_tx_u32(wb, Cfg::W_STAGE);
+            const int wk = (tap * cchunks + cc) * BK_TC;  // K offset of (tap, chunk) in the [Cout][(kh, kw, ci)] weight rows
+            tma_load_2d_u32(sw, &map_w_hi, wb, wk, 0);
+            tma_load_2d_u32(sw + Cfg::W_BYTES, &map_w_lo, wb, wk, 0);
+            if (++ws == Cfg::WS) { ws = 0; wph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      // ================= MMA issuer: 9 taps = 9 row-shifted windows of the same halo tile =================
+      constexpr uint32_t idesc = umma_idesc_f16(BM_TC, BN);
+      constexpr uint32_t idesc_wide = umma_idesc_f16(BM_TC, 2 * BN);
+      static_assert(2 * BN <= 256, "the merged [W_hi ; W_lo] MMA needs N <= 256");
+      const uint32_t tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, acs = 0, acph = 1;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int t = item % tpi;
+        const int p0 = t * BM_TC;
+        const int r0 = (p0 + WP - 1) / WP - 2;
+        const int base = p0 - r0 * WP;                    // line of the tile's first position inside the box (>= WP + 1)
+        mbar_wait_u32(tempty0 + acs * 8, acph);
+        tc_fence_after();
+        const uint32_t d_hi = tmem_base + acs * Cfg::TILE_COLS, d_lo = d_hi + BN;
+        uint32_t accum = 0;
+        for (int cc = 0; cc < cchunks; ++cc) {
+          mbar_wait_u32(a_full0 + as * 8, aph);
+          tc_fence_after();
+          const uint32_t a0 = umma_desc_sw128_lo(smem0 + as * Cfg::A_STAGE);
+          int start = base - WP - 1;                      // tap (0, 0)
+          for (int kh = 0; kh < 3; ++kh, start += WP - 3)
+            for (int kw = 0; kw < 3; ++kw, ++start) {
+              mbar_wait_u32(w_full0 + ws * 8, wph);
+              tc_fence_after();
+              const uint32_t a_hi = a0 + (uint32_t)start * 8u;          // 128 bytes per line = 8 descriptor units
+              const uint32_t a_lo = a_hi + (Cfg::A_PLANE >> 4);
+              const uint32_t w_hi = umma_desc_sw128_lo(smem0 + Cfg::W_OFF + ws * Cfg::W_STAGE);
+#pragma unroll
+              for (int k = 0; k < BK_TC / 16; ++k) {
+                umma_f16_lohi(d_hi, a_hi + 2 * k, w_hi + 2 * k, idesc_wide, accum);      // A_hi.[W_hi ; W_lo] -> [acc_hi | acc_lo]
+                umma_f16_lohi(d_lo, a_lo + 2 * k, w_hi + 2 * k, idesc, 1);               // A_lo.W_hi
+                accum = 1;
+              }
+              umma_commit_u32(w_empty0 + ws * 8);
+              if (++ws == Cfg::WS) { ws = 0; wph ^= 1; }
+            }
+          umma_commit_u32(a_empty0 + as * 8);
+          if (++as == Cfg::AS) { as = 0; aph ^= 1; }
+        }
+        umma_commit_u32(tfull0 + acs * 8);
+        if (++acs == 2) { acs = 0; acph ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue: raster position -> pixel, border positions discarded =================
+    static_assert(EPW == 4 || EPW == 8, "one or two epilogue warps per TMEM lane quadrant");
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    constexpr int NCHUNK = BN / 32;
+    constexpr int CSTEP = EPW / 4;
+    const int part = (EPW > 4) ? ((warp - 2) >> 2) : 0;
+    uint32_t ti = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++ti) {
+      const int b = item / tpi, t = item - b * tpi;
+      const int pos = t * BM_TC + row;
+      const int py = pos / WP, px = pos - py * WP;
+      const bool valid = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
+      const size_t obase = (((size_t)b * p.H + (py - 1)) * p.W + (px - 1)) * p.cout;   // only used when valid
+      const uint32_t acs = ti & 1;
+      uint4 rh[4], rl[4];
+      auto fetch_residual = [&](int chunk) {
+        if (p.res_hi && chunk < NCHUNK && valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + obase + chunk * 32) + q);
+            rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + obase + chunk * 32) + q);
+          }
+        }
+      };
+      fetch_residual(part);
+      mbar_wait(&tfull[acs], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = part; chunk < NCHUNK; chunk += CSTEP) {
+        const int c0 = chunk * 32;
+        uint32_t v[32], vl[32];
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + acs * Cfg::TILE_COLS + c0;
+        tmem_ld_32x32(tacc, v);
+        tmem_ld_32x32(tacc + BN, vl);
+        tmem_ld_wait();
+        float y[32];
+        const float4* sh4 = reinterpret_cast<const float4*>(p.shift + c0);
+        const float4* us4 = reinterpret_cast<const float4*>(p.unscale + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
+          y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
+          y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
+          y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
+          y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+        }
+        if (valid && p.res_hi) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t hw[4] = {rh[q].x, rh[q].y, rh[q].z, rh[q].w}, lw[4] = {rl[q].x, rl[q].y, rl[q].z, rl[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              y[q * 8 + e * 2 + 0] += f16lo_to_f(hw[e]) + f16lo_to_f(lw[e]);
+              y[q * 8 + e * 2 + 1] += f16hi_to_f(hw[e]) + f16hi_to_f(lw[e]);
+            }
+          }
+        }
+        fetch_residual(chunk + CSTEP);
+        if (valid) {
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
+          }
+          uint32_t ph[16], pl[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __half h0, l0, h1, l1;
+            split_f16(y[2 * i], h0, l0);
+            split_f16(y[2 * i + 1], h1, l1);
+            ph[i] = pack_f16(h0, h1);
+            pl[i] = pack_f16(l0, l1);
+          }
+          uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
+          uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
+            ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acs]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv1 (7x7 / stride 2 / pad 3, Cout = 64) from a pixel-PAIR layout of the padded input -- STRAPS_TC_CONV1=s2d | s2d2.
+// WRITTEN AFTER THE ROUND'S GPU BUDGET WAS SPENT: compiled, its index arithmetic replayed against conv2d on the CPU
+// (tools/conv1_s2d_emulation.py); NOT yet run on hardware, and the default path never reaches it.  It applies to conv1 what
+// conv_halo_kernel proved on hardware for the 3x3 layers (row-shifted SWIZZLE_128B descriptors over one TMA box).
+//
+// conv_tc_kernel reads conv1's A operand as 21 K-blocks of 128 x 64 elements per output row (672 KB of A + 336 KB of W per tile in
+// 84 TMA operations) although an output row only depends on 7 input rows (7 x 262 pixels x 24 channels x 2 planes = 176 KB), and
+// conv1 is paced by exactly that TMA stream (516 us with the MMAs off, 307 us with the TMA traffic off).  Here the
+// padded input is stored as pixel PAIRS:  xs[b][ph][q][0..23] = padded pixel 2q, [24..47] = padded pixel 2q+1, one 128-byte line
+// per pair (elements 48..63 unused; ph = h + 3, padded pixel = w + 3).  Output pixel ow and filter tap pair kw' = kw / 2 read pair
+// ow + kw', so for one filter row kh the whole A operand of an output row is ONE box of 131 lines {pairs 0..130 of input row
+// 2 oh + kh}, and tap pair kw' is the 128-line window that starts at line kw' (descriptor start address + kw' * 128 B).
+// K inside a filter row is ordered (kw, c) = kw' * 48 + (kw & 1) * 24 + c -- exactly the order of the existing conv1 weight rows
+// (C1_KROW = 192 per filter row, kw = 7 zero), so the packed weights are shared with conv_tc_kernel.  K step j = 0..10 of a filter
+// row (16 elements; step 11 is all padding) reads A at window j / 3, byte offset (j % 3) * 32, and W at chunk j / 4, byte offset
+// (j % 4) * 32.  W_hi and W_lo of conv1 are adjacent in HBM, so one 2-D box {64, 128} of the [2 x 64][1344] view brings the
+// [W_hi ; W_lo] chunk of the wide MMA in one operation.
+// Per output row: 7 x (2 x 16.4 KB A + 48 KB W) = 565 KB in 35 TMA operations (MT = 2: two output rows share the weights, 400 KB
+// per row) against 1008 KB in 84.  Two rings: NA slots of one input row (hi + lo plane), NW slots of one weight chunk.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int XS_H = 262, XS_PAIRS = 132;          // padded rows / pixel pairs per padded row of the pair layout
+constexpr int S2D_LINES = 131;                     // pairs 0..130 serve output pixels 0..127 with tap pairs 0..3
+
+struct S2dParams {
+  int n_items;            // groups of MT output rows
+  int n_rows;             // batch * 128 output rows
+  uint32_t a_bytes;       // bytes ONE A box delivers (131 lines x bytes per pair line in HBM)
+  const float* shift;
+  const float* unscale;
+  float* out;             // NHWC fp32 [B,128,128,64]
+  int relu;
+};
+
+template <int MT>
+struct S2dCfg {
+  static constexpr int A_PLANE = 17 * 1024;                         // 131 lines x 128 B = 16,768 B; planes start on swizzle atoms
+  static constexpr int A_SLOT = 2 * A_PLANE;                        // hi + lo plane of one input row
+  static constexpr int NA = (MT == 1) ? 3 : 4;
+  static constexpr int W_SLOT = 128 * 128;                          // [W_hi (64 rows) ; W_lo (64 rows)] x 64 K elements
+  static constexpr int NW = (MT == 1) ? 6 : 5;
+  static constexpr int W_OFF = NA * A_SLOT;
+  static constexpr int BAR_OFF = W_OFF + NW * W_SLOT;
+  static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256;
+  static constexpr int TILE_COLS = 128;                             // [acc_hi (64) | acc_lo (64)]
+  static constexpr int ACC_COLS = MT * TILE_COLS;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(S2D_LINES * 128 <= A_PLANE, "A plane too small");
+  static_assert(3 + 128 <= S2D_LINES, "the last tap window must lie inside the box");
+  static_assert(NA % MT == 0, "the rows of one filter-row step occupy consecutive ring slots");
+  static_assert(SMEM_BYTES <= 232448 && TMEM_COLS <= 512 && 2 * (NA + NW) * 8 + 40 <= 256, "conv1 pair-layout configuration does not fit");
+};
+
+template <int MT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv1_s2d_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w, const S2dParams p) {
+  using Cfg = S2dCfg<MT>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* a_full = bars;                          // [NA]
+  uint64_t* a_empty = a_full + Cfg::NA;             // [NA]
+  uint64_t* w_full = a_empty + Cfg::NA;             // [NW]
+  uint64_t* w_empty = w_full + Cfg::NW;             // [NW]
+  uint64_t* tfull = w_empty + Cfg::NW;              // [2]
+  uint64_t* tempty = tfull + 2;                     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < Cfg::NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty), w_full0 = smem_u32(w_full), w_empty0 = smem_u32(w_empty);
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // ================= TMA producer: per filter row the input row of every tile of the item, then the 3 weight chunks =================
+      uint32_t as = 0, aph = 1, ws = 0, wph = 1;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int r_first = item * MT;                    // output row index over (b, oh); 128 rows per image, MT divides 128
+        const int b = r_first >> 7, oh0 = r_first & 127;
+        for (int kh = 0; kh < 7; ++kh) {
+#pragma unroll
+          for (int t = 0; t < MT; ++t) {
+            const uint32_t sa = smem0 + as * Cfg::A_SLOT, fb = a_full0 + as * 8;
+            mbar_wait_u32(a_empty0 + as * 8, aph);
+            mbar_expect_tx_u32(fb, 2 * p.a_bytes);
+            // rows past the end of the batch (last item of an odd row count) land out of bounds -> zeros, never stored
+            tma_load_4d_u32(sa, &map_a_hi, fb, 0, 0, 2 * (oh0 + t) + kh, b);
+            tma_load_4d_u32(sa + Cfg::A_PLANE, &map_a_lo, fb, 0, 0, 2 * (oh0 + t) + kh, b);
+            if (++as == Cfg::NA) { as = 0; aph ^= 1; }
+          }
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            const uint32_t wb = w_full0 + ws * 8;
+            mbar_wait_u32(w_empty0 + ws * 8, wph);
+            mbar_expect_tx_u32(wb, Cfg::W_SLOT);
+            tma_load_2d_u32(smem0 + Cfg::W_OFF + ws * Cfg::W_SLOT, &map_w, wb, kh * C1_KROW + c * 64, 0);
+            if (++ws == Cfg::NW) { ws = 0; wph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      // ================= MMA issuer: 11 K steps per filter row, tap pairs = line-shifted windows of the row's box =================
+      constexpr uint32_t idesc = umma_idesc_f16(BM_TC, 64);
+      constexpr uint32_t idesc_wide = umma_idesc_f16(BM_TC, 128);
+      const uint32_t tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
+      const uint32_t adesc0 = umma_desc_sw128_lo(smem0), wdesc0 = umma_desc_sw128_lo(smem0 + Cfg::W_OFF);
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, acs = 0, acph = 1;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        mbar_wait_u32(tempty0 + acs * 8, acph);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + acs * Cfg::ACC_COLS;
+        uint32_t accum = 0;
+        for (int kh = 0; kh < 7; ++kh) {
+          // the MT input rows of this step sit in the consecutive slots as .. as + MT - 1 (NA is a multiple of MT: no wrap inside)
+#pragma unroll
+          for (int t = 0; t < MT; ++t) mbar_wait_u32(a_full0 + (as + t) * 8, aph);
+          tc_fence_after();
+          uint32_t wd = 0;
+#pragma unroll
+          for (int j = 0; j < 11; ++j) {
+            if ((j & 3) == 0) {
+              mbar_wait_u32(w_full0 + ws * 8, wph);
+              tc_fence_after();
+              wd = wdesc0 + ws * (Cfg::W_SLOT >> 4);
+            }
+            const uint32_t w_k = wd + (j & 3) * 2;                         // +32 bytes along K inside the weight chunk
+            const uint32_t a_off = (j / 3) * 8 + (j % 3) * 2;              // window (j / 3) lines down, +32 bytes along K inside the pair
+#pragma unroll
+            for (int t = 0; t < MT; ++t) {
+              const uint32_t a_hi = adesc0 + (as + t) * (Cfg::A_SLOT >> 4) + a_off, a_lo = a_hi + (Cfg::A_PLANE >> 4);
+              const uint32_t d_hi = acc + t * Cfg::TILE_COLS, d_lo = d_hi + 64;
+              umma_f16_lohi(d_hi, a_hi, w_k, idesc_wide, accum);           // A_hi.[W_hi ; W_lo] -> [acc_hi | acc_lo]
+              umma_f16_lohi(d_lo, a_lo, w_k, idesc, 1);                    // A_lo.W_hi
+            }
+            accum = 1;
+            if ((j & 3) == 3 || j == 10) {
+              umma_commit_u32(w_empty0 + ws * 8);
+              if (++ws == Cfg::NW) { ws = 0; wph ^= 1; }
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < MT; ++t) umma_commit_u32(a_empty0 + (as + t) * 8);
+          as += MT;
+          if (as == Cfg::NA) { as = 0; aph ^= 1; }
+        }
+        umma_commit_u32(tfull0 + acs * 8);
+        if (++acs == 2) { acs = 0; acph ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..5: BatchNorm shift, ReLU, fp32 NHWC stores =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint32_t ti = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++ti) {
+      const uint32_t acs = ti & 1;
+      mbar_wait(&tfull[acs], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < MT * 2; ++chunk) {
+        const int t = chunk >> 1, c0 = (chunk & 1) * 32;
+        const int r = item * MT + t;
+        const bool valid = r < p.n_rows;
+        uint32_t v[32], vl[32];
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + acs * Cfg::ACC_COLS + t * Cfg::TILE_COLS + c0;
+        tmem_ld_32x32(tacc, v);
+        tmem_ld_32x32(tacc + 64, vl);
+        tmem_ld_wait();
+        float y[32];
+        const float4* sh4 = reinterpret_cast<const float4*>(p.shift + c0);
+        const float4* us4 = reinterpret_cast<const float4*>(p.unscale + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
+          y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
+          y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
+          y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
+          y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+        }
+        if (valid) {
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
+          }
+          float4* o = reinterpret_cast<float4*>(p.out + ((size_t)r * BM_TC + row) * 64 + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acs]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// x NCHW fp32 [B,C,256,256] -> pixel-pair planes xs[B][262][132][PITCH] (hi, lo) for conv1_s2d_kernel.  One CTA per (b, h) image row:
+// the C channel rows are read with coalesced 1 KB requests, split to fp16 hi / lo and assembled in shared memory as the complete
+// padded row (pairs 0..131: the 3-pixel left border, the interior, the right border and the unused tail of every line are written
+// as zeros, so only the 6 border ROWS rely on the one-time memset), which then leaves as contiguous 16-byte stores.
+// PITCH = 64 elements (128-byte lines, the TMA box is {64, 131}) or 48 (dense pairs, box {48, 131}: TMA then fills 96 of the 128 bytes
+// of every shared-memory line -- smaller HBM footprint, to be confirmed on hardware).
+template <int PITCH>
+__global__ void __launch_bounds__(256) pack_input_s2d_kernel(const float* __restrict__ x, int C, __half* __restrict__ hi,
+                                                             __half* __restrict__ lo) {
+  constexpr int WPP = PITCH / 2;                                   // 32-bit words per pair line
+  constexpr int ROW_WORDS = XS_PAIRS * WPP;
+  __shared__ __align__(16) uint32_t srow[2][ROW_WORDS];
+  const int h = blockIdx.x, b = blockIdx.y, w = threadIdx.x;
+  for (int i = w; i < 2 * ROW_WORDS; i += 256) (&srow[0][0])[i] = 0u;
+  const float* src = x + ((size_t)b * C * IMG + h) * IMG + w;
+  float v[XP_C];
+#pragma unroll
+  for (int c = 0; c < XP_C; ++c) v[c] = (c < C) ? __ldg(src + (size_t)c * IMG * IMG) : 0.f;
+  __syncthreads();
+  const int pw = w + 3;                                            // padded pixel
+  const int pair = pw >> 1;
+  // PITCH 64: a pair line is 32 words = every bank once, so all lanes of a store would hit the same two banks; the 16-byte units of a
+  // line are therefore rotated by the pair index in shared memory (4-way conflicts, as for the dense layout) and rotated back below
+  auto phys = [&](int q, int word) { return (PITCH == 64) ? q * WPP + ((((word >> 2) + q) & 7) << 2) + (word & 3) : q * WPP + word; };
+#pragma unroll
+  for (int c = 0; c < XP_C; c += 2) {
+    __half h0, l0, h1, l1;
+    split_f16(v[c], h0, l0);
+    split_f16(v[c + 1], h1, l1);
+    const int o = phys(pair, (pw & 1) * (XP_C / 2) + c / 2);
+    srow[0][o] = pack_f16(h0, h1);
+    srow[1][o] = pack_f16(l0, l1);
+  }
+  __syncthreads();
+  const size_t base = ((size_t)b * XS_H + h + 3) * XS_PAIRS * PITCH;      // 16-byte aligned for PITCH 64 and 48
+  uint4* dh = reinterpret_cast<uint4*>(hi + base);
+  uint4* dl = reinterpret_cast<uint4*>(lo + base);
+  const uint4* sh = reinterpret_cast<const uint4*>(srow[0]);
+  const uint4* sl = reinterpret_cast<const uint4*>(srow[1]);
+  for (int i = w; i < ROW_WORDS / 4; i += 256) {
+    const int si = (PITCH == 64) ? (i & ~7) + (((i & 7) + (i >> 3)) & 7) : i;   // 8 units per 128-byte line: unit u of pair q sits at (u + q) & 7
+    dh[i] = sh[si];
+    dl[i] = sl[si];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): two CTAs of a cluster compute M = 256 output pixels together.  Each CTA stages its own
 // 128-pixel A tile but only HALF of the weight tile (BN/2 rows); the pair's MMA (issued by the leader) reads the other half
 // from the peer's shared memory, so per SM the weight bytes -- TMA writes and MMA operand reads -- halve.  That is the
@@ -755,6 +1273,9 @@ struct TcLayerMaps {
   CUtensorMap w4_hi, w4_lo;     // quarter-tile boxes for the 4-CTA multicast clusters
   // BK = 32 stages: boxes of 32 K elements, SWIZZLE_64B (w32h = half-tile rows for the 2-CTA multicast clusters)
   CUtensorMap a32_hi, a32_lo, w32_hi, w32_lo, w32h_hi, w32h_lo;
+  // halo boxes {64 channels, W + 2 pixels, RH rows} of the unpadded planes for conv_halo_kernel (halo = 1 when the layer qualifies)
+  CUtensorMap h_hi, h_lo;
+  int halo;
 };
 
 struct TcState {
@@ -773,6 +1294,12 @@ struct TcState {
   cudaStream_t side;
   cudaEvent_t ev_fork, ev_join;
   int ds_overlap;
+  // pixel-pair input planes of conv1_s2d_kernel (STRAPS_TC_CONV1=s2d | s2d2): allocated on first use, for max_batch
+  __half* xs;
+  size_t xs_plane;
+  int xs_pitch;                 // elements per pair line in HBM: 64 (default) or 48 (STRAPS_TC_S2D_PITCH=48)
+  struct S2dMaps { CUtensorMap a_hi, a_lo, w; };
+  std::map<int, S2dMaps> s2d_maps;
 };
 
 static inline __half* plane_hi(const straps_regressor* r, int buf) {
@@ -791,6 +1318,7 @@ int tc_create(straps_regressor* r) {
   r->tc = t;
   t->xp = nullptr; t->wpool = nullptr; t->encode = nullptr; t->num_sms = 148; t->train = nullptr;
   t->side = nullptr; t->ev_fork = t->ev_join = nullptr;
+  t->xs = nullptr; t->xs_plane = 0; t->xs_pitch = 64;
   { const char* e = getenv("STRAPS_TC_DS_OVERLAP"); t->ds_overlap = e ? atoi(e) : 1; }
   // The driver entry point is resolved at first use (no GPU / driver in the build container).
   t->xp_plane = (size_t)r->max_batch * XP_H * XP_W * XP_C;
@@ -833,6 +1361,7 @@ void tc_destroy(straps_regressor* r) {
   if (!t) return;
   tc_train_free(t);
   if (t->xp) cudaFree(t->xp);
+  if (t->xs) cudaFree(t->xs);
   if (t->wpool) cudaFree(t->wpool);
   if (t->rowscale) cudaFree(t->rowscale);
   if (t->ev_fork) cudaEventDestroy(t->ev_fork);
@@ -911,9 +1440,18 @@ static int ensure_encode(TcState* t) {
   return 0;
 }
 
+// layers conv_halo_kernel is instantiated for: 3x3 / stride 1 / pad 1, Cin = Cout = the N tile, 64x64x64 (layer1) or 32x32x128 (layer2)
+static bool halo_geom(const TcGeom& c, int* rh) {
+  if (c.conv1 || c.ksize != 3 || c.stride != 1 || c.pad != 1 || c.cin != c.cout || c.hin != c.win || c.hout != c.hin) return false;
+  if (c.cout == 64 && c.hin == 64) { *rh = 5; return true; }
+  if (c.cout == 128 && c.hin == 32) { *rh = 7; return true; }
+  return false;
+}
+
 // tensor maps of one convolution: A over the split activation planes, W over [Cout][K_eff]
 static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __half* a_lo, void* w_hi, void* w_lo, TcLayerMaps& out) {
   const int bn = tile_bn(c.cout);
+  out.halo = 0;
   {
     cuuint64_t dims[2] = {(cuuint64_t)c.k_eff, (cuuint64_t)c.cout};
     cuuint64_t str[1] = {(cuuint64_t)c.k_eff * 2};
@@ -956,6 +1494,14 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     box[0] = 32;
     if (encode(t, &out.a32_hi, a_hi, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (encode(t, &out.a32_lo, a_lo, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    int rh = 0;
+    if (halo_geom(c, &rh)) {
+      cuuint32_t hbox[4] = {64, (cuuint32_t)(c.win + 2), (cuuint32_t)rh, 1};
+      cuuint32_t hes[4] = {1, 1, 1, 1};
+      if (encode(t, &out.h_hi, a_hi, 4, dims, str, hbox, hes)) return 1;
+      if (encode(t, &out.h_lo, a_lo, 4, dims, str, hbox, hes)) return 1;
+      out.halo = 1;
+    }
   }
   return 0;
 }
@@ -1037,6 +1583,32 @@ static int launch_conv_tc2(const TcLayerMaps& m, const TcConvParams& p, int num_
   return 0;
 }
 
+// halo variant (conv_halo_kernel): one work item = one 128-position tile of one image's padded raster
+template <int BN, int RH, int WP, int EPW = 4>
+static int launch_conv_halo(const TcLayerMaps& m, const TcConvParams& p, const TcGeom& c, int B, int num_sms, cudaStream_t st) {
+  using Cfg = HaloCfg<BN, RH, WP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    STRAPS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, RH, WP, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  HaloParams h;
+  memset(&h, 0, sizeof(h));
+  h.H = c.hin; h.W = c.win;
+  h.tiles_per_image = (c.hin * WP + c.win) / BM_TC + 1;      // the last tile that still holds interior position (H, W)
+  h.n_items = B * h.tiles_per_image;
+  h.cchunks = c.cin / 64;
+  h.cout = c.cout;
+  h.shift = p.shift; h.unscale = p.unscale;
+  h.out_hi = p.out_hi; h.out_lo = p.out_lo;
+  h.res_hi = p.res_hi; h.res_lo = p.res_lo;
+  h.relu = p.relu;
+  const int grid = h.n_items < num_sms ? h.n_items : num_sms;
+  conv_halo_kernel<BN, RH, WP, EPW><<<grid, 64 + 32 * EPW, Cfg::SMEM_BYTES, st>>>(m.h_hi, m.h_lo, m.w_hi, m.w_lo, h);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
 // p carries the pointers (shift, unscale, outputs, residuals, relu); the geometry fields are filled here
 static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParams p, int B, cudaStream_t st) {
   const int bn = tile_bn(c.cout);
@@ -1061,6 +1633,19 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
   p.cout = c.cout;
   { const char* d = getenv("STRAPS_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
   {
+    // STRAPS_TC_HALO: "1" = layer1 and layer2 stride-1 3x3 convolutions through conv_halo_kernel, "64" / "128" = only the layers of
+    // that width; "8" appended ("1,8") = two epilogue warps per quadrant.  Read per launch so that one process can compare both paths.
+    // Verified on B200 (profiles/r01_halo_check.json) but slower than conv_tc_kernel: off by default.
+    const char* e = getenv("STRAPS_TC_HALO");
+    const int sel = e ? atoi(e) : 0;
+    if (sel && m.halo && p.out_hi && !p.out_f32 && !p.res_f32 && bn == c.cout && (sel == 1 || sel == c.cout)) {
+      const bool e8 = strstr(e, ",8") != nullptr;
+      if (c.cout == 64)
+        return e8 ? launch_conv_halo<64, 5, 66, 8>(m, p, c, B, t->num_sms, st) : launch_conv_halo<64, 5, 66>(m, p, c, B, t->num_sms, st);
+      return e8 ? launch_conv_halo<128, 7, 34, 8>(m, p, c, B, t->num_sms, st) : launch_conv_halo<128, 7, 34>(m, p, c, B, t->num_sms, st);
+    }
+  }
+  {
     // STRAPS_TC_PAIR: "128" = CTA pairs for the Cout >= 128 layers, "all" = every layer, unset/"0" = single-CTA kernels
     const char* e = getenv("STRAPS_TC_PAIR");
     const bool pair = e && ((e[0] == 'a') || (e[0] == '1' && c.cout >= 128));
@@ -1076,10 +1661,10 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
     return mc == 2 ? launch_conv_tc_cl<128, 2>(m, p, t->num_sms, st) : launch_conv_tc_cl<128, 4>(m, p, t->num_sms, st);
   }
   {
-    // STRAPS_TC_EPI_WARPS = 8: two epilogue warps per TMEM lane quadrant.  WRITTEN AFTER THE ROUND'S GPU BUDGET WAS SPENT: compiled and
-    // reviewed, not yet run on hardware (first item for round 2); the default stays 4.
-    static const int epw = [] { const char* e = getenv("STRAPS_TC_EPI_WARPS"); return e ? atoi(e) : 4; }();
-    if (epw == 8 && mt == 1 && bn <= 128)
+    // STRAPS_TC_EPI_WARPS = 8: two epilogue warps per TMEM lane quadrant.  Bit-identical on B200 but 4 % slower (encoder 1.651 vs
+    // 1.584 ms, profiles/r01_halo_check.json): the epilogue is not short of warps to hide latency; the default stays 4.
+    const char* e = getenv("STRAPS_TC_EPI_WARPS");      // read per launch: one process can compare both settings
+    if (e && atoi(e) == 8 && mt == 1 && bn <= 128)
       return bn == 64 ? launch_conv_tc<64, 1, 64, 8>(m, p, t->num_sms, st) : launch_conv_tc<128, 1, 64, 8>(m, p, t->num_sms, st);
   }
   if (bn == 64) return mt == 2 ? launch_conv_tc<64, 2>(m, p, t->num_sms, st) : launch_conv_tc<64, 1>(m, p, t->num_sms, st);
@@ -1109,6 +1694,76 @@ static int run_conv_tc(straps_regressor* r, const std::vector<TcLayerMaps>& maps
   return run_tc(t, geom_fwd(c, ci), maps[ci], p, B, st);
 }
 
+// conv1 through the pixel-pair layout (conv1_s2d_kernel): buffer + tensor maps on first use, then pack + convolution
+static int s2d_prepare(straps_regressor* r, int B, const TcState::S2dMaps** out, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  if (ensure_encode(t)) return 1;
+  const ConvSpec& c = r->conv[0];
+  STRAPS_CHECK(c.cout == 64 && c.k_eff == 7 * C1_KROW && r->c_in <= XP_C, "conv1_s2d_kernel: unexpected conv1 geometry");
+  STRAPS_CHECK(static_cast<__half*>(c.w_lo) == static_cast<__half*>(c.w_hi) + (size_t)c.cout * c.k_eff,
+               "conv1_s2d_kernel: W_hi and W_lo of conv1 must be adjacent");
+  if (!t->xs) {
+    const char* e = getenv("STRAPS_TC_S2D_PITCH");
+    t->xs_pitch = (e && atoi(e) == 48) ? 48 : 64;
+    t->xs_plane = (size_t)r->max_batch * XS_H * XS_PAIRS * t->xs_pitch;
+    STRAPS_CUDA(cudaMalloc(&t->xs, 2 * t->xs_plane * sizeof(__half)));
+    STRAPS_CUDA(cudaMemsetAsync(t->xs, 0, 2 * t->xs_plane * sizeof(__half), st));      // the 6 border rows stay zero for good
+  }
+  auto it = t->s2d_maps.find(B);
+  if (it == t->s2d_maps.end()) {
+    TcState::S2dMaps m;
+    const cuuint64_t pitch = (cuuint64_t)t->xs_pitch;
+    cuuint64_t dims[4] = {pitch, (cuuint64_t)XS_PAIRS, (cuuint64_t)XS_H, (cuuint64_t)B};
+    cuuint64_t str[3] = {pitch * 2, (cuuint64_t)XS_PAIRS * pitch * 2, (cuuint64_t)XS_H * XS_PAIRS * pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)pitch, (cuuint32_t)S2D_LINES, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (encode(t, &m.a_hi, t->xs, 4, dims, str, box, es)) return 1;
+    if (encode(t, &m.a_lo, t->xs + t->xs_plane, 4, dims, str, box, es)) return 1;
+    cuuint64_t wdims[2] = {(cuuint64_t)c.k_eff, (cuuint64_t)2 * c.cout};          // rows 0..63 = W_hi, 64..127 = W_lo
+    cuuint64_t wstr[1] = {(cuuint64_t)c.k_eff * 2};
+    cuuint32_t wbox[2] = {64, 128};
+    if (encode(t, &m.w, c.w_hi, 2, wdims, wstr, wbox, es)) return 1;
+    it = t->s2d_maps.emplace(B, m).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+template <int MT>
+static int launch_conv1_s2d(straps_regressor* r, const TcState::S2dMaps& m, int B, cudaStream_t st) {
+  using Cfg = S2dCfg<MT>;
+  TcState* t = static_cast<TcState*>(r->tc);
+  static bool attr_set = false;
+  if (!attr_set) {
+    STRAPS_CUDA(cudaFuncSetAttribute(conv1_s2d_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const ConvSpec& c = r->conv[0];
+  S2dParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_rows = B * 128;
+  p.n_items = (p.n_rows + MT - 1) / MT;
+  p.a_bytes = (uint32_t)(S2D_LINES * t->xs_pitch * 2);
+  p.shift = c.shift;
+  p.unscale = t->unscale + t->ch_off[0];
+  p.out = act_ptr(r, c.out_buf);
+  p.relu = c.relu;
+  const int grid = p.n_items < t->num_sms ? p.n_items : t->num_sms;
+  conv1_s2d_kernel<MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w, p);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+static int run_conv1_s2d(straps_regressor* r, const float* x, int B, int mt, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  const TcState::S2dMaps* m = nullptr;
+  if (s2d_prepare(r, B, &m, st)) return 1;
+  if (t->xs_pitch == 64) pack_input_s2d_kernel<64><<<dim3(IMG, B), 256, 0, st>>>(x, r->c_in, t->xs, t->xs + t->xs_plane);
+  else pack_input_s2d_kernel<48><<<dim3(IMG, B), 256, 0, st>>>(x, r->c_in, t->xs, t->xs + t->xs_plane);
+  STRAPS_LAUNCH_CHECK();
+  return mt == 2 ? launch_conv1_s2d<2>(r, *m, B, st) : launch_conv1_s2d<1>(r, *m, B, st);
+}
+
 int tc_encoder_forward(straps_regressor* r, const float* x, int B, float* feat, cudaStream_t st) {
   TcState* t = static_cast<TcState*>(r->tc);
   STRAPS_CHECK(t, "tc_encoder_forward: tensor-core state missing");
@@ -1119,9 +1774,16 @@ int tc_encoder_forward(straps_regressor* r, const float* x, int B, float* feat, 
     it = t->maps.emplace(B, std::move(v)).first;
   }
   const std::vector<TcLayerMaps>& maps = it->second;
-  pack_input_tc_kernel<<<dim3(IMG, B), 256, 0, st>>>(x, r->c_in, t->xp, t->xp + t->xp_plane);
-  STRAPS_LAUNCH_CHECK();
-  if (run_conv_tc(r, maps, 0, B, st)) return 1;
+  // STRAPS_TC_CONV1 = "s2d" / "s2d2": conv1 from the pixel-pair layout (one / two output rows per work item); read per call.
+  // NOT YET RUN ON HARDWARE (see conv1_s2d_kernel); unset = the shipped path.
+  const char* c1 = getenv("STRAPS_TC_CONV1");
+  if (c1 && strncmp(c1, "s2d", 3) == 0) {
+    if (run_conv1_s2d(r, x, B, c1[3] == '2' ? 2 : 1, st)) return 1;
+  } else {
+    pack_input_tc_kernel<<<dim3(IMG, B), 256, 0, st>>>(x, r->c_in, t->xp, t->xp + t->xp_plane);
+    STRAPS_LAUNCH_CHECK();
+    if (run_conv_tc(r, maps, 0, B, st)) return 1;
+  }
   {
     const size_t n = (size_t)B * 64 * 64 * 16;
     maxpool_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(act_ptr(r, r->buf_stem), B, 128, 128, 64,

@@ -1,0 +1,100 @@
+"""CPU emulation of conv1_s2d_kernel's index arithmetic (csrc/conv_tc.cu): the 7x7 / stride 2 / pad 3 stem convolution computed from
+the pixel-PAIR layout of the padded input, with tap pairs as line-shifted windows of one TMA box per filter row.
+
+Replayed exactly as the device code does it:
+  pack_input_s2d_kernel   xs[b][h + 3][(w + 3) >> 1][((w + 3) & 1) * 24 + c] = x[b][c][h][w]      (262 rows x 132 pairs x PITCH)
+  pack_w_tc_kernel        wrow[co][kh * 192 + kw * 24 + c] = w[co][c][kh][kw]   (kw = 7 and c >= C are zero)    -- conv1 branch
+  producer                box {PITCH, 131 pairs} of padded row 2 oh + kh  ->  131 shared-memory lines of 64 elements
+  MMA issuer              K step j = 0..10 of filter row kh: A = lines [j // 3, j // 3 + 128), elements [(j % 3) * 16, +16);
+                          W = wrow[:, kh * 192 + 16 j : +16]   (weight chunk j // 4, byte offset (j % 4) * 32)
+and compared with torch's conv2d.  Also checks the shared-memory rotation of the PITCH = 64 pack kernel (write index -> read index).
+
+    python tools/conv1_s2d_emulation.py      -> prints the max error; exits non-zero on a mismatch
+"""
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+XS_H, XS_PAIRS, LINES, XP_C, KROW = 262, 132, 131, 24, 192
+
+
+def pack_input(x, pitch):
+    B, C, H, W = x.shape
+    assert H == 256 and W == 256 and C <= XP_C
+    xs = np.zeros((B, XS_H, XS_PAIRS, pitch))
+    for w in range(W):
+        pw = w + 3
+        xs[:, 3:3 + H, pw >> 1, (pw & 1) * XP_C:(pw & 1) * XP_C + C] = np.transpose(x[:, :, :, w], (0, 2, 1))
+    return xs
+
+
+def pack_weights(w):
+    co, C = w.shape[:2]
+    rows = np.zeros((co, 7 * KROW))
+    for kh in range(7):
+        for kw in range(7):
+            rows[:, kh * KROW + kw * XP_C:kh * KROW + kw * XP_C + C] = w[:, :, kh, kw]
+    return rows
+
+
+def conv1_s2d(x, w, pitch=64):
+    B = x.shape[0]
+    xs, wr = pack_input(x, pitch), pack_weights(w)
+    out = np.zeros((B, 128, 128, w.shape[0]))
+    for b in range(B):
+        for oh in range(128):
+            acc = np.zeros((128, w.shape[0]))
+            for kh in range(7):
+                box = np.zeros((LINES, 64))
+                box[:, :pitch] = xs[b, 2 * oh + kh, :LINES, :]            # TMA box {pitch, 131}: the rest of each 128-byte line is never read
+                for j in range(11):
+                    tap, sub = j // 3, j % 3
+                    a = box[tap:tap + 128, sub * 16:sub * 16 + 16]
+                    assert sub * 16 + 16 <= 48 <= pitch
+                    acc += a @ wr[:, kh * KROW + 16 * j:kh * KROW + 16 * j + 16].T
+            out[b, oh] = acc
+    return np.transpose(out, (0, 3, 1, 2))
+
+
+def check_pack_rotation():
+    """pack_input_s2d_kernel<64>: word `l` of pair `q` is written at q*32 + (((l>>2)+q)&7)*4 + (l&3); 16-byte unit i of the row is read
+    from (i & ~7) + (((i & 7) + (i >> 3)) & 7).  The composition must be the identity on the row."""
+    words = XS_PAIRS * 32
+    smem = np.full(words, -1, dtype=np.int64)
+    for q in range(XS_PAIRS):
+        for l in range(32):
+            smem[q * 32 + ((((l >> 2) + q) & 7) << 2) + (l & 3)] = q * 32 + l
+    assert (smem >= 0).all()
+    out = np.empty(words, dtype=np.int64)
+    for i in range(words // 4):
+        si = (i & ~7) + (((i & 7) + (i >> 3)) & 7)
+        out[4 * i:4 * i + 4] = smem[4 * si:4 * si + 4]
+    return bool((out == np.arange(words)).all())
+
+
+def main():
+    rng = np.random.RandomState(0)
+    worst = 0.0
+    for C, pitch in ((17, 64), (18, 64), (17, 48)):
+        x = rng.normal(0, 1, (1, C, 256, 256))
+        w = rng.normal(0, 1, (4, C, 7, 7))
+        got = conv1_s2d(x, w, pitch)
+        ref = F.conv2d(torch.from_numpy(x), torch.from_numpy(w), stride=2, padding=3).numpy()
+        err = float(np.abs(got - ref).max())
+        worst = max(worst, err)
+        print('C=%d pitch=%d: max abs error %.2e (output %s)' % (C, pitch, err, got.shape))
+    rot = check_pack_rotation()
+    print('shared-memory rotation of the PITCH = 64 pack kernel is its own inverse:', rot)
+    a_now, w_now, a_new, w_new = 21 * 2 * 128 * 128, 21 * 2 * 64 * 128, 7 * 2 * LINES * 128, 21 * 128 * 128
+    print('bytes per output row: A %d -> %d KB, W %d -> %d KB (%d with two rows per item); TMA operations 84 -> 35'
+          % (a_now // 1024, a_new // 1024, w_now // 1024, w_new // 1024, w_new // 2048))
+    if worst > 1e-9 or not rot:
+        print('MISMATCH')
+        sys.exit(1)
+    print('pair-layout conv1 == conv2d (max abs error %.2e)' % worst)
+
+
+if __name__ == '__main__':
+    main()
