@@ -39,10 +39,16 @@ constexpr int C1_KROW = 192;                       // K elements per filter row 
 constexpr int TC_THREADS = 192;
 // STRAPS_TC_EXPERIMENTS builds keep the in-situ timing switches of profiles/r01_conv_experiments.txt (p.debug); normal builds have
 // no trace of them in the hot loops
+// STRAPS_TC_DEBUG is a bit mask: 1 = no TMA traffic (the producer only arrives on the full barriers, MMAs run on stale operands),
+// 2 = no MMAs (the issuer only commits), 4 = no epilogue global I/O.  3 / 5 / 6 leave ONE of the three parts running alone.
 #ifdef STRAPS_TC_EXPERIMENTS
-#define TC_EPI_IO(p) ((p).debug != 3)
+#define TC_EPI_IO(p) (((p).debug & 4) == 0)
+#define TC_NO_TMA(p) (((p).debug & 1) != 0)
+#define TC_NO_MMA(p) (((p).debug & 2) != 0)
 #else
 #define TC_EPI_IO(p) true
+#define TC_NO_TMA(p) false
+#define TC_NO_MMA(p) false
 #endif
 constexpr int BM_TC = 128;
 constexpr int BK_TC = 64;
@@ -68,7 +74,7 @@ struct TcConvParams {
   const __half* res_lo;
   const float* res_f32;     // fp32 NHWC tensor added to the result (data-gradient accumulation) or null
   int relu;
-  int debug;        // timing experiments only (STRAPS_TC_DEBUG): 1 = no TMA traffic, 2 = no MMAs, 3 = no epilogue stores
+  int debug;        // timing experiments only (STRAPS_TC_DEBUG bit mask): 1 = no TMA traffic, 2 = no MMAs, 4 = no epilogue global I/O
 };
 
 // BN = output-channel tile, MT = number of 128-pixel M-tiles that share one weight tile per K-block.
@@ -182,7 +188,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint32_t fb = full0 + st * 8;
           mbar_wait_u32(empty0 + st * 8, ph);
 #ifdef STRAPS_TC_EXPERIMENTS
-          if (p.debug == 1) { mbar_arrive(&full[st]); if (++st == Cfg::STAGES) { st = 0; ph ^= 1; } continue; }
+          if (TC_NO_TMA(p)) { mbar_arrive(&full[st]); if (++st == Cfg::STAGES) { st = 0; ph ^= 1; } continue; }
 #endif
           mbar_expect_tx_u32(fb, Cfg::STAGE_BYTES);
 #pragma unroll
@@ -245,7 +251,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           int ksteps = BK / 16;
           if (conv1) { if (++sub == Cfg::C1_CHUNKS) { sub = 0; ksteps = Cfg::C1_LAST_KSTEPS; } }
 #ifdef STRAPS_TC_EXPERIMENTS
-          if (p.debug == 2) ksteps = 0;                                   // timing experiment: TMA only
+          if (TC_NO_MMA(p)) ksteps = 0;                                   // timing experiment: no MMAs
 #endif
 #pragma unroll
           for (int t = 0; t < MT; ++t) {
@@ -423,6 +429,7 @@ struct HaloParams {
   const __half* res_hi;   // residual (identity) planes or null
   const __half* res_lo;
   int relu;
+  int debug;              // STRAPS_TC_DEBUG bit mask (experiment builds only)
 };
 
 template <int BN, int RH, int WP>
@@ -492,18 +499,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         for (int cc = 0; cc < cchunks; ++cc) {
           const uint32_t sa = smem0 + as * Cfg::A_STAGE, fb = a_full0 + as * 8;
           mbar_wait_u32(a_empty0 + as * 8, aph);
-          mbar_expect_tx_u32(fb, 2 * Cfg::A_BOX_BYTES);
-          // image coordinates of the box origin: pixel -1 (left border), row r0 - 1 (raster row r = image row r - 1)
-          tma_load_4d_u32(sa, &map_a_hi, fb, cc * 64, -1, r0 - 1, b);
-          tma_load_4d_u32(sa + Cfg::A_PLANE, &map_a_lo, fb, cc * 64, -1, r0 - 1, b);
+          if (TC_NO_TMA(p)) {
+            mbar_arrive(&a_full[as]);
+          } else {
+            mbar_expect_tx_u32(fb, 2 * Cfg::A_BOX_BYTES);
+            // image coordinates of the box origin: pixel -1 (left border), row r0 - 1 (raster row r = image row r - 1)
+            tma_load_4d_u32(sa, &map_a_hi, fb, cc * 64, -1, r0 - 1, b);
+            tma_load_4d_u32(sa + Cfg::A_PLANE, &map_a_lo, fb, cc * 64, -1, r0 - 1, b);
+          }
           if (++as == Cfg::AS) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t sw = smem0 + Cfg::W_OFF + ws * Cfg::W_STAGE, wb = w_full0 + ws * 8;
             mbar_wait_u32(w_empty0 + ws * 8, wph);
-            mbar_expect_tx_u32(wb, Cfg::W_STAGE);
-            const int wk = (tap * cchunks + cc) * BK_TC;  // K offset of (tap, chunk) in the [Cout][(kh, kw, ci)] weight rows
-            tma_load_2d_u32(sw, &map_w_hi, wb, wk, 0);
-            tma_load_2d_u32(sw + Cfg::W_BYTES, &map_w_lo, wb, wk, 0);
+            if (TC_NO_TMA(p)) {
+              mbar_arrive(&w_full[ws]);
+            } else {
+              mbar_expect_tx_u32(wb, Cfg::W_STAGE);
+              const int wk = (tap * cchunks + cc) * BK_TC;  // K offset of (tap, chunk) in the [Cout][(kh, kw, ci)] weight rows
+              tma_load_2d_u32(sw, &map_w_hi, wb, wk, 0);
+              tma_load_2d_u32(sw + Cfg::W_BYTES, &map_w_lo, wb, wk, 0);
+            }
             if (++ws == Cfg::WS) { ws = 0; wph ^= 1; }
           }
         }
@@ -538,11 +553,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               const uint32_t a_hi = a0 + (uint32_t)start * 8u;          // 128 bytes per line = 8 descriptor units
               const uint32_t a_lo = a_hi + (Cfg::A_PLANE >> 4);
               const uint32_t w_hi = umma_desc_sw128_lo(smem0 + Cfg::W_OFF + ws * Cfg::W_STAGE);
+              if (!TC_NO_MMA(p)) {
 #pragma unroll
-              for (int k = 0; k < BK_TC / 16; ++k) {
-                umma_f16_lohi(d_hi, a_hi + 2 * k, w_hi + 2 * k, idesc_wide, accum);      // A_hi.[W_hi ; W_lo] -> [acc_hi | acc_lo]
-                umma_f16_lohi(d_lo, a_lo + 2 * k, w_hi + 2 * k, idesc, 1);               // A_lo.W_hi
-                accum = 1;
+                for (int k = 0; k < BK_TC / 16; ++k) {
+                  umma_f16_lohi(d_hi, a_hi + 2 * k, w_hi + 2 * k, idesc_wide, accum);      // A_hi.[W_hi ; W_lo] -> [acc_hi | acc_lo]
+                  umma_f16_lohi(d_lo, a_lo + 2 * k, w_hi + 2 * k, idesc, 1);               // A_lo.W_hi
+                  accum = 1;
+                }
               }
               umma_commit_u32(w_empty0 + ws * 8);
               if (++ws == Cfg::WS) { ws = 0; wph ^= 1; }
@@ -572,7 +589,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const uint32_t acs = ti & 1;
       uint4 rh[4], rl[4];
       auto fetch_residual = [&](int chunk) {
-        if (p.res_hi && chunk < NCHUNK && valid) {
+        if (p.res_hi && chunk < NCHUNK && valid && TC_EPI_IO(p)) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + obase + chunk * 32) + q);
@@ -602,7 +619,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
           y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
         }
-        if (valid && p.res_hi) {
+        if (valid && p.res_hi && TC_EPI_IO(p)) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t hw[4] = {rh[q].x, rh[q].y, rh[q].z, rh[q].w}, lw[4] = {rl[q].x, rl[q].y, rl[q].z, rl[q].w};
@@ -614,7 +631,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           }
         }
         fetch_residual(chunk + CSTEP);
-        if (valid) {
+        if (valid && TC_EPI_IO(p)) {
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
@@ -681,6 +698,7 @@ struct S2dParams {
   const float* unscale;
   float* out;             // NHWC fp32 [B,128,128,64]
   int relu;
+  int debug;              // STRAPS_TC_DEBUG bit mask (experiment builds only)
 };
 
 template <int MT>
@@ -746,18 +764,25 @@ conv1_s2d_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           for (int t = 0; t < MT; ++t) {
             const uint32_t sa = smem0 + as * Cfg::A_SLOT, fb = a_full0 + as * 8;
             mbar_wait_u32(a_empty0 + as * 8, aph);
-            mbar_expect_tx_u32(fb, 2 * p.a_bytes);
-            // rows past the end of the batch (last item of an odd row count) land out of bounds -> zeros, never stored
-            tma_load_4d_u32(sa, &map_a_hi, fb, 0, 0, 2 * (oh0 + t) + kh, b);
-            tma_load_4d_u32(sa + Cfg::A_PLANE, &map_a_lo, fb, 0, 0, 2 * (oh0 + t) + kh, b);
+            if (TC_NO_TMA(p)) {
+              mbar_arrive(&a_full[as]);
+            } else {
+              mbar_expect_tx_u32(fb, 2 * p.a_bytes);
+              tma_load_4d_u32(sa, &map_a_hi, fb, 0, 0, 2 * (oh0 + t) + kh, b);
+              tma_load_4d_u32(sa + Cfg::A_PLANE, &map_a_lo, fb, 0, 0, 2 * (oh0 + t) + kh, b);
+            }
             if (++as == Cfg::NA) { as = 0; aph ^= 1; }
           }
 #pragma unroll 1
           for (int c = 0; c < 3; ++c) {
             const uint32_t wb = w_full0 + ws * 8;
             mbar_wait_u32(w_empty0 + ws * 8, wph);
-            mbar_expect_tx_u32(wb, Cfg::W_SLOT);
-            tma_load_2d_u32(smem0 + Cfg::W_OFF + ws * Cfg::W_SLOT, &map_w, wb, kh * C1_KROW + c * 64, 0);
+            if (TC_NO_TMA(p)) {
+              mbar_arrive(&w_full[ws]);
+            } else {
+              mbar_expect_tx_u32(wb, Cfg::W_SLOT);
+              tma_load_2d_u32(smem0 + Cfg::W_OFF + ws * Cfg::W_SLOT, &map_w, wb, kh * C1_KROW + c * 64, 0);
+            }
             if (++ws == Cfg::NW) { ws = 0; wph ^= 1; }
           }
         }
@@ -795,8 +820,10 @@ conv1_s2d_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             for (int t = 0; t < MT; ++t) {
               const uint32_t a_hi = adesc0 + (as + t) * (Cfg::A_SLOT >> 4) + a_off, a_lo = a_hi + (Cfg::A_PLANE >> 4);
               const uint32_t d_hi = acc + t * Cfg::TILE_COLS, d_lo = d_hi + 64;
-              umma_f16_lohi(d_hi, a_hi, w_k, idesc_wide, accum);           // A_hi.[W_hi ; W_lo] -> [acc_hi | acc_lo]
-              umma_f16_lohi(d_lo, a_lo, w_k, idesc, 1);                    // A_lo.W_hi
+              if (!TC_NO_MMA(p)) {
+                umma_f16_lohi(d_hi, a_hi, w_k, idesc_wide, accum);         // A_hi.[W_hi ; W_lo] -> [acc_hi | acc_lo]
+                umma_f16_lohi(d_lo, a_lo, w_k, idesc, 1);                  // A_lo.W_hi
+              }
             }
             accum = 1;
             if ((j & 3) == 3 || j == 10) {
@@ -843,7 +870,7 @@ conv1_s2d_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
           y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
         }
-        if (valid) {
+        if (valid && TC_EPI_IO(p)) {
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
@@ -1603,6 +1630,7 @@ static int launch_conv_halo(const TcLayerMaps& m, const TcConvParams& p, const T
   h.out_hi = p.out_hi; h.out_lo = p.out_lo;
   h.res_hi = p.res_hi; h.res_lo = p.res_lo;
   h.relu = p.relu;
+  h.debug = p.debug;
   const int grid = h.n_items < num_sms ? h.n_items : num_sms;
   conv_halo_kernel<BN, RH, WP, EPW><<<grid, 64 + 32 * EPW, Cfg::SMEM_BYTES, st>>>(m.h_hi, m.h_lo, m.w_hi, m.w_lo, h);
   STRAPS_LAUNCH_CHECK();
@@ -1748,6 +1776,7 @@ static int launch_conv1_s2d(straps_regressor* r, const TcState::S2dMaps& m, int 
   p.unscale = t->unscale + t->ch_off[0];
   p.out = act_ptr(r, c.out_buf);
   p.relu = c.relu;
+  { const char* d = getenv("STRAPS_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
   const int grid = p.n_items < t->num_sms ? p.n_items : t->num_sms;
   conv1_s2d_kernel<MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w, p);
   STRAPS_LAUNCH_CHECK();

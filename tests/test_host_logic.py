@@ -79,3 +79,13 @@ def test_round2_halo_scheme_matches_conv2d():
     from conftest import REPO
     res = subprocess.run([sys.executable, os.path.join(REPO, 'tools', 'halo_emulation.py')], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and 'halo scheme == conv2d' in res.stdout, res.stdout[-1000:] + res.stderr[-1000:]
+
+
+def test_conv1_pair_layout_scheme_matches_conv2d():
+    """tools/conv1_s2d_emulation.py: conv1_s2d_kernel's pixel-pair layout, box / window / K-step arithmetic and the pack kernel's
+    shared-memory rotation, replayed in numpy, equal the 7x7 / stride 2 / pad 3 conv2d."""
+    import subprocess
+    import sys
+    from conftest import REPO
+    res = subprocess.run([sys.executable, os.path.join(REPO, 'tools', 'conv1_s2d_emulation.py')], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and 'pair-layout conv1 == conv2d' in res.stdout, res.stdout[-1000:] + res.stderr[-1000:]
