@@ -50,6 +50,18 @@ inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_o
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: a process that drives several GPUs (or moves a module to another device)
+// must configure a kernel once per device, not once per process.  One bit per device ordinal (CUDA allows at most 64 per process here).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool need(int dev) const { return dev < 0 || dev >= 64 || !((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
+  void done(int dev) { if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
+static inline int current_device() {
+  int d = 0;
+  return cudaGetDevice(&d) == cudaSuccess ? d : -1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // device-side PTX wrappers: mbarrier, bulk (TMA) copies, tcgen05
 // ------------------------------------------------------------------------------------------------

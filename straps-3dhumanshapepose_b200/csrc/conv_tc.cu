@@ -1549,10 +1549,11 @@ static int build_maps(straps_regressor* r, int B, std::vector<TcLayerMaps>& out)
 template <int BN, int MT, int BK = 64, int EPW = 4>
 static int launch_conv_tc(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
   using Cfg = TcCfg<BN, MT, BK>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
     STRAPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MT, 1, BK, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   const int items = ((p.n_mtiles + MT - 1) / MT) * p.n_ntiles;
   const int grid = items < num_sms ? items : num_sms;
@@ -1568,10 +1569,11 @@ template <int BN, int CL, int BK = 64>
 static int launch_conv_tc_cl(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
   using Cfg = TcCfg<BN, 1, BK>;
   static_assert(BK == 64 || CL == 2, "BK = 32 has half-tile weight maps only");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
     STRAPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, CL, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   const int items = ((p.n_mtiles + CL - 1) / CL) * p.n_ntiles;
   const int clusters = items < num_sms / CL ? items : num_sms / CL;
@@ -1598,10 +1600,11 @@ static int launch_conv_tc_cl(const TcLayerMaps& m, const TcConvParams& p, int nu
 template <int BN>
 static int launch_conv_tc2(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
   using Cfg = TcCfg2<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
     STRAPS_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   const int items = ((p.n_mtiles + 1) / 2) * p.n_ntiles;
   const int clusters = items < num_sms / 2 ? items : num_sms / 2;
@@ -1614,10 +1617,11 @@ static int launch_conv_tc2(const TcLayerMaps& m, const TcConvParams& p, int num_
 template <int BN, int RH, int WP, int EPW = 4>
 static int launch_conv_halo(const TcLayerMaps& m, const TcConvParams& p, const TcGeom& c, int B, int num_sms, cudaStream_t st) {
   using Cfg = HaloCfg<BN, RH, WP>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
     STRAPS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, RH, WP, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   HaloParams h;
   memset(&h, 0, sizeof(h));
@@ -1761,10 +1765,11 @@ template <int MT>
 static int launch_conv1_s2d(straps_regressor* r, const TcState::S2dMaps& m, int B, cudaStream_t st) {
   using Cfg = S2dCfg<MT>;
   TcState* t = static_cast<TcState*>(r->tc);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
     STRAPS_CUDA(cudaFuncSetAttribute(conv1_s2d_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   const ConvSpec& c = r->conv[0];
   S2dParams p;
@@ -2404,10 +2409,11 @@ int tc_train_conv_dgrad(straps_regressor* r, int ci, int B, const float* add, fl
 template <int BN>
 static int launch_wgrad_tc(const TcLayerMaps& m, const WgParams& p, int num_sms, cudaStream_t st) {
   using Cfg = WgCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
     STRAPS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   const int items = p.n_mtiles * p.n_ntiles * p.splits;
   wgrad_tc_kernel<BN><<<items < num_sms ? items : num_sms, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w_hi, m.w_lo, p);

@@ -282,11 +282,12 @@ int ief_pack(straps_regressor* r, const float* const* fc_w, const float* const* 
 int ief_launch_train(const straps_regressor* r, const float* feat, int batch, int iters, float* params, float* saved, cudaStream_t st) {
   const int nclusters = ceil_div(batch, TBI);
   const size_t smem = sizeof(IefSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
     STRAPS_CUDA(cudaFuncSetAttribute(ief_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     STRAPS_CUDA(cudaFuncSetAttribute(ief_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
