@@ -1143,6 +1143,257 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair kernel, second version (STRAPS_TC_PAIR=m | m128): merged wide MMA + lean issue loops.
+// WRITTEN AFTER THE ROUND'S GPU BUDGET WAS SPENT: compiled and reviewed against conv_tc2_kernel (which is verified on hardware), NOT
+// yet run; the default path never reaches it.
+//
+// Why conv_tc2_kernel lost 3-8 %: the shared-memory port model that predicts conv_tc_kernel's K-block time to within 5 % --
+// cycles = (bytes the MMAs read from shared memory + bytes TMA writes into it) / 128 B/clk -- says per K-block and SM
+//   conv_tc_kernel  (64,1):  wide A_hi 16 + [W_hi;W_lo] 16, narrow A_lo 16 + W_hi 8  = 56 KB read + 48 KB written = 104 KB
+//   conv_tc2_kernel BN = 64: three N = 64 MMAs, each 16 KB of A + 4 KB of half-W     = 60 KB read + 40 KB written = 100 KB
+// i.e. splitting the wide MMA back into two made the pair READ more than it saved in writes.  Here the pair issues the same two
+// MMAs as conv_tc_kernel, with M = 256:
+//   wide   A_hi . [W_hi ; W_lo]   N = 2 BN: CTA 0 holds the W_hi rows, CTA 1 the W_lo rows        (per SM: 16 + BN/8 KB read)
+//   narrow A_lo . W_hi            N = BN:   each CTA holds its half of the W_hi rows (own slot)   (per SM: 16 + BN/16 KB read)
+//   BN = 64: 44 KB read + 44 KB written = 88 KB (-15 %);  BN = 128: 56 + 56 = 112 KB against 144 KB (-22 %)
+// and a stage shrinks to 44 / 56 KB, so the ring holds 5 / 4 stages instead of 4 / 3.  The producer and issuer loops are the lean ones
+// of conv_tc_kernel (elect.sync, incremental K-block coordinates, 32-bit descriptor words); the epilogue software-pipelines the
+// residual loads like conv_tc_kernel's.  Barriers as in conv_tc2_kernel.
+// ---------------------------------------------------------------------------------------------------------
+template <int BN>
+struct TcCfg2m {
+  static constexpr int A_BYTES = BM_TC * 128;                        // one plane of this CTA's A tile
+  static constexpr int WB_BYTES = BN * 128;                          // wide-B slot: W_hi rows (rank 0) or W_lo rows (rank 1)
+  static constexpr int NB_BYTES = (BN / 2) * 128;                    // narrow-B slot: this CTA's half of the W_hi rows
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + WB_BYTES + NB_BYTES;
+  static constexpr int STAGES = (BN == 64) ? 5 : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int ACC_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(SMEM_BYTES <= 232448 && TMEM_COLS <= 512 && 2 * BN <= 256, "CTA-pair configuration does not fit");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc2m_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                 const __grid_constant__ CUtensorMap map_wh_hi, const TcConvParams p) {
+  using Cfg = TcCfg2m<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]  leader's: TMA of BOTH CTAs completes on it
+  uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]  one per CTA, released by the leader's multicast commit
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;    // [2]       one per CTA (multicast commit)
+  uint64_t* tempty = tfull + 2;                // [2]       leader's: 256 arrivals (epilogue threads of both CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int n_pairs = (p.n_mtiles + 1) / 2;
+  const int n_items = n_pairs * p.n_ntiles;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
+    tma_prefetch_desc(&map_wh_hi);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 256); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // ================= TMA producer (both CTAs): own A tile, own wide-B rows, own half of the narrow-B rows =================
+      const uint32_t full_leader0 = mapa_u32(full0, 0);      // the leader's full[0] as a shared::cluster address (+ 8 per stage)
+      const CUtensorMap* map_wide = rank ? &map_w_lo : &map_w_hi;
+      uint32_t st = 0, ph = 1;
+      const int nkb = p.n_kblocks, cchunks = p.cchunks, kwc = p.kw_count, pad = p.pad, stride = p.stride;
+      const bool conv1 = p.conv1 != 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int mg = item / p.n_ntiles, nt = item - mg * p.n_ntiles;
+        const long long pix0 = (long long)(mg * 2 + rank) * BM_TC;       // a tile past the end lands out of bounds -> zeros
+        const int b0 = (int)(pix0 / p.hw_out);
+        const int oh0 = (int)((pix0 % p.hw_out) / p.wout);
+        const int row0 = conv1 ? oh0 : oh0 * stride - pad;
+        const int wrow = nt * BN, nrow = wrow + rank * (BN / 2);
+        int c0 = 0, c1 = conv1 ? 0 : -pad, dh = 0, sub = 0, kwi = 0, wk = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t sa = smem0 + st * Cfg::STAGE_BYTES;
+          const uint32_t fb = full_leader0 + st * 8;
+          mbar_wait_u32(empty0 + st * 8, ph);
+          if (TC_NO_TMA(p)) {
+            if (rank == 0) mbar_arrive(&full[st]);
+          } else {
+            if (rank == 0) mbar_expect_tx_u32(full0 + st * 8, 2 * Cfg::STAGE_BYTES);       // bytes landing in BOTH CTAs
+            tma_load_4d_2cta_u32(sa, &map_a_hi, fb, c0, c1, row0 + dh, b0);
+            tma_load_4d_2cta_u32(sa + Cfg::A_BYTES, &map_a_lo, fb, c0, c1, row0 + dh, b0);
+            tma_load_2d_2cta_u32(sa + 2 * Cfg::A_BYTES, map_wide, fb, wk, wrow);
+            tma_load_2d_2cta_u32(sa + 2 * Cfg::A_BYTES + Cfg::WB_BYTES, &map_wh_hi, fb, wk, nrow);
+          }
+          wk += BK_TC;
+          if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
+          if (conv1) {
+            c0 += BK_TC;
+            if (++sub == C1_KROW / BK_TC) { sub = 0; c0 += XP_W * XP_C - C1_KROW; }
+          } else {
+            c0 += BK_TC;
+            if (++sub == cchunks) {
+              sub = 0; c0 = 0; ++c1;
+              if (++kwi == kwc) { kwi = 0; c1 = -pad; ++dh; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one_sync()) {
+      // ================= MMA issuer (leader CTA only): M = 256 over both CTAs' A tiles =================
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM_TC, BN);
+      constexpr uint32_t idesc_wide = umma_idesc_f16(2 * BM_TC, 2 * BN);
+      constexpr uint32_t STAGE16 = Cfg::STAGE_BYTES >> 4, A16 = Cfg::A_BYTES >> 4, WB16 = Cfg::WB_BYTES >> 4;
+      constexpr int C1_LAST = (7 * XP_C - (C1_KROW / BK_TC - 1) * BK_TC + 15) / 16;
+      const uint32_t desc0 = umma_desc_sw128_lo(smem0);
+      const uint32_t tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
+      uint32_t st = 0, ph = 0, as = 0, aph = 1;
+      const int nkb = p.n_kblocks;
+      const bool conv1 = p.conv1 != 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        mbar_wait_u32(tempty0 + as * 8, aph);
+        tc_fence_after();
+        const uint32_t d_hi = tmem_base + as * Cfg::ACC_COLS, d_lo = d_hi + BN;
+        int sub = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_u32(full0 + st * 8, ph);
+          tc_fence_after();
+          const uint32_t a_hi = desc0 + st * STAGE16, a_lo = a_hi + A16;
+          const uint32_t wb = a_hi + 2 * A16, nb = wb + WB16;
+          int ksteps = BK_TC / 16;
+          if (conv1) { if (++sub == C1_KROW / BK_TC) { sub = 0; ksteps = C1_LAST; } }
+          if (TC_NO_MMA(p)) ksteps = 0;
+#pragma unroll
+          for (int k = 0; k < BK_TC / 16; ++k) {
+            if (k < ksteps) {
+              const uint32_t ko = k * 2;
+              umma_f16_2cta_lohi(d_hi, a_hi + ko, wb + ko, idesc_wide, (kb | k) != 0);     // -> [acc_hi | acc_lo] in both CTAs
+              umma_f16_2cta_lohi(d_lo, a_lo + ko, nb + ko, idesc, 1);
+            }
+          }
+          umma_commit_2cta_u32(empty0 + st * 8);      // frees the stage in both CTAs
+          if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
+        }
+        umma_commit_2cta_u32(tfull0 + as * 8);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..5 (both CTAs, each its own 128 rows) =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    constexpr int NCHUNK = BN / 32;
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(tempty), 0);
+    uint32_t ti = 0;
+    for (int item = cluster_id; item < n_items; item += n_clusters, ++ti) {
+      const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
+      const uint32_t as = ti & 1;
+      const long long m = (long long)(mg * 2 + rank) * BM_TC + row;
+      const bool valid = m < p.m_total;
+      const size_t obase = (size_t)m * p.cout + (size_t)nt * BN;
+      uint4 rh[4], rl[4];
+      auto fetch_residual = [&](int chunk) {
+        if (p.res_hi && chunk < NCHUNK && valid && TC_EPI_IO(p)) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + obase + chunk * 32) + q);
+            rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + obase + chunk * 32) + q);
+          }
+        }
+      };
+      fetch_residual(0);
+      mbar_wait(&tfull[as], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+        const int c0 = chunk * 32;
+        uint32_t v[32], vl[32];
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + as * Cfg::ACC_COLS + c0;
+        tmem_ld_32x32(tacc, v);
+        tmem_ld_32x32(tacc + BN, vl);
+        tmem_ld_wait();
+        float y[32];
+        const float4* sh4 = reinterpret_cast<const float4*>(p.shift + nt * BN + c0);
+        const float4* us4 = reinterpret_cast<const float4*>(p.unscale + nt * BN + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
+          y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
+          y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
+          y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
+          y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+        }
+        if (valid && p.res_hi && TC_EPI_IO(p)) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t hw[4] = {rh[q].x, rh[q].y, rh[q].z, rh[q].w}, lw[4] = {rl[q].x, rl[q].y, rl[q].z, rl[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              y[q * 8 + e * 2 + 0] += f16lo_to_f(hw[e]) + f16lo_to_f(lw[e]);
+              y[q * 8 + e * 2 + 1] += f16hi_to_f(hw[e]) + f16hi_to_f(lw[e]);
+            }
+          }
+        }
+        fetch_residual(chunk + 1);
+        if (valid && TC_EPI_IO(p)) {
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
+          }
+          if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+          } else {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              __half h0, l0, h1, l1;
+              split_f16(y[2 * i], h0, l0);
+              split_f16(y[2 * i + 1], h1, l1);
+              ph[i] = pack_f16(h0, h1);
+              pl[i] = pack_f16(l0, l1);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
+            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
+              ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(tempty_leader0 + as * 8);     // the leader's accumulator-free barrier
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();          // nobody leaves (or frees TMEM) while the peer may still touch its shared memory / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
 // x NCHW fp32 [B,C,256,256] -> padded NHWC split planes [B,262,264,24] (interior only; the halo stays zero).
 // One CTA per (b, h) image row, one thread per pixel: the C channel rows are read with fully coalesced 1 KB
 // requests (all loads in flight before the first use), split to fp16 hi/lo and staged through shared memory so
@@ -1613,6 +1864,23 @@ static int launch_conv_tc2(const TcLayerMaps& m, const TcConvParams& p, int num_
   return 0;
 }
 
+template <int BN>
+static int launch_conv_tc2m(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg2m<BN>;
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
+    STRAPS_CUDA(cudaFuncSetAttribute(conv_tc2m_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_once.done(attr_dev);
+  }
+  const int items = ((p.n_mtiles + 1) / 2) * p.n_ntiles;
+  const int clusters = items < num_sms / 2 ? items : num_sms / 2;
+  // full-tile weight boxes {64, BN} for the wide operand (W_hi for rank 0, W_lo for rank 1), half-tile boxes of W_hi for the narrow one
+  conv_tc2m_kernel<BN><<<2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w_hi, m.w_lo, m.w2_hi, p);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
 // halo variant (conv_halo_kernel): one work item = one 128-position tile of one image's padded raster
 template <int BN, int RH, int WP, int EPW = 4>
 static int launch_conv_halo(const TcLayerMaps& m, const TcConvParams& p, const TcGeom& c, int B, int num_sms, cudaStream_t st) {
@@ -1678,8 +1946,11 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
     }
   }
   {
-    // STRAPS_TC_PAIR: "128" = CTA pairs for the Cout >= 128 layers, "all" = every layer, unset/"0" = single-CTA kernels
+    // STRAPS_TC_PAIR: "128" = CTA pairs for the Cout >= 128 layers, "all" = every layer, unset/"0" = single-CTA kernels;
+    // "m" / "m128" = the same selection with conv_tc2m_kernel (merged wide MMA, lean loops; not yet run on hardware)
     const char* e = getenv("STRAPS_TC_PAIR");
+    if (e && e[0] == 'm' && (e[1] == '\0' || c.cout >= 128) && mt == 1 && bn <= 128 && !p.res_f32 && !k32)
+      return bn == 64 ? launch_conv_tc2m<64>(m, p, t->num_sms, st) : launch_conv_tc2m<128>(m, p, t->num_sms, st);
     const bool pair = e && ((e[0] == 'a') || (e[0] == '1' && c.cout >= 128));
     if (pair && mt == 1 && bn <= 128 && !p.res_f32 && !k32)
       return bn == 64 ? launch_conv_tc2<64>(m, p, t->num_sms, st) : launch_conv_tc2<128>(m, p, t->num_sms, st);

@@ -21,7 +21,7 @@ _UNVERIFIED = pytest.mark.skipif(not os.environ.get('STRAPS_TEST_UNVERIFIED'), r
 def _check(names, tmp_path, extra_env=None):
     out = os.path.join(str(tmp_path), 'check.json')
     env = dict(os.environ)
-    for k in ('STRAPS_TC_HALO', 'STRAPS_TC_EPI_WARPS', 'STRAPS_TC_CONV1', 'STRAPS_TC_S2D_PITCH', 'STRAPS_TC_DEBUG'):
+    for k in ('STRAPS_TC_HALO', 'STRAPS_TC_EPI_WARPS', 'STRAPS_TC_CONV1', 'STRAPS_TC_S2D_PITCH', 'STRAPS_TC_DEBUG', 'STRAPS_TC_PAIR'):
         env.pop(k, None)
     env.update(extra_env or {})
     res = subprocess.run([sys.executable, os.path.join(REPO, 'tools', 'halo_check.py'), '--out', out, '--only', ','.join(names),
@@ -54,3 +54,12 @@ def test_conv1_pair_layout_kernel_matches_shipped_kernel(tmp_path, pitch):
     _assert_close(got, names)
     # same K order per output row as the shipped kernel (filter row major, then (kw, c)): the stem should be bit-identical
     assert got['conv1_s2d']['layers']['stem'] == 0.0, got['conv1_s2d']
+
+
+@_UNVERIFIED
+def test_merged_pair_kernel_matches_shipped_kernel(tmp_path):
+    """conv_tc2m_kernel issues the MMAs of conv_tc_kernel with M = 256 over a CTA pair: same K order, same accumulators."""
+    names = ['pair_m128', 'pair_m']
+    got = _check(names, tmp_path)
+    _assert_close(got, names)
+    assert got['pair_m']['bit_identical'], got['pair_m']

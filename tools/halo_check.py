@@ -1,5 +1,5 @@
 """One-process hardware check of the convolution variants behind switches (conv_halo_kernel, EPW = 8, conv1_s2d_kernel) against the
-shipped path.
+shipped path (also the second CTA-pair kernel, conv_tc2m_kernel).
 
     python tools/halo_check.py [--out gpurun_out/halo_check.json] [--batch 8] [--time-batch 64] [--iters 20] [--only name,name]
     STRAPS_TC_S2D_PITCH=48 python tools/halo_check.py --only conv1_s2d,conv1_s2d2     (dense pair lines: a separate process)
@@ -27,9 +27,11 @@ for p in (ORACLE, PKG):
 
 VARIANTS = (('halo64', {'STRAPS_TC_HALO': '64'}), ('halo128', {'STRAPS_TC_HALO': '128'}), ('halo', {'STRAPS_TC_HALO': '1'}),
             ('halo_epw8', {'STRAPS_TC_HALO': '1,8'}), ('epw8', {'STRAPS_TC_EPI_WARPS': '8'}),
-            ('conv1_s2d', {'STRAPS_TC_CONV1': 's2d'}), ('conv1_s2d2', {'STRAPS_TC_CONV1': 's2d2'}))
-LAYERS = ['stem'] + ['layer%d.%d%s' % (L, b, s) for L in (1, 2) for b in (0, 1) for s in ('.a', '')]
-SWITCHES = ('STRAPS_TC_HALO', 'STRAPS_TC_EPI_WARPS', 'STRAPS_TC_CONV1')
+            ('conv1_s2d', {'STRAPS_TC_CONV1': 's2d'}), ('conv1_s2d2', {'STRAPS_TC_CONV1': 's2d2'}),
+            ('pair', {'STRAPS_TC_PAIR': 'all'}), ('pair_m128', {'STRAPS_TC_PAIR': 'm128'}), ('pair_m', {'STRAPS_TC_PAIR': 'm'}),
+            ('pair_m+s2d2', {'STRAPS_TC_PAIR': 'm', 'STRAPS_TC_CONV1': 's2d2'}))
+LAYERS = ['stem'] + ['layer%d.%d%s' % (L, b, s) for L in (1, 2, 3, 4) for b in (0, 1) for s in ('.a', '')]
+SWITCHES = ('STRAPS_TC_HALO', 'STRAPS_TC_EPI_WARPS', 'STRAPS_TC_CONV1', 'STRAPS_TC_PAIR')
 
 
 def set_env(env):
