@@ -697,6 +697,8 @@ struct S2dParams {
   const float* shift;
   const float* unscale;
   float* out;             // NHWC fp32 [B,128,128,64]
+  __half* pool_hi;        // POOL variant: 3x3 / stride 2 max-pooled output, split planes [B,64,64,64] (the stem tensor is never written)
+  __half* pool_lo;
   int relu;
   int debug;              // STRAPS_TC_DEBUG bit mask (experiment builds only)
 };
@@ -710,7 +712,8 @@ struct S2dCfg {
   static constexpr int NW = (MT == 1) ? 6 : 5;
   static constexpr int W_OFF = NA * A_SLOT;
   static constexpr int BAR_OFF = W_OFF + NW * W_SLOT;
-  static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256;
+  static constexpr int EDGE_BYTES = 2 * 4 * 2 * 32 * 4;             // POOL: [channel chunk][quadrant][array][32] floats of the warps' last pixels
+  static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + EDGE_BYTES;
   static constexpr int TILE_COLS = 128;                             // [acc_hi (64) | acc_lo (64)]
   static constexpr int ACC_COLS = MT * TILE_COLS;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
@@ -720,11 +723,31 @@ struct S2dCfg {
   static_assert(SMEM_BYTES <= 232448 && TMEM_COLS <= 512 && 2 * (NA + NW) * 8 + 40 <= 256, "conv1 pair-layout configuration does not fit");
 };
 
-template <int MT>
+// POOL (STRAPS_TC_CONV1=s2dp, MT = 2): the 3x3 / stride 2 / pad 1 max pool is fused into the epilogue and the 268 MB stem tensor is never
+// written or re-read.  A work item is then one POOLED row pr of one image = conv rows 2 pr and 2 pr + 1; pooled row pr also needs conv
+// row 2 pr - 1, the odd row of the item above, so every CTA walks a CONTIGUOUS range of items and carries the horizontally pooled odd
+// row in registers from one item to the next (max commutes: pool(max(a, b, c)) = max(pool(a), pool(b), pool(c))).  The first item of
+// a range that does not start an image is preceded by the item above it, computed only for its carry (1 extra item in ~28).
+// Horizontal pooling: a thread owns one conv pixel (TMEM lane); even lanes combine lanes - 1 / + 1 with warp shuffles, and the one
+// neighbour that lives in another warp (pixel 32 q - 1) travels through 256 bytes of shared memory per warp and channel chunk.
+template <int MT, bool POOL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv1_s2d_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_w, const S2dParams p) {
   using Cfg = S2dCfg<MT>;
+  static_assert(!POOL || MT == 2, "the fused pool works on pairs of conv rows");
+  // items of this CTA: strided over the grid, or (POOL) one contiguous range, preceded by the item above when the range starts inside an image
+  int it0, it1, itstep, it_real;
+  if constexpr (POOL) {
+    const int per = (p.n_items + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int first = (int)blockIdx.x * per;
+    it1 = min(first + per, p.n_items);
+    it0 = first - (((first & 63) != 0 && first < it1) ? 1 : 0);
+    it_real = first;
+    itstep = 1;
+  } else {
+    it0 = (int)blockIdx.x; it1 = p.n_items; itstep = (int)gridDim.x; it_real = 0;
+  }
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
@@ -756,7 +779,7 @@ conv1_s2d_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if (elect_one_sync()) {
       // ================= TMA producer: per filter row the input row of every tile of the item, then the 3 weight chunks =================
       uint32_t as = 0, aph = 1, ws = 0, wph = 1;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = it0; item < it1; item += itstep) {
         const int r_first = item * MT;                    // output row index over (b, oh); 128 rows per image, MT divides 128
         const int b = r_first >> 7, oh0 = r_first & 127;
         for (int kh = 0; kh < 7; ++kh) {
@@ -796,7 +819,7 @@ conv1_s2d_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const uint32_t tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
       const uint32_t adesc0 = umma_desc_sw128_lo(smem0), wdesc0 = umma_desc_sw128_lo(smem0 + Cfg::W_OFF);
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, acs = 0, acph = 1;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = it0; item < it1; item += itstep) {
         mbar_wait_u32(tempty0 + acs * 8, acph);
         tc_fence_after();
         const uint32_t acc = tmem_base + acs * Cfg::ACC_COLS;
@@ -845,7 +868,108 @@ conv1_s2d_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     uint32_t ti = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++ti) {
+    if constexpr (POOL) {
+      float* edge = reinterpret_cast<float*>(smem + Cfg::BAR_OFF + 256);
+      const float ninf = __int_as_float(0xff800000);
+      const int pc = quad * 16 + (lane >> 1);                 // pooled column of an even lane
+      float carry[2][32];                                     // even lanes: the pooled odd conv row above, per channel chunk
+#pragma unroll
+      for (int i = 0; i < 32; ++i) carry[0][i] = carry[1][i] = ninf;
+      for (int item = it0; item < it1; ++item, ++ti) {
+        const uint32_t acs = ti & 1;
+        const bool top = (item & 63) == 0;                    // pooled row 0: no conv row above
+        const bool store = item >= it_real && TC_EPI_IO(p);
+        mbar_wait(&tfull[acs], (ti >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int c0 = c * 32;
+          float y0[32], y1[32];
+          {
+            const float4* sh4 = reinterpret_cast<const float4*>(p.shift + c0);
+            const float4* us4 = reinterpret_cast<const float4*>(p.unscale + c0);
+            const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + acs * Cfg::ACC_COLS + c0;
+            uint32_t v[32], vl[32];
+            tmem_ld_32x32(tacc, v);
+            tmem_ld_32x32(tacc + 64, vl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
+              y0[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
+              y0[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
+              y0[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
+              y0[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+            }
+            tmem_ld_32x32(tacc + Cfg::TILE_COLS, v);
+            tmem_ld_32x32(tacc + Cfg::TILE_COLS + 64, vl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
+              y1[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
+              y1[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
+              y1[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
+              y1[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+            }
+          }
+          if (c == 1) {                                       // every TMEM read of the item is done: the issuer may reuse the stage
+            tc_fence_before();
+            mbar_arrive(&tempty[acs]);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { y0[i] = fmaxf(y0[i], 0.f); y1[i] = fmaxf(y1[i], 0.f); }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y0[i] = fmaxf(y0[i], y1[i]);          // y0 = vertical max of the item's two conv rows
+          // the warp's last pixel is the left neighbour of the next warp's first pooled column
+          float* e = edge + ((c * 4 + quad) * 2) * 32;
+          if (lane == 31) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              reinterpret_cast<float4*>(e)[q] = make_float4(y0[q * 4], y0[q * 4 + 1], y0[q * 4 + 2], y0[q * 4 + 3]);
+              reinterpret_cast<float4*>(e + 32)[q] = make_float4(y1[q * 4], y1[q * 4 + 1], y1[q * 4 + 2], y1[q * 4 + 3]);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+          const float* ep = e - 64;                           // quadrant quad - 1 (read by lane 0 of quadrants 1..3 only)
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float um = __shfl_up_sync(0xffffffffu, y0[i], 1), u1 = __shfl_up_sync(0xffffffffu, y1[i], 1);
+            const float dm = __shfl_down_sync(0xffffffffu, y0[i], 1), d1 = __shfl_down_sync(0xffffffffu, y1[i], 1);
+            if (lane == 0) {
+              um = quad ? ep[i] : ninf;                       // pixel -1 is padding
+              u1 = quad ? ep[32 + i] : ninf;
+            }
+            const float hm = fmaxf(fmaxf(um, y0[i]), dm), h1 = fmaxf(fmaxf(u1, y1[i]), d1);
+            o[i] = top ? hm : fmaxf(hm, carry[c][i]);
+            carry[c][i] = h1;
+          }
+          if (store && !(lane & 1)) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              __half h0, l0, h1, l1;
+              split_f16(o[2 * i], h0, l0);
+              split_f16(o[2 * i + 1], h1, l1);
+              ph[i] = pack_f16(h0, h1);
+              pl[i] = pack_f16(l0, l1);
+            }
+            const size_t ob = ((size_t)item * 64 + pc) * 64 + c0;            // item = b * 64 + pooled row
+            uint4* oh = reinterpret_cast<uint4*>(p.pool_hi + ob);
+            uint4* ol = reinterpret_cast<uint4*>(p.pool_lo + ob);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
+              ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
+            }
+          }
+        }
+      }
+    } else
+    for (int item = it0; item < it1; item += itstep, ++ti) {
       const uint32_t acs = ti & 1;
       mbar_wait(&tfull[acs], (ti >> 1) & 1);
       tc_fence_after();
@@ -2032,14 +2156,14 @@ static int s2d_prepare(straps_regressor* r, int B, const TcState::S2dMaps** out,
   return 0;
 }
 
-template <int MT>
+template <int MT, bool POOL = false>
 static int launch_conv1_s2d(straps_regressor* r, const TcState::S2dMaps& m, int B, cudaStream_t st) {
   using Cfg = S2dCfg<MT>;
   TcState* t = static_cast<TcState*>(r->tc);
   static PerDeviceOnce attr_once;
   const int attr_dev = current_device();
   if (attr_once.need(attr_dev)) {
-    STRAPS_CUDA(cudaFuncSetAttribute(conv1_s2d_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    STRAPS_CUDA(cudaFuncSetAttribute(conv1_s2d_kernel<MT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_once.done(attr_dev);
   }
   const ConvSpec& c = r->conv[0];
@@ -2051,10 +2175,12 @@ static int launch_conv1_s2d(straps_regressor* r, const TcState::S2dMaps& m, int 
   p.shift = c.shift;
   p.unscale = t->unscale + t->ch_off[0];
   p.out = act_ptr(r, c.out_buf);
+  p.pool_hi = plane_hi(r, r->buf_pool);
+  p.pool_lo = plane_lo(r, r->buf_pool);
   p.relu = c.relu;
   { const char* d = getenv("STRAPS_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
   const int grid = p.n_items < t->num_sms ? p.n_items : t->num_sms;
-  conv1_s2d_kernel<MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w, p);
+  conv1_s2d_kernel<MT, POOL><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w, p);
   STRAPS_LAUNCH_CHECK();
   return 0;
 }
@@ -2066,6 +2192,7 @@ static int run_conv1_s2d(straps_regressor* r, const float* x, int B, int mt, cud
   if (t->xs_pitch == 64) pack_input_s2d_kernel<64><<<dim3(IMG, B), 256, 0, st>>>(x, r->c_in, t->xs, t->xs + t->xs_plane);
   else pack_input_s2d_kernel<48><<<dim3(IMG, B), 256, 0, st>>>(x, r->c_in, t->xs, t->xs + t->xs_plane);
   STRAPS_LAUNCH_CHECK();
+  if (mt == 3) return launch_conv1_s2d<2, true>(r, *m, B, st);          // two conv rows per item + fused max pool
   return mt == 2 ? launch_conv1_s2d<2>(r, *m, B, st) : launch_conv1_s2d<1>(r, *m, B, st);
 }
 
@@ -2079,17 +2206,20 @@ int tc_encoder_forward(straps_regressor* r, const float* x, int B, float* feat, 
     it = t->maps.emplace(B, std::move(v)).first;
   }
   const std::vector<TcLayerMaps>& maps = it->second;
-  // STRAPS_TC_CONV1 = "s2d" / "s2d2": conv1 from the pixel-pair layout (one / two output rows per work item); read per call.
+  // STRAPS_TC_CONV1 = "s2d" / "s2d2" / "s2dp": conv1 from the pixel-pair layout (one / two output rows per work item / two rows and the
+  // max pool fused into the epilogue); read per call.
   // NOT YET RUN ON HARDWARE (see conv1_s2d_kernel); unset = the shipped path.
   const char* c1 = getenv("STRAPS_TC_CONV1");
-  if (c1 && strncmp(c1, "s2d", 3) == 0) {
-    if (run_conv1_s2d(r, x, B, c1[3] == '2' ? 2 : 1, st)) return 1;
+  const bool s2d = c1 && strncmp(c1, "s2d", 3) == 0;
+  const bool fused_pool = s2d && c1[3] == 'p';                  // "s2dp": the max pool runs in conv1's epilogue
+  if (s2d) {
+    if (run_conv1_s2d(r, x, B, fused_pool ? 3 : c1[3] == '2' ? 2 : 1, st)) return 1;
   } else {
     pack_input_tc_kernel<<<dim3(IMG, B), 256, 0, st>>>(x, r->c_in, t->xp, t->xp + t->xp_plane);
     STRAPS_LAUNCH_CHECK();
     if (run_conv_tc(r, maps, 0, B, st)) return 1;
   }
-  {
+  if (!fused_pool) {
     const size_t n = (size_t)B * 64 * 64 * 16;
     maxpool_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(act_ptr(r, r->buf_stem), B, 128, 128, 64,
                                                                     plane_hi(r, r->buf_pool), plane_lo(r, r->buf_pool));

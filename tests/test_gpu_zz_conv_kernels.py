@@ -49,11 +49,12 @@ def test_halo_kernel_matches_shipped_kernel(tmp_path):
 @_UNVERIFIED
 @pytest.mark.parametrize('pitch', ['64', '48'])
 def test_conv1_pair_layout_kernel_matches_shipped_kernel(tmp_path, pitch):
-    names = ['conv1_s2d', 'conv1_s2d2']
+    names = ['conv1_s2d', 'conv1_s2d2', 'conv1_s2dp']
     got = _check(names, tmp_path, {'STRAPS_TC_S2D_PITCH': pitch})
     _assert_close(got, names)
     # same K order per output row as the shipped kernel (filter row major, then (kw, c)): the stem should be bit-identical
     assert got['conv1_s2d']['layers']['stem'] == 0.0, got['conv1_s2d']
+    assert got['conv1_s2dp']['layers']['pool'] == 0.0, got['conv1_s2dp']       # max is exact: the fused pool must be bit-identical
 
 
 @_UNVERIFIED

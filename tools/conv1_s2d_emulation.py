@@ -74,6 +74,40 @@ def check_pack_rotation():
     return bool((out == np.arange(words)).all())
 
 
+def check_fused_pool(grid=148, B=3):
+    """The POOL epilogue (STRAPS_TC_CONV1=s2dp) replayed per CTA: contiguous item ranges with the item above recomputed for its carry,
+    even lanes combining lanes -1 / +1 (pixel -1 = padding), carry = horizontally pooled odd conv row -> must equal max_pool2d(3, 2, 1)."""
+    rng = np.random.RandomState(1)
+    y = np.maximum(rng.normal(0, 1, (B, 128, 128, 4)), 0)                      # relu(bn(conv1)) rows, NHWC
+    n_items = B * 64
+    per = -(-n_items // grid)
+    out = np.full((B, 64, 64, 4), np.nan)
+    stored = 0
+    for cta in range(grid):
+        first = cta * per
+        it1 = min(first + per, n_items)
+        it0 = first - (1 if (first & 63) != 0 and first < it1 else 0)
+        carry = np.full((64, 4), -np.inf)
+        for item in range(it0, it1):
+            b, pr = item >> 6, item & 63
+            y0, y1 = y[b, 2 * pr], y[b, 2 * pr + 1]
+            m = np.maximum(y0, y1)
+
+            def hpool(v):                                                     # lanes 2j: max(v[2j-1], v[2j], v[2j+1])
+                up = np.vstack([np.full((1, v.shape[1]), -np.inf), v[:-1]])
+                dn = np.vstack([v[1:], np.full((1, v.shape[1]), -np.inf)])
+                return np.maximum(np.maximum(up, v), dn)[0::2]
+            hm, h1 = hpool(m), hpool(y1)
+            o = hm if pr == 0 else np.maximum(hm, carry)
+            carry = h1
+            if item >= first:
+                assert np.isnan(out[b, pr]).all()
+                out[b, pr] = o
+                stored += 1
+    ref = F.max_pool2d(torch.from_numpy(np.transpose(y, (0, 3, 1, 2))), 3, 2, 1).numpy()
+    return stored == n_items and bool(np.array_equal(np.transpose(out, (0, 3, 1, 2)), ref))
+
+
 def main():
     rng = np.random.RandomState(0)
     worst = 0.0
@@ -90,7 +124,9 @@ def main():
     a_now, w_now, a_new, w_new = 21 * 2 * 128 * 128, 21 * 2 * 64 * 128, 7 * 2 * LINES * 128, 21 * 128 * 128
     print('bytes per output row: A %d -> %d KB, W %d -> %d KB (%d with two rows per item); TMA operations 84 -> 35'
           % (a_now // 1024, a_new // 1024, w_now // 1024, w_new // 1024, w_new // 2048))
-    if worst > 1e-9 or not rot:
+    pool = check_fused_pool() and check_fused_pool(grid=148, B=64 // 8) and check_fused_pool(grid=5, B=1)
+    print('fused max-pool epilogue (contiguous item ranges + carried odd row) == max_pool2d(3, 2, 1):', pool)
+    if worst > 1e-9 or not rot or not pool:
         print('MISMATCH')
         sys.exit(1)
     print('pair-layout conv1 == conv2d (max abs error %.2e)' % worst)
