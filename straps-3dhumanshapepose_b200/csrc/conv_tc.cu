@@ -117,7 +117,11 @@ struct TcCfg {
 // only after EVERY CTA of the cluster has consumed it (empty barriers count CL arrivals: each issuer's commit is multicast).
 // EPW = epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, alternating 32-column chunks).  On the short-K layers
 // the epilogue of a tile is as long as its main loop (layer1: MMAs alone 53 us of 68) and a single warp per scheduler hides no latency.
-template <int BN, int MT, int CL = 1, int BK = 64, int EPW = 4>
+// PDL = launched with programmatic stream serialization (STRAPS_TC_PDL=1): the CTA lets the next kernel of the stream start as soon as
+// this grid's CTAs have begun (griddepcontrol.launch_dependents), and does its own set-up (barriers, TMEM allocation, descriptor
+// prefetch) BEFORE it waits for the previous kernel's results (griddepcontrol.wait) -- launch latency and prologue move under the
+// previous kernel's tail.  Not yet run on hardware; the default instantiations carry neither instruction.
+template <int BN, int MT, int CL = 1, int BK = 64, int EPW = 4, bool PDL = false>
 __global__ void __launch_bounds__(64 + 32 * EPW, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -156,6 +160,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if constexpr (CL > 1) cluster_sync_all();      // every CTA's barriers exist before any multicast load / remote commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if constexpr (PDL) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // every thread: activations, residuals and outputs are touched only after this
+  }
 
   // The two issue roles are ONE thread each, so their cost is instruction LATENCY, not throughput: the first version of these
   // loops (div/mod per K-block, 64-bit descriptor arithmetic, `lane == 0` divergence that made the compiler wrap every
@@ -1921,6 +1929,33 @@ static int build_maps(straps_regressor* r, int B, std::vector<TcLayerMaps>& out)
   return 0;
 }
 
+// the shipped tile shapes launched with programmatic stream serialization (see conv_tc_kernel: PDL)
+template <int BN>
+static int launch_conv_tc_pdl(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg<BN, 1, 64>;
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
+    STRAPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 1, 64, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_once.done(attr_dev);
+  }
+  const int items = p.n_mtiles * p.n_ntiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(items < num_sms ? items : num_sms, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  STRAPS_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 1, 1, 64, 4, true>, m.a_hi, m.a_lo, m.w_hi, m.w_lo, p));
+  straps::count_launch();
+  return 0;
+}
+
 template <int BN, int MT, int BK = 64, int EPW = 4>
 static int launch_conv_tc(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
   using Cfg = TcCfg<BN, MT, BK>;
@@ -2093,6 +2128,12 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
     const char* e = getenv("STRAPS_TC_EPI_WARPS");      // read per launch: one process can compare both settings
     if (e && atoi(e) == 8 && mt == 1 && bn <= 128)
       return bn == 64 ? launch_conv_tc<64, 1, 64, 8>(m, p, t->num_sms, st) : launch_conv_tc<128, 1, 64, 8>(m, p, t->num_sms, st);
+  }
+  {
+    // STRAPS_TC_PDL=1: programmatic dependent launch of the shipped tile shapes (read per launch; not yet run on hardware)
+    const char* e = getenv("STRAPS_TC_PDL");
+    if (e && atoi(e) == 1 && mt == 1 && bn <= 128)
+      return bn == 64 ? launch_conv_tc_pdl<64>(m, p, t->num_sms, st) : launch_conv_tc_pdl<128>(m, p, t->num_sms, st);
   }
   if (bn == 64) return mt == 2 ? launch_conv_tc<64, 2>(m, p, t->num_sms, st) : launch_conv_tc<64, 1>(m, p, t->num_sms, st);
   if (bn == 256) return launch_conv_tc<256, 1>(m, p, t->num_sms, st);

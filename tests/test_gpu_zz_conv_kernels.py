@@ -21,7 +21,7 @@ _UNVERIFIED = pytest.mark.skipif(not os.environ.get('STRAPS_TEST_UNVERIFIED'), r
 def _check(names, tmp_path, extra_env=None):
     out = os.path.join(str(tmp_path), 'check.json')
     env = dict(os.environ)
-    for k in ('STRAPS_TC_HALO', 'STRAPS_TC_EPI_WARPS', 'STRAPS_TC_CONV1', 'STRAPS_TC_S2D_PITCH', 'STRAPS_TC_DEBUG', 'STRAPS_TC_PAIR'):
+    for k in ('STRAPS_TC_HALO', 'STRAPS_TC_EPI_WARPS', 'STRAPS_TC_CONV1', 'STRAPS_TC_S2D_PITCH', 'STRAPS_TC_DEBUG', 'STRAPS_TC_PAIR', 'STRAPS_TC_PDL'):
         env.pop(k, None)
     env.update(extra_env or {})
     res = subprocess.run([sys.executable, os.path.join(REPO, 'tools', 'halo_check.py'), '--out', out, '--only', ','.join(names),
@@ -64,3 +64,12 @@ def test_merged_pair_kernel_matches_shipped_kernel(tmp_path):
     got = _check(names, tmp_path)
     _assert_close(got, names)
     assert got['pair_m']['bit_identical'], got['pair_m']
+
+
+@_UNVERIFIED
+def test_programmatic_dependent_launch_matches_shipped_kernel(tmp_path):
+    """STRAPS_TC_PDL=1: the same kernel code launched with programmatic stream serialization -- identical bits, or the
+    griddepcontrol.wait is in the wrong place."""
+    got = _check(['pdl'], tmp_path)
+    _assert_close(got, ['pdl'])
+    assert got['pdl']['bit_identical'], got['pdl']
