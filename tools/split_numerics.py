@@ -1,0 +1,161 @@
+"""Numerical study (CPU, float64 accumulation): which operand splits keep the encoder inside the 1e-4 bar?
+
+The shipped tensor-core mode carries every operand as a 2-term fp16 split and issues A_hi.W_hi + A_hi.W_lo + A_lo.W_hi.
+Under the shared-memory port model of DESIGN.md 4.2 the third term costs 25-30 % of the bytes through the port and 43 % of the tensor
+pipe, so this script prices cheaper forms of it BEFORE any kernel is written.  Every variant runs the whole ResNet-18 encoder of the
+reference (models/resnet.py:201-216, via the oracle's weights and synthetic proxy inputs) with eval-mode BatchNorm folded into the
+weights exactly as csrc/conv_tc.cu does (per-output-channel power-of-two row scale into [2^13, 2^14)), products accumulated in float64
+(so only the OPERAND representation differs; the tensor core's accumulator truncation, ~1e-5 at the features, comes on top), and the
+activations re-split after every layer like the kernel's epilogue.  Error = max-abs / max-abs of the fp64 result of the fp32 network.
+
+  f16x3        A_hi.W_hi + A_hi.W_lo + A_lo.W_hi                         (shipped)
+  f16x2_w      A_hi.W_hi + A_hi.W_lo                                     (activations rounded to fp16: drops the narrow MMA)
+  f16x2_a      A_hi.W_hi + A_lo.W_hi                                     (weights rounded to fp16)
+  f16x1        A_hi.W_hi                                                 (one pass; ~ the TF32 figure of SURVEY 0.9)
+  lo_e4m3      A_hi.W_hi + A_hi.W_lo + e4m3(A_lo).e4m3(W_hi)             (third term as an fp8 MMA: half the bytes, twice the rate;
+                                                                          A_lo with one power-of-two scale per tensor, W_hi per row)
+  lo_e5m2      the same with e5m2(A_lo) (fp16's exponent range: no per-tensor scale needed)
+  both_lo_f8   A_hi.W_hi + [A_hi8 | A_lo8].[W_lo8 ; W_hi8]               (both small terms as ONE fp8 MMA over a doubled K)
+
+    python tools/split_numerics.py [--batch 2] [--channels 17]
+"""
+import argparse
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(REPO, 'oracle'), os.path.join(REPO, 'straps-3dhumanshapepose_b200')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np                      # noqa: E402
+import torch                            # noqa: E402
+import torch.nn.functional as F         # noqa: E402
+
+BLOCKS = [('layer1.0', 1, False), ('layer1.1', 1, False), ('layer2.0', 2, True), ('layer2.1', 1, False),
+          ('layer3.0', 2, True), ('layer3.1', 1, False), ('layer4.0', 2, True), ('layer4.1', 1, False)]
+
+
+def f16(t):
+    return t.clamp(-65504, 65504).to(torch.float16).to(torch.float64)
+
+
+def split16(t):
+    hi = f16(t)
+    return hi, f16(t - hi)
+
+
+def pow2_scale_to(t, target_max, dim=None):
+    """power of two s with max|t| * s in [target_max / 2, target_max)"""
+    m = t.abs().amax(dim=dim, keepdim=True) if dim is not None else t.abs().max()
+    m = torch.where(m > 0, m, torch.ones_like(m))
+    return torch.exp2(torch.floor(torch.log2(target_max / m)))
+
+
+def f8(t, kind):
+    dt = torch.float8_e4m3fn if kind == 'e4m3' else torch.float8_e5m2
+    lim = 448.0 if kind == 'e4m3' else 57344.0
+    return t.clamp(-lim, lim).to(torch.float32).to(dt).to(torch.float64)
+
+
+def conv(variant, a, w, stride, pad):
+    """a: fp64 activations (exactly hi + lo of the previous epilogue), w: fp64 folded + row-scaled weights."""
+    c = lambda x, y: F.conv2d(x, y, None, stride, pad)
+    if variant == 'exact':
+        return c(a, w)
+    a_hi, a_lo = split16(a)
+    w_hi, w_lo = split16(w)
+    if variant == 'f16x3':
+        return c(a_hi, w_hi) + c(a_hi, w_lo) + c(a_lo, w_hi)
+    if variant == 'f16x2_w':
+        return c(a_hi, w_hi) + c(a_hi, w_lo)
+    if variant == 'f16x2_a':
+        return c(a_hi, w_hi) + c(a_lo, w_hi)
+    if variant == 'f16x1':
+        return c(a_hi, w_hi)
+    if variant in ('lo_e4m3', 'lo_e5m2', 'both_lo_f8'):
+        sw = pow2_scale_to(w_hi, 256.0, dim=(1, 2, 3))                     # per output channel, e4m3 max 448
+        w8 = f8(w_hi * sw, 'e4m3') / sw
+        if variant == 'lo_e5m2':
+            a8 = f8(a_lo, 'e5m2')
+        else:
+            sa = pow2_scale_to(a_lo, 256.0)
+            a8 = f8(a_lo * sa, 'e4m3') / sa
+        if variant == 'both_lo_f8':
+            sh = pow2_scale_to(a_hi, 256.0)
+            ah8 = f8(a_hi * sh, 'e4m3') / sh
+            sl = pow2_scale_to(w_lo, 256.0, dim=(1, 2, 3))
+            wl8 = f8(w_lo * sl, 'e4m3') / sl
+            return c(a_hi, w_hi) + c(ah8, wl8) + c(a8, w8)
+        return c(a_hi, w_hi) + c(a_hi, w_lo) + c(a8, w8)
+    raise ValueError(variant)
+
+
+def encoder(x, sd, variant, taps):
+    pre = 'image_encoder.'
+
+    def folded(conv_name, bn_name):
+        w = sd[pre + conv_name + '.weight'].double()
+        g, b = sd[pre + bn_name + '.weight'].double(), sd[pre + bn_name + '.bias'].double()
+        rm, rv = sd[pre + bn_name + '.running_mean'].double(), sd[pre + bn_name + '.running_var'].double()
+        if variant == 'exact':
+            scale = g / torch.sqrt(rv + 1e-5)
+            return w * scale.view(-1, 1, 1, 1), torch.ones_like(scale), b - rm * scale
+        # the device path computes scale / shift in fp32 (fold_bn_kernel) and folds scale * 2^e into the weights before the split
+        scale = (g.float() / torch.sqrt(rv.float() + 1e-5)).double()
+        shift = (b.float() - rm.float() * scale.float()).double()
+        ws = (w.float() * scale.float().view(-1, 1, 1, 1)).double()
+        p2 = pow2_scale_to(ws, 16384.0, dim=(1, 2, 3))
+        return (ws.float() * p2.float()).double(), (1.0 / p2).view(-1), shift
+
+    def layer(a, conv_name, bn_name, stride, pad, relu, res=None):
+        w, unscale, shift = folded(conv_name, bn_name)
+        y = conv(variant, a, w, stride, pad) * unscale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+        if res is not None:
+            y = y + res
+        if relu:
+            y = F.relu(y)
+        if variant != 'exact':
+            y = y.float().double()                       # the epilogue works in fp32
+            hi, lo = split16(y)
+            y = hi + lo                                  # what the next layer can see
+        return y
+
+    y = layer(x.double(), 'conv1', 'bn1', 2, 3, True)
+    taps['stem'] = y
+    y = F.max_pool2d(y, 3, 2, 1)
+    for name, stride, ds in BLOCKS:
+        idt = y
+        o = layer(y, name + '.conv1', name + '.bn1', stride, 1, True)
+        if ds:
+            idt = layer(y, name + '.downsample.0', name + '.downsample.1', stride, 0, False)
+        y = layer(o, name + '.conv2', name + '.bn2', 1, 1, True, res=idt)
+        taps[name] = y
+    return torch.flatten(F.adaptive_avg_pool2d(y, (1, 1)), 1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=2)
+    ap.add_argument('--channels', type=int, default=17)
+    args = ap.parse_args()
+    import straps_oracle as O
+    from straps_b200 import synthetic_inputs
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.make_regressor_state(args.channels, seed=1)
+    x = torch.from_numpy(synthetic_inputs.make_proxy_batch(args.batch, args.channels, seed=3))
+    ref_taps = {}
+    ref = encoder(x, sd, 'exact', ref_taps)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    print('%-12s %10s %10s %10s %10s %10s   (max-abs error / max-abs reference; bar 1e-4; fp64 accumulation)'
+          % ('variant', 'stem', 'layer1.1', 'layer2.1', 'layer4.1', 'features'))
+    for variant in ('f16x3', 'lo_e4m3', 'lo_e5m2', 'both_lo_f8', 'f16x2_w', 'f16x2_a', 'f16x1'):
+        taps = {}
+        feat = encoder(x, sd, variant, taps)
+        print('%-12s %10.2e %10.2e %10.2e %10.2e %10.2e' % (variant, rel(taps['stem'], ref_taps['stem']),
+              rel(taps['layer1.1'], ref_taps['layer1.1']), rel(taps['layer2.1'], ref_taps['layer2.1']),
+              rel(taps['layer4.1'], ref_taps['layer4.1']), rel(feat, ref)))
+
+
+if __name__ == '__main__':
+    main()
