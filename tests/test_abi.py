@@ -33,3 +33,25 @@ def test_version_and_error_string():
     h = ctypes.c_void_p()
     assert L.straps_regressor_create(ctypes.byref(h), 99, 4) != 0
     assert b'c_in' in L.straps_last_error()
+
+
+def test_shipped_kernels_carry_tcgen05_and_tma_sass():
+    """The built library's shipped convolution kernels really are tcgen05 / TMEM / TMA code (B200_PROFILING.md mnemonics):
+    UTCHMMA = tcgen05.mma, UTMALDG = TMA tile load, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit; the LBS and IEF kernels stage their
+    constants with bulk-async copies (UBLKCP) on mbarriers (SYNCS).  Checked on the .so the tests load (cuobjdump, no GPU needed)."""
+    import shutil
+    import sys
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not on PATH')
+    sys.path.insert(0, os.path.join(REPO, 'tools'))
+    import sass_summary
+    from straps_b200 import _lib
+    counts = sass_summary.summary(_lib.LIB_PATH)
+    names = sass_summary.demangle(list(counts))
+    by_name = {names[k].replace('(int)', '').replace('(bool)', '').split('(')[0].replace('void ', ''): v for k, v in counts.items()}
+    for shipped in ('straps::conv_tc_kernel<64, 1, 1, 64, 4, 0>', 'straps::conv_tc_kernel<128, 1, 1, 64, 4, 0>'):
+        c = by_name[shipped]
+        assert c['UTCHMMA'] >= 8 and c['UTMALDG'] >= 4 and c['LDTM'] >= 2 and c['UTCBAR'] >= 2 and c['SYNCS'] >= 4, (shipped, dict(c))
+        assert c['ACQBULK'] == 0, shipped                      # the programmatic-dependent-launch wait is only in the PDL instantiations
+    assert any(k.startswith('straps::lbs_kernel<') and v['UBLKCP'] > 0 for k, v in by_name.items())
+    assert by_name['straps::ief_kernel']['UBLKCP'] > 0
