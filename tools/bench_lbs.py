@@ -59,12 +59,46 @@ def main():
             warm_ms = e0.elapsed_time(e1) / args.iters
         cold_ms = float(np.median(cold))
         bytes_ = CONST_BYTES + BODY_BYTES * B
+        # The two figures above contain the host side of SMPL.forward (Python + ctypes + two launches, ~35 us): below B ~ 64 the GPU
+        # waits for the host.  A CUDA graph of K forwards (with and without an L2 flush before each) minus a graph of the K flushes
+        # alone gives the device time of the two kernels by themselves.
+        graph = {}
+        try:
+            K = 20
+
+            def timed_graph(with_fwd, with_flush):
+                g = torch.cuda.CUDAGraph()
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s), torch.no_grad():
+                    with torch.cuda.graph(g, stream=s):
+                        for _ in range(K):
+                            if with_flush:
+                                flush.zero_()
+                            if with_fwd:
+                                smpl(body_pose=bp, global_orient=go, betas=betas, pose2rot=False)
+                torch.cuda.current_stream().wait_stream(s)
+                g.replay()
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(5):
+                    g.replay()
+                t1.record()
+                torch.cuda.synchronize()
+                return t0.elapsed_time(t1) / (5 * K)
+            flush_ms = timed_graph(False, True)
+            graph = {'ms_graph_cold_l2': timed_graph(True, True) - flush_ms, 'ms_graph_back_to_back': timed_graph(True, False)}
+            graph['achieved_gbs_graph_cold'] = bytes_ / (graph['ms_graph_cold_l2'] * 1e-3) / 1e9
+            graph['frac_graph_cold'] = graph['achieved_gbs_graph_cold'] / hbm
+        except Exception as e:                       # capture is an extra: the eager figures stand on their own
+            graph = {'graph_error': str(e)[:200]}
         print(json.dumps({'workload': 'SMPL LBS forward (lbs_kernel + joints_kernel)', 'batch': B,
                           'ms_cold_l2': cold_ms, 'ms_back_to_back': warm_ms, 'bodies_per_s': B / (warm_ms * 1e-3),
                           'algorithmic_bytes': bytes_, 'achieved_gbs_cold': bytes_ / (cold_ms * 1e-3) / 1e9,
                           'achieved_gbs_back_to_back': bytes_ / (warm_ms * 1e-3) / 1e9, 'peak_gbs': hbm,
                           'frac_cold': bytes_ / (cold_ms * 1e-3) / 1e9 / hbm,
-                          'fma_gflops': 2 * 8.56e6 * B / (warm_ms * 1e-3) / 1e9}))
+                          'fma_gflops': 2 * 8.56e6 * B / (warm_ms * 1e-3) / 1e9, **graph}))
 
 
 if __name__ == '__main__':
