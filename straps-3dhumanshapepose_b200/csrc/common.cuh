@@ -215,6 +215,19 @@ __device__ __forceinline__ void tma_load_4d_u32(uint32_t dst, const CUtensorMap*
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 // SWIZZLE_128B K-major descriptor split into its two words: only the low word (start address >> 4, LBO = 1) moves with the
 // stage / K step; the high word (SBO = 1024 B, version 1, SWIZZLE_128B) is the constant below.
 constexpr uint32_t UMMA_DESC_SW128_HI = (1024u >> 4) | (1u << 14) | (2u << 29);

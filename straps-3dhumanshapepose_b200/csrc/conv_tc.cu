@@ -121,7 +121,11 @@ struct TcCfg {
 // this grid's CTAs have begun (griddepcontrol.launch_dependents), and does its own set-up (barriers, TMEM allocation, descriptor
 // prefetch) BEFORE it waits for the previous kernel's results (griddepcontrol.wait) -- launch latency and prologue move under the
 // previous kernel's tail.  Not yet run on hardware; the default instantiations carry neither instruction.
-template <int BN, int MT, int CL = 1, int BK = 64, int EPW = 4, bool PDL = false>
+// M2 (STRAPS_TC_TMA2=1) = two TMA operations per stage instead of four, with NO change of the data in HBM: the hi and lo planes of a
+// tensor are two allocations a fixed distance apart, so "plane" is simply one more (outermost) tensor-map dimension -- a 5-D box
+// {64 ch, w, h, images, 2 planes} lands as [A_hi tile][A_lo tile] and a 3-D box {64 K, BN rows, 2 planes} as [W_hi][W_lo], exactly the
+// stage layout the MMAs read.  map_a_hi / map_w_hi then carry the merged maps.  Tests the per-operation cost of item 3 in DESIGN.md 4.2.
+template <int BN, int MT, int CL = 1, int BK = 64, int EPW = 4, bool PDL = false, bool M2 = false>
 __global__ void __launch_bounds__(64 + 32 * EPW, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -199,12 +203,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (TC_NO_TMA(p)) { mbar_arrive(&full[st]); if (++st == Cfg::STAGES) { st = 0; ph ^= 1; } continue; }
 #endif
           mbar_expect_tx_u32(fb, Cfg::STAGE_BYTES);
+          if constexpr (M2) {
+            static_assert(!M2 || (CL == 1 && BK == 64), "merged-plane boxes: single-CTA SWIZZLE_128B stages only");
+#pragma unroll
+            for (int t = 0; t < MT; ++t) tma_load_5d_u32(sa + (2 * t) * Cfg::A_BYTES, &map_a_hi, fb, c0, c1, row0[t] + dh, b0[t], 0);
+            tma_load_3d_u32(sa + MT * 2 * Cfg::A_BYTES, &map_w_hi, fb, wk, wrow, 0);
+          } else {
 #pragma unroll
           for (int t = 0; t < MT; ++t) {
             tma_load_4d_u32(sa + (2 * t) * Cfg::A_BYTES, &map_a_hi, fb, c0, c1, row0[t] + dh, b0[t]);
             tma_load_4d_u32(sa + (2 * t + 1) * Cfg::A_BYTES, &map_a_lo, fb, c0, c1, row0[t] + dh, b0[t]);
           }
-          if constexpr (CL > 1) {
+          }
+          if constexpr (M2) {
+          } else if constexpr (CL > 1) {
             // this CTA's 1/CL of the weight rows, delivered to every CTA of the cluster (the W maps have BN / CL-row boxes)
             const uint32_t wo = sa + MT * 2 * Cfg::A_BYTES + crank * (Cfg::W_BYTES / CL);
             tma_load_2d_mc_u32(wo, &map_w_hi, fb, wk, wrow + crank * (BN / CL), CMASK);
@@ -1686,6 +1698,9 @@ struct TcLayerMaps {
   // halo boxes {64 channels, W + 2 pixels, RH rows} of the unpadded planes for conv_halo_kernel (halo = 1 when the layer qualifies)
   CUtensorMap h_hi, h_lo;
   int halo;
+  // merged-plane maps (STRAPS_TC_TMA2): A over {.., 2 planes} (5-D), W over {K, Cout, 2 planes} (3-D)
+  CUtensorMap a5, w3;
+  int has_merged;
 };
 
 struct TcState {
@@ -1862,6 +1877,7 @@ static bool halo_geom(const TcGeom& c, int* rh) {
 static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __half* a_lo, void* w_hi, void* w_lo, TcLayerMaps& out) {
   const int bn = tile_bn(c.cout);
   out.halo = 0;
+  const long long wplane = (const char*)w_lo - (const char*)w_hi;           // the lo plane follows the hi plane in the weight pool
   {
     cuuint64_t dims[2] = {(cuuint64_t)c.k_eff, (cuuint64_t)c.cout};
     cuuint64_t str[1] = {(cuuint64_t)c.k_eff * 2};
@@ -1880,7 +1896,17 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     if (encode(t, &out.w32_lo, w_lo, 2, dims, str, b32, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (encode(t, &out.w32h_hi, w_hi, 2, dims, str, b32h, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (encode(t, &out.w32h_lo, w_lo, 2, dims, str, b32h, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (wplane > 0 && wplane % 16 == 0) {
+      cuuint64_t d3[3] = {(cuuint64_t)c.k_eff, (cuuint64_t)c.cout, 2};
+      cuuint64_t s3[2] = {(cuuint64_t)c.k_eff * 2, (cuuint64_t)wplane};
+      cuuint32_t b3[3] = {64, (cuuint32_t)bn, 2};
+      cuuint32_t e3[3] = {1, 1, 1};
+      if (encode(t, &out.w3, w_hi, 3, d3, s3, b3, e3)) return 1;
+    }
   }
+  const long long aplane = (const char*)a_lo - (const char*)a_hi;
+  const bool a5_ok = aplane > 0 && aplane % 16 == 0;
+  out.has_merged = (a5_ok && wplane > 0 && wplane % 16 == 0) ? 1 : 0;
   if (c.conv1) {
     // conv1: (flattened kw,c run | ow | oh | b) over the padded input, strides bake in the stride-2 sampling
     cuuint64_t dims[4] = {(cuuint64_t)6 * XP_W * XP_C + C1_KROW, 128, 128, (cuuint64_t)B};
@@ -1889,6 +1915,13 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (encode(t, &out.a_hi, a_hi, 4, dims, str, box, es)) return 1;
     if (encode(t, &out.a_lo, a_lo, 4, dims, str, box, es)) return 1;
+    if (a5_ok) {
+      cuuint64_t d5[5] = {dims[0], dims[1], dims[2], dims[3], 2};
+      cuuint64_t s5[4] = {str[0], str[1], str[2], (cuuint64_t)aplane};
+      cuuint32_t b5[5] = {64, 128, 1, 1, 2};
+      cuuint32_t e5[5] = {1, 1, 1, 1, 1};
+      if (encode(t, &out.a5, a_hi, 5, d5, s5, b5, e5)) return 1;
+    }
     box[0] = 32;
     if (encode(t, &out.a32_hi, a_hi, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (encode(t, &out.a32_lo, a_lo, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
@@ -1901,6 +1934,13 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     cuuint32_t es[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
     if (encode(t, &out.a_hi, a_hi, 4, dims, str, box, es)) return 1;
     if (encode(t, &out.a_lo, a_lo, 4, dims, str, box, es)) return 1;
+    if (a5_ok) {
+      cuuint64_t d5[5] = {dims[0], dims[1], dims[2], dims[3], 2};
+      cuuint64_t s5[4] = {str[0], str[1], str[2], (cuuint64_t)aplane};
+      cuuint32_t b5[5] = {box[0], box[1], box[2], box[3], 2};
+      cuuint32_t e5[5] = {es[0], es[1], es[2], es[3], 1};
+      if (encode(t, &out.a5, a_hi, 5, d5, s5, b5, e5)) return 1;
+    }
     box[0] = 32;
     if (encode(t, &out.a32_hi, a_hi, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (encode(t, &out.a32_lo, a_lo, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
@@ -1926,6 +1966,23 @@ static int build_maps(straps_regressor* r, int B, std::vector<TcLayerMaps>& out)
     __half* a_lo = (i == 0) ? t->xp + t->xp_plane : plane_lo(r, c.in_buf);
     if (build_layer_maps(t, geom_fwd(c, i), B, a_hi, a_lo, c.w_hi, c.w_lo, out[i])) return 1;
   }
+  return 0;
+}
+
+// the shipped tile shapes with two TMA operations per stage (see conv_tc_kernel: M2)
+template <int BN>
+static int launch_conv_tc_m2(const TcLayerMaps& m, const TcConvParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg<BN, 1, 64>;
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
+    STRAPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, 1, 64, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_once.done(attr_dev);
+  }
+  const int items = p.n_mtiles * p.n_ntiles;
+  const int grid = items < num_sms ? items : num_sms;
+  conv_tc_kernel<BN, 1, 1, 64, 4, false, true><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a5, m.a5, m.w3, m.w3, p);
+  STRAPS_LAUNCH_CHECK();
   return 0;
 }
 
@@ -2128,6 +2185,12 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
     const char* e = getenv("STRAPS_TC_EPI_WARPS");      // read per launch: one process can compare both settings
     if (e && atoi(e) == 8 && mt == 1 && bn <= 128)
       return bn == 64 ? launch_conv_tc<64, 1, 64, 8>(m, p, t->num_sms, st) : launch_conv_tc<128, 1, 64, 8>(m, p, t->num_sms, st);
+  }
+  {
+    // STRAPS_TC_TMA2=1: merged-plane tensor maps, two TMA operations per stage (read per launch; not yet run on hardware)
+    const char* e = getenv("STRAPS_TC_TMA2");
+    if (e && atoi(e) == 1 && mt == 1 && bn <= 128 && m.has_merged)
+      return bn == 64 ? launch_conv_tc_m2<64>(m, p, t->num_sms, st) : launch_conv_tc_m2<128>(m, p, t->num_sms, st);
   }
   {
     // STRAPS_TC_PDL=1: programmatic dependent launch of the shipped tile shapes (read per launch; not yet run on hardware)

@@ -21,7 +21,7 @@ _UNVERIFIED = pytest.mark.skipif(not os.environ.get('STRAPS_TEST_UNVERIFIED'), r
 def _check(names, tmp_path, extra_env=None):
     out = os.path.join(str(tmp_path), 'check.json')
     env = dict(os.environ)
-    for k in ('STRAPS_TC_HALO', 'STRAPS_TC_EPI_WARPS', 'STRAPS_TC_CONV1', 'STRAPS_TC_S2D_PITCH', 'STRAPS_TC_DEBUG', 'STRAPS_TC_PAIR', 'STRAPS_TC_PDL'):
+    for k in ('STRAPS_TC_HALO', 'STRAPS_TC_EPI_WARPS', 'STRAPS_TC_CONV1', 'STRAPS_TC_S2D_PITCH', 'STRAPS_TC_DEBUG', 'STRAPS_TC_PAIR', 'STRAPS_TC_PDL', 'STRAPS_TC_TMA2'):
         env.pop(k, None)
     env.update(extra_env or {})
     res = subprocess.run([sys.executable, os.path.join(REPO, 'tools', 'halo_check.py'), '--out', out, '--only', ','.join(names),
@@ -73,3 +73,12 @@ def test_programmatic_dependent_launch_matches_shipped_kernel(tmp_path):
     got = _check(['pdl'], tmp_path)
     _assert_close(got, ['pdl'])
     assert got['pdl']['bit_identical'], got['pdl']
+
+
+@_UNVERIFIED
+def test_merged_plane_tensor_maps_match_shipped_kernel(tmp_path):
+    """STRAPS_TC_TMA2=1: the hi and lo tiles of A (5-D box) and of W (3-D box) arrive in one TMA operation each -- same bytes in the
+    same shared-memory places, so identical bits."""
+    got = _check(['tma2'], tmp_path)
+    _assert_close(got, ['tma2'])
+    assert got['tma2']['bit_identical'], got['tma2']

@@ -29,10 +29,10 @@ VARIANTS = (('halo64', {'STRAPS_TC_HALO': '64'}), ('halo128', {'STRAPS_TC_HALO':
             ('halo_epw8', {'STRAPS_TC_HALO': '1,8'}), ('epw8', {'STRAPS_TC_EPI_WARPS': '8'}),
             ('conv1_s2d', {'STRAPS_TC_CONV1': 's2d'}), ('conv1_s2d2', {'STRAPS_TC_CONV1': 's2d2'}), ('conv1_s2dp', {'STRAPS_TC_CONV1': 's2dp'}),
             ('pair', {'STRAPS_TC_PAIR': 'all'}), ('pair_m128', {'STRAPS_TC_PAIR': 'm128'}), ('pair_m', {'STRAPS_TC_PAIR': 'm'}),
-            ('pair_m+s2dp', {'STRAPS_TC_PAIR': 'm', 'STRAPS_TC_CONV1': 's2dp'}), ('pdl', {'STRAPS_TC_PDL': '1'}),
+            ('pair_m+s2dp', {'STRAPS_TC_PAIR': 'm', 'STRAPS_TC_CONV1': 's2dp'}), ('pdl', {'STRAPS_TC_PDL': '1'}), ('tma2', {'STRAPS_TC_TMA2': '1'}),
             ('pdl+s2dp', {'STRAPS_TC_PDL': '1', 'STRAPS_TC_CONV1': 's2dp'}))
 LAYERS = ['stem', 'pool'] + ['layer%d.%d%s' % (L, b, s) for L in (1, 2, 3, 4) for b in (0, 1) for s in ('.a', '')]
-SWITCHES = ('STRAPS_TC_HALO', 'STRAPS_TC_EPI_WARPS', 'STRAPS_TC_CONV1', 'STRAPS_TC_PAIR', 'STRAPS_TC_PDL')
+SWITCHES = ('STRAPS_TC_HALO', 'STRAPS_TC_EPI_WARPS', 'STRAPS_TC_CONV1', 'STRAPS_TC_PAIR', 'STRAPS_TC_PDL', 'STRAPS_TC_TMA2')
 
 
 def set_env(env):
