@@ -108,9 +108,13 @@ def encoder(x, sd, variant, taps):
         p2 = pow2_scale_to(ws, 16384.0, dim=(1, 2, 3))
         return (ws.float() * p2.float()).double(), (1.0 / p2).view(-1), shift
 
+    base, _, override = variant.partition('|')
+    sel, _, alt = override.partition(':')
+
     def layer(a, conv_name, bn_name, stride, pad, relu, res=None):
         w, unscale, shift = folded(conv_name, bn_name)
-        y = conv(variant, a, w, stride, pad) * unscale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+        v = alt if (sel and any(conv_name.startswith(q) for q in sel.split(','))) else base
+        y = conv(v, a, w, stride, pad) * unscale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
         if res is not None:
             y = y + res
         if relu:
@@ -147,12 +151,15 @@ def main():
     ref_taps = {}
     ref = encoder(x, sd, 'exact', ref_taps)
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
-    print('%-12s %10s %10s %10s %10s %10s   (max-abs error / max-abs reference; bar 1e-4; fp64 accumulation)'
+    print('%-34s %10s %10s %10s %10s %10s   (max-abs error / max-abs reference; bar 1e-4; fp64 accumulation)'
           % ('variant', 'stem', 'layer1.1', 'layer2.1', 'layer4.1', 'features'))
-    for variant in ('f16x3', 'lo_e4m3', 'lo_e5m2', 'both_lo_f8', 'f16x2_w', 'f16x2_a', 'f16x1'):
+    for variant in ('f16x3', 'lo_e4m3', 'lo_e5m2', 'both_lo_f8', 'f16x2_w', 'f16x2_a', 'f16x1',
+                    # the narrow MMA (A_lo.W_hi) dropped on the deepest layers only: "base|layer prefixes:variant for those layers"
+                    'f16x3|layer4.1.conv2:f16x2_w', 'f16x3|layer4.1:f16x2_w', 'f16x3|layer4:f16x2_w', 'f16x3|layer3,layer4:f16x2_w',
+                    'f16x3|layer4:lo_e5m2', 'f16x3|layer3,layer4:lo_e5m2'):
         taps = {}
         feat = encoder(x, sd, variant, taps)
-        print('%-12s %10.2e %10.2e %10.2e %10.2e %10.2e' % (variant, rel(taps['stem'], ref_taps['stem']),
+        print('%-34s %10.2e %10.2e %10.2e %10.2e %10.2e' % (variant, rel(taps['stem'], ref_taps['stem']),
               rel(taps['layer1.1'], ref_taps['layer1.1']), rel(taps['layer2.1'], ref_taps['layer2.1']),
               rel(taps['layer4.1'], ref_taps['layer4.1']), rel(feat, ref)))
 
