@@ -1896,17 +1896,18 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     if (encode(t, &out.w32_lo, w_lo, 2, dims, str, b32, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (encode(t, &out.w32h_hi, w_hi, 2, dims, str, b32h, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (encode(t, &out.w32h_lo, w_lo, 2, dims, str, b32h, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    if (wplane > 0 && wplane % 16 == 0) {
-      cuuint64_t d3[3] = {(cuuint64_t)c.k_eff, (cuuint64_t)c.cout, 2};
-      cuuint64_t s3[2] = {(cuuint64_t)c.k_eff * 2, (cuuint64_t)wplane};
-      cuuint32_t b3[3] = {64, (cuuint32_t)bn, 2};
-      cuuint32_t e3[3] = {1, 1, 1};
-      if (encode(t, &out.w3, w_hi, 3, d3, s3, b3, e3)) return 1;
-    }
   }
+  // Optional maps of switched-off variants must never take the shipped path down: a failed encode only clears the variant's flag.
   const long long aplane = (const char*)a_lo - (const char*)a_hi;
   const bool a5_ok = aplane > 0 && aplane % 16 == 0;
   out.has_merged = (a5_ok && wplane > 0 && wplane % 16 == 0) ? 1 : 0;
+  if (out.has_merged) {
+    cuuint64_t d3[3] = {(cuuint64_t)c.k_eff, (cuuint64_t)c.cout, 2};
+    cuuint64_t s3[2] = {(cuuint64_t)c.k_eff * 2, (cuuint64_t)wplane};
+    cuuint32_t b3[3] = {64, (cuuint32_t)bn, 2};
+    cuuint32_t e3[3] = {1, 1, 1};
+    if (encode(t, &out.w3, w_hi, 3, d3, s3, b3, e3)) out.has_merged = 0;
+  }
   if (c.conv1) {
     // conv1: (flattened kw,c run | ow | oh | b) over the padded input, strides bake in the stride-2 sampling
     cuuint64_t dims[4] = {(cuuint64_t)6 * XP_W * XP_C + C1_KROW, 128, 128, (cuuint64_t)B};
@@ -1915,12 +1916,12 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (encode(t, &out.a_hi, a_hi, 4, dims, str, box, es)) return 1;
     if (encode(t, &out.a_lo, a_lo, 4, dims, str, box, es)) return 1;
-    if (a5_ok) {
+    if (out.has_merged) {
       cuuint64_t d5[5] = {dims[0], dims[1], dims[2], dims[3], 2};
       cuuint64_t s5[4] = {str[0], str[1], str[2], (cuuint64_t)aplane};
       cuuint32_t b5[5] = {64, 128, 1, 1, 2};
       cuuint32_t e5[5] = {1, 1, 1, 1, 1};
-      if (encode(t, &out.a5, a_hi, 5, d5, s5, b5, e5)) return 1;
+      if (encode(t, &out.a5, a_hi, 5, d5, s5, b5, e5)) out.has_merged = 0;
     }
     box[0] = 32;
     if (encode(t, &out.a32_hi, a_hi, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
@@ -1934,12 +1935,12 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     cuuint32_t es[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
     if (encode(t, &out.a_hi, a_hi, 4, dims, str, box, es)) return 1;
     if (encode(t, &out.a_lo, a_lo, 4, dims, str, box, es)) return 1;
-    if (a5_ok) {
+    if (out.has_merged) {
       cuuint64_t d5[5] = {dims[0], dims[1], dims[2], dims[3], 2};
       cuuint64_t s5[4] = {str[0], str[1], str[2], (cuuint64_t)aplane};
       cuuint32_t b5[5] = {box[0], box[1], box[2], box[3], 2};
       cuuint32_t e5[5] = {es[0], es[1], es[2], es[3], 1};
-      if (encode(t, &out.a5, a_hi, 5, d5, s5, b5, e5)) return 1;
+      if (encode(t, &out.a5, a_hi, 5, d5, s5, b5, e5)) out.has_merged = 0;
     }
     box[0] = 32;
     if (encode(t, &out.a32_hi, a_hi, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
@@ -1948,9 +1949,7 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
     if (halo_geom(c, &rh)) {
       cuuint32_t hbox[4] = {64, (cuuint32_t)(c.win + 2), (cuuint32_t)rh, 1};
       cuuint32_t hes[4] = {1, 1, 1, 1};
-      if (encode(t, &out.h_hi, a_hi, 4, dims, str, hbox, hes)) return 1;
-      if (encode(t, &out.h_lo, a_lo, 4, dims, str, hbox, hes)) return 1;
-      out.halo = 1;
+      out.halo = (encode(t, &out.h_hi, a_hi, 4, dims, str, hbox, hes) || encode(t, &out.h_lo, a_lo, 4, dims, str, hbox, hes)) ? 0 : 1;
     }
   }
   return 0;
