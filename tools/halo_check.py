@@ -115,13 +115,20 @@ def main():
     flush()
     xt = torch.from_numpy(synthetic_inputs.make_proxy_batch(args.time_batch, C, seed=2)).cuda()
     res['timing_ms'] = {}
+    res['feat_at_time_batch'] = {}
+    ft0 = None
     for name, env in [('shipped', {})] + [v for v in variants if 'error' not in res.get(v[0], {})]:
         res['reached'] = 'timing:' + name
         flush()
         set_env(env)
         with torch.no_grad():
             for _ in range(3):
-                enc(xt)
+                ft = enc(xt).clone()
+            torch.cuda.synchronize()
+            if ft0 is None:
+                ft0 = ft
+            # the comparison above runs at a small batch; this one is the bench's batch (more tiles per SM, every ring wraps many times)
+            res['feat_at_time_batch'][name] = {'rel': rel(ft, ft0), 'bit_identical': bool(torch.equal(ft, ft0))}
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             e0.record()
