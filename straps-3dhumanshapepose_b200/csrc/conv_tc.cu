@@ -687,6 +687,259 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Halo kernel, second configuration (STRAPS_TC_HALO=2, layer1 only): MT = 2 consecutive 128-position tiles per work item share ONE
+// halo box (7 raster rows) and every weight stage, with a 5-stage weight ring and a single halo stage.
+// WRITTEN AFTER THE ROUND'S GPU BUDGET WAS SPENT; a separate kernel so that the hardware-verified conv_halo_kernel stays untouched.
+//
+// Why: conv_halo_kernel was correct but not faster.  Reading (a) of that result: per tile it still streams all
+// 9 weight tiles (144 KB on layer1) through a ring that keeps only 2 x 16 KB in flight, and with ~2600 cycles of loaded TMA latency that
+// alone is ~11,000 cycles per tile.  Here a weight stage feeds the MMAs of two tiles (72 KB of W per tile) and four stages are in
+// flight while one is consumed; the price is a single-buffered halo box (118 KB), whose load is exposed once per two tiles.
+// If reading (a) is right this is ~5,500 cycles per tile instead of ~9,700; if the epilogue is the limit (reading (b)) it is not
+// faster -- one run decides.
+// ---------------------------------------------------------------------------------------------------------
+template <int BN, int RH, int WP, int MT, int NAS, int NWS>
+struct Halo2Cfg {
+  static constexpr int A_LINES = RH * WP;
+  static constexpr int A_BOX_BYTES = A_LINES * 128;
+  static constexpr int A_PLANE = (A_BOX_BYTES + 1023) / 1024 * 1024;
+  static constexpr int A_STAGE = 2 * A_PLANE;
+  static constexpr int AS = NAS;
+  static constexpr int W_BYTES = BN * 128;
+  static constexpr int W_STAGE = 2 * W_BYTES;
+  static constexpr int WS = NWS;
+  static constexpr int W_OFF = AS * A_STAGE;
+  static constexpr int SMEM_BYTES = AS * A_STAGE + WS * W_STAGE + 1024 + 256;
+  static constexpr int TILE_COLS = 2 * BN;
+  static constexpr int ACC_COLS = MT * TILE_COLS;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(RH * WP >= MT * 128 + 2 * WP + 2 + WP - 1, "halo box too small");
+  static_assert(WP <= 256 && RH <= 256, "TMA box dimensions are limited to 256");
+  static_assert(SMEM_BYTES <= 232448 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "halo tile configuration does not fit");
+  static_assert(2 * (AS + WS) * 8 + 40 <= 256, "barrier block too small");
+};
+
+template <int BN, int RH, int WP, int MT, int NAS, int NWS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const HaloParams p) {
+  using Cfg = Halo2Cfg<BN, RH, WP, MT, NAS, NWS>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::AS * Cfg::A_STAGE + Cfg::WS * Cfg::W_STAGE);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + Cfg::AS;
+  uint64_t* w_full = a_empty + Cfg::AS;
+  uint64_t* w_empty = w_full + Cfg::WS;
+  uint64_t* tfull = w_empty + Cfg::WS;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::AS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < Cfg::WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty), w_full0 = smem_u32(w_full), w_empty0 = smem_u32(w_empty);
+  const int ipi = p.tiles_per_image, cchunks = p.cchunks;     // here: ITEMS (groups of MT tiles) per image
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      uint32_t as = 0, aph = 1, ws = 0, wph = 1;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int b = item / ipi, it = item - b * ipi;
+        const int p0 = it * (MT * BM_TC);
+        const int r0 = (p0 + WP - 1) / WP - 2;
+        for (int cc = 0; cc < cchunks; ++cc) {
+          const uint32_t sa = smem0 + as * Cfg::A_STAGE, fb = a_full0 + as * 8;
+          mbar_wait_u32(a_empty0 + as * 8, aph);
+          if (TC_NO_TMA(p)) {
+            mbar_arrive(&a_full[as]);
+          } else {
+            mbar_expect_tx_u32(fb, 2 * Cfg::A_BOX_BYTES);
+            tma_load_4d_u32(sa, &map_a_hi, fb, cc * 64, -1, r0 - 1, b);
+            tma_load_4d_u32(sa + Cfg::A_PLANE, &map_a_lo, fb, cc * 64, -1, r0 - 1, b);
+          }
+          if (++as == Cfg::AS) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t sw = smem0 + Cfg::W_OFF + ws * Cfg::W_STAGE, wb = w_full0 + ws * 8;
+            mbar_wait_u32(w_empty0 + ws * 8, wph);
+            if (TC_NO_TMA(p)) {
+              mbar_arrive(&w_full[ws]);
+            } else {
+              mbar_expect_tx_u32(wb, Cfg::W_STAGE);
+              const int wk = (tap * cchunks + cc) * BK_TC;
+              tma_load_2d_u32(sw, &map_w_hi, wb, wk, 0);
+              tma_load_2d_u32(sw + Cfg::W_BYTES, &map_w_lo, wb, wk, 0);
+            }
+            if (++ws == Cfg::WS) { ws = 0; wph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM_TC, BN);
+      constexpr uint32_t idesc_wide = umma_idesc_f16(BM_TC, 2 * BN);
+      static_assert(2 * BN <= 256, "the merged [W_hi ; W_lo] MMA needs N <= 256");
+      const uint32_t tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, acs = 0, acph = 1;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int it = item % ipi;
+        const int p0 = it * (MT * BM_TC);
+        const int r0 = (p0 + WP - 1) / WP - 2;
+        const int base = p0 - r0 * WP;
+        mbar_wait_u32(tempty0 + acs * 8, acph);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + acs * Cfg::ACC_COLS;
+        uint32_t accum = 0;
+        for (int cc = 0; cc < cchunks; ++cc) {
+          mbar_wait_u32(a_full0 + as * 8, aph);
+          tc_fence_after();
+          const uint32_t a0 = umma_desc_sw128_lo(smem0 + as * Cfg::A_STAGE);
+          int start = base - WP - 1;
+          for (int kh = 0; kh < 3; ++kh, start += WP - 3)
+            for (int kw = 0; kw < 3; ++kw, ++start) {
+              mbar_wait_u32(w_full0 + ws * 8, wph);
+              tc_fence_after();
+              const uint32_t w_hi = umma_desc_sw128_lo(smem0 + Cfg::W_OFF + ws * Cfg::W_STAGE);
+              if (!TC_NO_MMA(p)) {
+#pragma unroll
+                for (int t = 0; t < MT; ++t) {
+                  const uint32_t a_hi = a0 + (uint32_t)(start + t * BM_TC) * 8u;      // tile t = the next 128 lines of the same box
+                  const uint32_t a_lo = a_hi + (Cfg::A_PLANE >> 4);
+                  const uint32_t d_hi = acc + t * Cfg::TILE_COLS, d_lo = d_hi + BN;
+#pragma unroll
+                  for (int k = 0; k < BK_TC / 16; ++k) {
+                    umma_f16_lohi(d_hi, a_hi + 2 * k, w_hi + 2 * k, idesc_wide, accum);
+                    umma_f16_lohi(d_lo, a_lo + 2 * k, w_hi + 2 * k, idesc, 1);
+                  }
+                }
+              }
+              accum = 1;
+              umma_commit_u32(w_empty0 + ws * 8);
+              if (++ws == Cfg::WS) { ws = 0; wph ^= 1; }
+            }
+          umma_commit_u32(a_empty0 + as * 8);
+          if (++as == Cfg::AS) { as = 0; aph ^= 1; }
+        }
+        umma_commit_u32(tfull0 + acs * 8);
+        if (++acs == 2) { acs = 0; acph ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    constexpr int NCHUNK = MT * (BN / 32);
+    uint32_t ti = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++ti) {
+      const int b = item / ipi, it = item - b * ipi;
+      const uint32_t acs = ti & 1;
+      // raster position, validity and output offset of this thread's row in tile t of the item
+      auto locate = [&](int t, bool& valid, size_t& obase) {
+        const int pos = it * (MT * BM_TC) + t * BM_TC + row;
+        const int py = pos / WP, px = pos - py * WP;
+        valid = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
+        obase = (((size_t)b * p.H + (py - 1)) * p.W + (px - 1)) * p.cout;             // only used when valid
+      };
+      uint4 rh[4], rl[4];
+      auto fetch_residual = [&](int chunk) {
+        if (p.res_hi && chunk < NCHUNK && TC_EPI_IO(p)) {
+          bool valid; size_t obase;
+          locate(chunk / (BN / 32), valid, obase);
+          if (valid) {
+            const int c0 = (chunk % (BN / 32)) * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + obase + c0) + q);
+              rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + obase + c0) + q);
+            }
+          }
+        }
+      };
+      fetch_residual(0);
+      mbar_wait(&tfull[acs], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+        const int t = chunk / (BN / 32), c0 = (chunk % (BN / 32)) * 32;
+        bool valid; size_t obase;
+        locate(t, valid, obase);
+        uint32_t v[32], vl[32];
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + acs * Cfg::ACC_COLS + t * Cfg::TILE_COLS + c0;
+        tmem_ld_32x32(tacc, v);
+        tmem_ld_32x32(tacc + BN, vl);
+        tmem_ld_wait();
+        float y[32];
+        const float4* sh4 = reinterpret_cast<const float4*>(p.shift + c0);
+        const float4* us4 = reinterpret_cast<const float4*>(p.unscale + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
+          y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
+          y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
+          y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
+          y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+        }
+        if (valid && p.res_hi && TC_EPI_IO(p)) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t hw[4] = {rh[q].x, rh[q].y, rh[q].z, rh[q].w}, lw[4] = {rl[q].x, rl[q].y, rl[q].z, rl[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              y[q * 8 + e * 2 + 0] += f16lo_to_f(hw[e]) + f16lo_to_f(lw[e]);
+              y[q * 8 + e * 2 + 1] += f16hi_to_f(hw[e]) + f16hi_to_f(lw[e]);
+            }
+          }
+        }
+        fetch_residual(chunk + 1);
+        if (valid && TC_EPI_IO(p)) {
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
+          }
+          uint32_t ph[16], pl[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __half h0, l0, h1, l1;
+            split_f16(y[2 * i], h0, l0);
+            split_f16(y[2 * i + 1], h1, l1);
+            ph[i] = pack_f16(h0, h1);
+            pl[i] = pack_f16(l0, l1);
+          }
+          uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
+          uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
+            ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acs]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // conv1 (7x7 / stride 2 / pad 3, Cout = 64) from a pixel-PAIR layout of the padded input -- STRAPS_TC_CONV1=s2d | s2d2.
 // WRITTEN AFTER THE ROUND'S GPU BUDGET WAS SPENT: compiled, its index arithmetic replayed against conv2d on the CPU
 // (tools/conv1_s2d_emulation.py); NOT yet run on hardware, and the default path never reaches it.  It applies to conv1 what
@@ -1698,6 +1951,8 @@ struct TcLayerMaps {
   // halo boxes {64 channels, W + 2 pixels, RH rows} of the unpadded planes for conv_halo_kernel (halo = 1 when the layer qualifies)
   CUtensorMap h_hi, h_lo;
   int halo;
+  CUtensorMap h2_hi, h2_lo;     // 7-row boxes for conv_halo2_kernel (layer1: two tiles per item); halo2 = 1 when present
+  int halo2;
   // merged-plane maps (STRAPS_TC_TMA2): A over {.., 2 planes} (5-D), W over {K, Cout, 2 planes} (3-D)
   CUtensorMap a5, w3;
   int has_merged;
@@ -1877,6 +2132,7 @@ static bool halo_geom(const TcGeom& c, int* rh) {
 static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __half* a_lo, void* w_hi, void* w_lo, TcLayerMaps& out) {
   const int bn = tile_bn(c.cout);
   out.halo = 0;
+  out.halo2 = 0;
   const long long wplane = (const char*)w_lo - (const char*)w_hi;           // the lo plane follows the hi plane in the weight pool
   {
     cuuint64_t dims[2] = {(cuuint64_t)c.k_eff, (cuuint64_t)c.cout};
@@ -1950,6 +2206,10 @@ static int build_layer_maps(TcState* t, const TcGeom& c, int B, __half* a_hi, __
       cuuint32_t hbox[4] = {64, (cuuint32_t)(c.win + 2), (cuuint32_t)rh, 1};
       cuuint32_t hes[4] = {1, 1, 1, 1};
       out.halo = (encode(t, &out.h_hi, a_hi, 4, dims, str, hbox, hes) || encode(t, &out.h_lo, a_lo, 4, dims, str, hbox, hes)) ? 0 : 1;
+      if (c.cout == 64) {
+        hbox[2] = 7;
+        out.halo2 = (encode(t, &out.h2_hi, a_hi, 4, dims, str, hbox, hes) || encode(t, &out.h2_lo, a_lo, 4, dims, str, hbox, hes)) ? 0 : 1;
+      }
     }
   }
   return 0;
@@ -2124,6 +2384,35 @@ static int launch_conv_halo(const TcLayerMaps& m, const TcConvParams& p, const T
   return 0;
 }
 
+// conv_halo2_kernel, layer1 configuration: two tiles per item, one halo stage of 7 raster rows, five weight stages
+static int launch_conv_halo2(const TcLayerMaps& m, const TcConvParams& p, const TcGeom& c, int B, int num_sms, cudaStream_t st) {
+  constexpr int BN = 64, RH = 7, WP = 66, MT = 2;
+  using Cfg = Halo2Cfg<BN, RH, WP, MT, 1, 5>;
+  static PerDeviceOnce attr_once;
+  const int attr_dev = current_device();
+  if (attr_once.need(attr_dev)) {
+    STRAPS_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<BN, RH, WP, MT, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_once.done(attr_dev);
+  }
+  HaloParams h;
+  memset(&h, 0, sizeof(h));
+  h.H = c.hin; h.W = c.win;
+  const int tiles = (c.hin * WP + c.win) / BM_TC + 1;          // tiles that hold an interior position (34 on layer1)
+  h.tiles_per_image = (tiles + MT - 1) / MT;                   // this kernel counts ITEMS of MT tiles
+  h.n_items = B * h.tiles_per_image;
+  h.cchunks = c.cin / 64;
+  h.cout = c.cout;
+  h.shift = p.shift; h.unscale = p.unscale;
+  h.out_hi = p.out_hi; h.out_lo = p.out_lo;
+  h.res_hi = p.res_hi; h.res_lo = p.res_lo;
+  h.relu = p.relu;
+  h.debug = p.debug;
+  const int grid = h.n_items < num_sms ? h.n_items : num_sms;
+  conv_halo2_kernel<BN, RH, WP, MT, 1, 5><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.h2_hi, m.h2_lo, m.w_hi, m.w_lo, h);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
 // p carries the pointers (shift, unscale, outputs, residuals, relu); the geometry fields are filled here
 static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParams p, int B, cudaStream_t st) {
   const int bn = tile_bn(c.cout);
@@ -2153,7 +2442,10 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
     // Verified on B200 (profiles/r01_halo_check.json) but slower than conv_tc_kernel: off by default.
     const char* e = getenv("STRAPS_TC_HALO");
     const int sel = e ? atoi(e) : 0;
-    if (sel && m.halo && p.out_hi && !p.out_f32 && !p.res_f32 && bn == c.cout && (sel == 1 || sel == c.cout)) {
+    // "2": layer1 through conv_halo2_kernel (two tiles per item, deeper weight ring); not yet run on hardware
+    if (sel == 2 && m.halo2 && p.out_hi && !p.out_f32 && !p.res_f32 && c.cout == 64 && bn == 64 && c.hin == 64)
+      return launch_conv_halo2(m, p, c, B, t->num_sms, st);
+    if (sel && sel != 2 && m.halo && p.out_hi && !p.out_f32 && !p.res_f32 && bn == c.cout && (sel == 1 || sel == c.cout)) {
       const bool e8 = strstr(e, ",8") != nullptr;
       if (c.cout == 64)
         return e8 ? launch_conv_halo<64, 5, 66, 8>(m, p, c, B, t->num_sms, st) : launch_conv_halo<64, 5, 66>(m, p, c, B, t->num_sms, st);

@@ -82,3 +82,11 @@ def test_merged_plane_tensor_maps_match_shipped_kernel(tmp_path):
     got = _check(['tma2'], tmp_path)
     _assert_close(got, ['tma2'])
     assert got['tma2']['bit_identical'], got['tma2']
+
+
+@_UNVERIFIED
+def test_two_tile_halo_kernel_matches_shipped_kernel(tmp_path):
+    """conv_halo2_kernel (layer1, two tiles per item, five weight stages): same K order as the shipped kernel on layer1."""
+    got = _check(['halo2'], tmp_path)
+    _assert_close(got, ['halo2'])
+    assert got['halo2']['bit_identical'], got['halo2']

@@ -25,7 +25,7 @@ for p in (ORACLE, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-VARIANTS = (('halo64', {'STRAPS_TC_HALO': '64'}), ('halo128', {'STRAPS_TC_HALO': '128'}), ('halo', {'STRAPS_TC_HALO': '1'}),
+VARIANTS = (('halo2', {'STRAPS_TC_HALO': '2'}), ('halo64', {'STRAPS_TC_HALO': '64'}), ('halo128', {'STRAPS_TC_HALO': '128'}), ('halo', {'STRAPS_TC_HALO': '1'}),
             ('halo_epw8', {'STRAPS_TC_HALO': '1,8'}), ('epw8', {'STRAPS_TC_EPI_WARPS': '8'}),
             ('conv1_s2d', {'STRAPS_TC_CONV1': 's2d'}), ('conv1_s2d2', {'STRAPS_TC_CONV1': 's2d2'}), ('conv1_s2dp', {'STRAPS_TC_CONV1': 's2dp'}),
             ('pair', {'STRAPS_TC_PAIR': 'all'}), ('pair_m128', {'STRAPS_TC_PAIR': 'm128'}), ('pair_m', {'STRAPS_TC_PAIR': 'm'}),

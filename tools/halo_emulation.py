@@ -34,8 +34,11 @@ def tiles_per_image(H, W):
     return last_interior // TILE + 1
 
 
-def halo_conv3x3(x_nchw, w_oihw):
-    """3x3 / stride 1 / pad 1 convolution through the virtual padded raster + halo box + tap-shift scheme."""
+def halo_conv3x3(x_nchw, w_oihw, mt=1):
+    """3x3 / stride 1 / pad 1 convolution through the virtual padded raster + halo box + tap-shift scheme.
+    mt = 2: conv_halo2_kernel -- two consecutive tiles per work item share one (taller) box."""
+    if mt > 1:
+        return halo_conv3x3_items(x_nchw, w_oihw, mt)
     B, C, H, W = x_nchw.shape
     Co = w_oihw.shape[0]
     Hp, Wp = H + 2, W + 2
@@ -69,6 +72,46 @@ def halo_conv3x3(x_nchw, w_oihw):
     return np.transpose(out, (0, 3, 1, 2)), RH
 
 
+def halo_conv3x3_items(x_nchw, w_oihw, mt):
+    """conv_halo2_kernel's arithmetic: an item = mt consecutive tiles; one box of rows(mt) raster rows; tile t of the item reads the
+    windows that start t * 128 lines further down."""
+    B, C, H, W = x_nchw.shape
+    Co = w_oihw.shape[0]
+    Wp = W + 2
+    RH = -(-(mt * TILE + 2 * Wp + 2) // Wp) + 1
+    items = -(-tiles_per_image(H, W) // mt)
+    x_nhwc = np.transpose(x_nchw, (0, 2, 3, 1)).astype(np.float64)
+    out = np.zeros((B, H, W, Co), dtype=np.float64)
+    wk = np.transpose(w_oihw, (2, 3, 1, 0)).astype(np.float64)
+    for b in range(B):
+        for it in range(items):
+            p0 = it * mt * TILE
+            r0 = (p0 + Wp - 1) // Wp - 2
+            halo = np.zeros((RH, Wp, C))
+            for i in range(RH):
+                y = r0 - 1 + i
+                if 0 <= y < H:
+                    halo[i, 1:W + 1] = x_nhwc[b, y]
+            lines = halo.reshape(RH * Wp, C)
+            base = p0 - r0 * Wp
+            for t in range(mt):
+                acc = np.zeros((TILE, Co))
+                start = base - Wp - 1
+                for kh in range(3):
+                    for kw in range(3):
+                        s0 = start + t * TILE
+                        assert 0 <= s0 and s0 + TILE <= RH * Wp, (p0, t, kh, kw, s0, RH * Wp)
+                        acc += lines[s0:s0 + TILE] @ wk[kh, kw]
+                        start += 1
+                    start += Wp - 3
+                for r in range(TILE):
+                    p = p0 + t * TILE + r
+                    py, px = p // Wp, p % Wp
+                    if 1 <= py <= H and 1 <= px <= W:
+                        out[b, py - 1, px - 1] = acc[r]
+    return np.transpose(out, (0, 3, 1, 2)), RH
+
+
 def main():
     rng = np.random.RandomState(0)
     worst = 0.0
@@ -81,6 +124,15 @@ def main():
         worst = max(worst, err)
         print('B=%d C=%d %dx%d -> Cout=%d: max abs error %.2e   (box of %d rows x %d pixels, %d tiles per image instead of %.1f)'
               % (B, C, H, W, Co, err, RH, W + 2, tiles_per_image(H, W), H * W / TILE))
+    x = rng.normal(0, 1, (2, 2, 64, 64))
+    w = rng.normal(0, 1, (2, 2, 3, 3))
+    got, RH = halo_conv3x3(x, w, mt=2)
+    ref = F.conv2d(torch.from_numpy(x), torch.from_numpy(w), padding=1).numpy()
+    err = float(np.abs(got - ref).max())
+    worst = max(worst, err)
+    print('two tiles per item (conv_halo2_kernel), 64x64: max abs error %.2e   (box of %d rows, %d items per image)'
+          % (err, RH, -(-tiles_per_image(64, 64) // 2)))
+    assert RH == 7
     for name, hw, cin, bn in (('layer1', 64, 64, 64), ('layer2', 32, 128, 128)):
         wp, rh = hw + 2, halo_rows(hw)
         a_now, a_halo = 9 * (cin // 64) * 2 * TILE * 128, (cin // 64) * 2 * rh * wp * 128

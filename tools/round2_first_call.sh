@@ -11,7 +11,7 @@ mkdir -p gpurun_out
 run() { name=$1; shift; timeout -s KILL 120 "$@" > gpurun_out/$name.log 2>&1; echo "$name rc=$?"; }
 run check_s2d    python tools/halo_check.py --out gpurun_out/check_s2d.json --only conv1_s2d,conv1_s2d2,conv1_s2dp
 run check_pair   python tools/halo_check.py --out gpurun_out/check_pair.json --only pair,pair_m128,pair_m
-run check_combo  python tools/halo_check.py --out gpurun_out/check_combo.json --only pair_m+s2dp,tma2,pdl,pdl+s2dp,halo
+run check_combo  python tools/halo_check.py --out gpurun_out/check_combo.json --only pair_m+s2dp,tma2,pdl,pdl+s2dp,halo,halo2
 STRAPS_TC_S2D_PITCH=48 run check_s2d_p48 python tools/halo_check.py --out gpurun_out/check_s2d_p48.json --only conv1_s2d,conv1_s2d2,conv1_s2dp
 STRAPS_TEST_UNVERIFIED=1 timeout -s KILL 600 python -m pytest tests/test_gpu_zz_conv_kernels.py tests/test_gpu_conv_variants.py -q -m gpu > gpurun_out/pytest_unverified.log 2>&1
 echo "pytest rc=$?"
