@@ -2099,10 +2099,38 @@ static TcGeom geom_dgrad(const ConvSpec& c) {
   return g;
 }
 
+// Kernel-selection switches (README: environment switches).  They are read from the environment ONCE PER ENCODER CALL / TRAINING STEP
+// (tc_refresh_switches), not per launch -- a process may still change them between calls to compare variants (tools/halo_check.py).
+// One host thread per GPU drives the library, so a plain global is enough; everything defaults to the shipped path.
+struct TcSwitches {
+  bool wide;          // STRAPS_TC_TILES=wide
+  int debug;          // STRAPS_TC_DEBUG (experiment builds)
+  int halo;           // STRAPS_TC_HALO: 0 off, 1 layer1 + layer2, 64 / 128 one of them, 2 = conv_halo2_kernel on layer1
+  bool halo_e8;       // "...,8": two epilogue warps per quadrant in conv_halo_kernel
+  char pair[8];       // STRAPS_TC_PAIR: "", "1", "all", "m", "m128"
+  int epw;            // STRAPS_TC_EPI_WARPS
+  int tma2;           // STRAPS_TC_TMA2
+  int pdl;            // STRAPS_TC_PDL
+  int conv1;          // STRAPS_TC_CONV1: 0 shipped, 1 s2d, 2 s2d2, 3 s2dp
+};
+static TcSwitches g_sw = {false, 0, 0, false, {0}, 4, 0, 0, 0};
+
+static void tc_refresh_switches() {
+  const char* e;
+  e = getenv("STRAPS_TC_TILES");      g_sw.wide = e && e[0] == 'w';
+  e = getenv("STRAPS_TC_DEBUG");      g_sw.debug = e ? atoi(e) : 0;
+  e = getenv("STRAPS_TC_HALO");       g_sw.halo = e ? atoi(e) : 0; g_sw.halo_e8 = e && strstr(e, ",8") != nullptr;
+  e = getenv("STRAPS_TC_PAIR");       memset(g_sw.pair, 0, sizeof(g_sw.pair)); if (e) strncpy(g_sw.pair, e, sizeof(g_sw.pair) - 1);
+  e = getenv("STRAPS_TC_EPI_WARPS");  g_sw.epw = e ? atoi(e) : 4;
+  e = getenv("STRAPS_TC_TMA2");       g_sw.tma2 = e ? atoi(e) : 0;
+  e = getenv("STRAPS_TC_PDL");        g_sw.pdl = e ? atoi(e) : 0;
+  e = getenv("STRAPS_TC_CONV1");
+  g_sw.conv1 = (e && strncmp(e, "s2d", 3) == 0) ? (e[3] == 'p' ? 3 : e[3] == '2' ? 2 : 1) : 0;
+}
+
 // tile configuration per layer (see TcCfg): BN, MT
 static void tile_cfg(int cout, int* bn, int* mt) {
-  const char* e = getenv("STRAPS_TC_TILES");      // "wide" selects the experimental (64,2)/(128,2)/(256,1) shapes
-  const bool wide = e && e[0] == 'w';
+  const bool wide = g_sw.wide;                    // "wide" selects the experimental (64,2)/(128,2)/(256,1) shapes
   if (cout == 64) { *bn = 64; *mt = wide ? 2 : 1; }
   else if (cout == 128) { *bn = 128; *mt = wide ? 2 : 1; }
   else if (cout == 256 && wide) { *bn = 256; *mt = 1; }
@@ -2435,18 +2463,17 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
   p.hw_out = c.hout * c.wout; p.wout = c.wout;
   p.th = (c.hout * c.wout >= BM_TC) ? BM_TC / c.wout : c.hout;
   p.cout = c.cout;
-  { const char* d = getenv("STRAPS_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
+  p.debug = g_sw.debug;
   {
     // STRAPS_TC_HALO: "1" = layer1 and layer2 stride-1 3x3 convolutions through conv_halo_kernel, "64" / "128" = only the layers of
-    // that width; "8" appended ("1,8") = two epilogue warps per quadrant.  Read per launch so that one process can compare both paths.
+    // that width; "8" appended ("1,8") = two epilogue warps per quadrant.
     // Verified on B200 (profiles/r01_halo_check.json) but slower than conv_tc_kernel: off by default.
-    const char* e = getenv("STRAPS_TC_HALO");
-    const int sel = e ? atoi(e) : 0;
+    const int sel = g_sw.halo;
     // "2": layer1 through conv_halo2_kernel (two tiles per item, deeper weight ring); not yet run on hardware
     if (sel == 2 && m.halo2 && p.out_hi && !p.out_f32 && !p.res_f32 && c.cout == 64 && bn == 64 && c.hin == 64)
       return launch_conv_halo2(m, p, c, B, t->num_sms, st);
     if (sel && sel != 2 && m.halo && p.out_hi && !p.out_f32 && !p.res_f32 && bn == c.cout && (sel == 1 || sel == c.cout)) {
-      const bool e8 = strstr(e, ",8") != nullptr;
+      const bool e8 = g_sw.halo_e8;
       if (c.cout == 64)
         return e8 ? launch_conv_halo<64, 5, 66, 8>(m, p, c, B, t->num_sms, st) : launch_conv_halo<64, 5, 66>(m, p, c, B, t->num_sms, st);
       return e8 ? launch_conv_halo<128, 7, 34, 8>(m, p, c, B, t->num_sms, st) : launch_conv_halo<128, 7, 34>(m, p, c, B, t->num_sms, st);
@@ -2455,10 +2482,10 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
   {
     // STRAPS_TC_PAIR: "128" = CTA pairs for the Cout >= 128 layers, "all" = every layer, unset/"0" = single-CTA kernels;
     // "m" / "m128" = the same selection with conv_tc2m_kernel (merged wide MMA, lean loops; not yet run on hardware)
-    const char* e = getenv("STRAPS_TC_PAIR");
-    if (e && e[0] == 'm' && (e[1] == '\0' || c.cout >= 128) && mt == 1 && bn <= 128 && !p.res_f32 && !k32)
+    const char* e = g_sw.pair;
+    if (e[0] == 'm' && (e[1] == '\0' || c.cout >= 128) && mt == 1 && bn <= 128 && !p.res_f32 && !k32)
       return bn == 64 ? launch_conv_tc2m<64>(m, p, t->num_sms, st) : launch_conv_tc2m<128>(m, p, t->num_sms, st);
-    const bool pair = e && ((e[0] == 'a') || (e[0] == '1' && c.cout >= 128));
+    const bool pair = (e[0] == 'a') || (e[0] == '1' && c.cout >= 128);
     if (pair && mt == 1 && bn <= 128 && !p.res_f32 && !k32)
       return bn == 64 ? launch_conv_tc2<64>(m, p, t->num_sms, st) : launch_conv_tc2<128>(m, p, t->num_sms, st);
   }
@@ -2473,20 +2500,17 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
   {
     // STRAPS_TC_EPI_WARPS = 8: two epilogue warps per TMEM lane quadrant.  Bit-identical on B200 but 4 % slower (encoder 1.651 vs
     // 1.584 ms, profiles/r01_halo_check.json): the epilogue is not short of warps to hide latency; the default stays 4.
-    const char* e = getenv("STRAPS_TC_EPI_WARPS");      // read per launch: one process can compare both settings
-    if (e && atoi(e) == 8 && mt == 1 && bn <= 128)
+    if (g_sw.epw == 8 && mt == 1 && bn <= 128)
       return bn == 64 ? launch_conv_tc<64, 1, 64, 8>(m, p, t->num_sms, st) : launch_conv_tc<128, 1, 64, 8>(m, p, t->num_sms, st);
   }
   {
-    // STRAPS_TC_TMA2=1: merged-plane tensor maps, two TMA operations per stage (read per launch; not yet run on hardware)
-    const char* e = getenv("STRAPS_TC_TMA2");
-    if (e && atoi(e) == 1 && mt == 1 && bn <= 128 && m.has_merged)
+    // STRAPS_TC_TMA2=1: merged-plane tensor maps, two TMA operations per stage (not yet run on hardware)
+    if (g_sw.tma2 == 1 && mt == 1 && bn <= 128 && m.has_merged)
       return bn == 64 ? launch_conv_tc_m2<64>(m, p, t->num_sms, st) : launch_conv_tc_m2<128>(m, p, t->num_sms, st);
   }
   {
-    // STRAPS_TC_PDL=1: programmatic dependent launch of the shipped tile shapes (read per launch; not yet run on hardware)
-    const char* e = getenv("STRAPS_TC_PDL");
-    if (e && atoi(e) == 1 && mt == 1 && bn <= 128)
+    // STRAPS_TC_PDL=1: programmatic dependent launch of the shipped tile shapes (not yet run on hardware)
+    if (g_sw.pdl == 1 && mt == 1 && bn <= 128)
       return bn == 64 ? launch_conv_tc_pdl<64>(m, p, t->num_sms, st) : launch_conv_tc_pdl<128>(m, p, t->num_sms, st);
   }
   if (bn == 64) return mt == 2 ? launch_conv_tc<64, 2>(m, p, t->num_sms, st) : launch_conv_tc<64, 1>(m, p, t->num_sms, st);
@@ -2573,7 +2597,7 @@ static int launch_conv1_s2d(straps_regressor* r, const TcState::S2dMaps& m, int 
   p.pool_hi = plane_hi(r, r->buf_pool);
   p.pool_lo = plane_lo(r, r->buf_pool);
   p.relu = c.relu;
-  { const char* d = getenv("STRAPS_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
+  p.debug = g_sw.debug;
   const int grid = p.n_items < t->num_sms ? p.n_items : t->num_sms;
   conv1_s2d_kernel<MT, POOL><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.a_hi, m.a_lo, m.w, p);
   STRAPS_LAUNCH_CHECK();
@@ -2594,6 +2618,7 @@ static int run_conv1_s2d(straps_regressor* r, const float* x, int B, int mt, cud
 int tc_encoder_forward(straps_regressor* r, const float* x, int B, float* feat, cudaStream_t st) {
   TcState* t = static_cast<TcState*>(r->tc);
   STRAPS_CHECK(t, "tc_encoder_forward: tensor-core state missing");
+  tc_refresh_switches();
   auto it = t->maps.find(B);
   if (it == t->maps.end()) {
     std::vector<TcLayerMaps> v;
@@ -2602,13 +2627,12 @@ int tc_encoder_forward(straps_regressor* r, const float* x, int B, float* feat, 
   }
   const std::vector<TcLayerMaps>& maps = it->second;
   // STRAPS_TC_CONV1 = "s2d" / "s2d2" / "s2dp": conv1 from the pixel-pair layout (one / two output rows per work item / two rows and the
-  // max pool fused into the epilogue); read per call.
+  // max pool fused into the epilogue); all switches are refreshed from the environment at the top of this call.
   // NOT YET RUN ON HARDWARE (see conv1_s2d_kernel); unset = the shipped path.
-  const char* c1 = getenv("STRAPS_TC_CONV1");
-  const bool s2d = c1 && strncmp(c1, "s2d", 3) == 0;
-  const bool fused_pool = s2d && c1[3] == 'p';                  // "s2dp": the max pool runs in conv1's epilogue
+  const bool s2d = g_sw.conv1 != 0;
+  const bool fused_pool = g_sw.conv1 == 3;                      // "s2dp": the max pool runs in conv1's epilogue
   if (s2d) {
-    if (run_conv1_s2d(r, x, B, fused_pool ? 3 : c1[3] == '2' ? 2 : 1, st)) return 1;
+    if (run_conv1_s2d(r, x, B, g_sw.conv1, st)) return 1;
   } else {
     pack_input_tc_kernel<<<dim3(IMG, B), 256, 0, st>>>(x, r->c_in, t->xp, t->xp + t->xp_plane);
     STRAPS_LAUNCH_CHECK();
@@ -2973,6 +2997,7 @@ static bool buf_is_conv_input(const straps_regressor* r, int buf) {
 int tc_train_begin(straps_regressor* r, int B, cudaStream_t st) {
   TcState* t = static_cast<TcState*>(r->tc);
   STRAPS_CHECK(t, "tc_train_begin: tensor-core state missing");
+  tc_refresh_switches();
   if (ensure_encode(t)) return 1;
   if (!t->train) {
     TcTrain* tt = new TcTrain();

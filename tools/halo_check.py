@@ -4,7 +4,7 @@ shipped path (also the second CTA-pair kernel, conv_tc2m_kernel).
     python tools/halo_check.py [--out gpurun_out/halo_check.json] [--batch 8] [--time-batch 64] [--iters 20] [--only name,name]
     STRAPS_TC_S2D_PITCH=48 python tools/halo_check.py --only conv1_s2d,conv1_s2d2     (dense pair lines: a separate process)
 
-Both switches are read by the library per launch (csrc/conv_tc.cu: run_tc), so one process runs the shipped configuration and every
+The switches are read by the library once per encoder call (csrc/conv_tc.cu: tc_refresh_switches), so one process runs the shipped configuration and every
 variant on the same weights and input.  The JSON is rewritten after every stage: a variant that hangs or faults still leaves the
 stages before it (and its own name under "reached") on disk.  For every variant: the error of the encoder features and of each
 layer1 / layer2 activation against the shipped path (max-abs / max-abs, the tolerance of tests/test_gpu_regressor.py), a per-pixel
