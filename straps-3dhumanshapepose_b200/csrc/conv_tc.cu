@@ -2284,8 +2284,7 @@ static int launch_conv_tc_pdl(const TcLayerMaps& m, const TcConvParams& p, int n
     attr_once.done(attr_dev);
   }
   const int items = p.n_mtiles * p.n_ntiles;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(items < num_sms ? items : num_sms, 1, 1);
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -2331,8 +2330,7 @@ static int launch_conv_tc_cl(const TcLayerMaps& m, const TcConvParams& p, int nu
   }
   const int items = ((p.n_mtiles + CL - 1) / CL) * p.n_ntiles;
   const int clusters = items < num_sms / CL ? items : num_sms / CL;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(CL * clusters, 1, 1);
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
