@@ -89,3 +89,15 @@ def test_conv1_pair_layout_scheme_matches_conv2d():
     from conftest import REPO
     res = subprocess.run([sys.executable, os.path.join(REPO, 'tools', 'conv1_s2d_emulation.py')], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and 'pair-layout conv1 == conv2d' in res.stdout, res.stdout[-1000:] + res.stderr[-1000:]
+
+
+def test_conv_model_reproduces_the_committed_table():
+    """tools/conv_model.py (byte model + shared-memory port model) runs without a GPU and still prints what profiles/r01_conv_model.txt
+    holds -- the numbers DESIGN.md 4.2 quotes (port model within 7 % on conv1 / layer1, -205 us pairs, -139 us pair-layout conv1)."""
+    import subprocess
+    import sys
+    from conftest import REPO
+    res = subprocess.run([sys.executable, os.path.join(REPO, 'tools', 'conv_model.py')], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr[-1000:]
+    assert res.stdout == open(os.path.join(REPO, 'profiles', 'r01_conv_model.txt')).read()
+    assert 'merged wide MMA -205 us' in res.stdout and '-139 us' in res.stdout
