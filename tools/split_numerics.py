@@ -15,6 +15,8 @@ activations re-split after every layer like the kernel's epilogue.  Error = max-
   lo_e4m3      A_hi.W_hi + A_hi.W_lo + e4m3(A_lo).e4m3(W_hi)             (third term as an fp8 MMA: half the bytes, twice the rate;
                                                                           A_lo with one power-of-two scale per tensor, W_hi per row)
   lo_e5m2      the same with e5m2(A_lo) (fp16's exponent range: no per-tensor scale needed)
+  lo_e5m2_x64  e5m2(A_lo * 2^6) . e4m3(W_hi * 2^-6): STATIC scales only -- implementable without knowing any activation statistics
+  lo_e4m3_s16  e4m3(A_lo * 2^4) . e4m3(W_hi * 2^-6) * 2^2: static worst-case scale for e4m3 (loses the small activations' lo terms)
   both_lo_f8   A_hi.W_hi + [A_hi8 | A_lo8].[W_lo8 ; W_hi8]               (both small terms as ONE fp8 MMA over a doubled K)
 
     python tools/split_numerics.py [--batch 2] [--channels 17]
@@ -73,6 +75,15 @@ def conv(variant, a, w, stride, pad):
         return c(a_hi, w_hi) + c(a_lo, w_hi)
     if variant == 'f16x1':
         return c(a_hi, w_hi)
+    if variant in ('lo_e5m2_x64', 'lo_e4m3_s16'):
+        # STATIC scales only (nothing data dependent, so the producing epilogue can write the fp8 plane directly):
+        #   weights: the row scale already puts max|W_hi| of a row in [2^13, 2^14); W8 = e4m3(W_hi * 2^-6) has its maximum in [128, 256)
+        #   lo_e5m2_x64: A8 = e5m2(A_lo * 2^6)   (|A_lo| <= 16 -> <= 1024; fp16's exponent range)       -> A8 . W8 = A_lo . W_hi exactly scaled
+        #   lo_e4m3_s16: A8 = e4m3(A_lo * 2^4)   (|A_lo| <= 16 -> <= 256)  and the product is rescaled by 2^2
+        w8 = f8(w_hi * 2.0 ** -6, 'e4m3')
+        if variant == 'lo_e5m2_x64':
+            return c(a_hi, w_hi) + c(a_hi, w_lo) + c(f8(a_lo * 64.0, 'e5m2'), w8)
+        return c(a_hi, w_hi) + c(a_hi, w_lo) + c(f8(a_lo * 16.0, 'e4m3'), w8) * 4.0
     if variant in ('lo_e4m3', 'lo_e5m2', 'both_lo_f8'):
         sw = pow2_scale_to(w_hi, 256.0, dim=(1, 2, 3))                     # per output channel, e4m3 max 448
         w8 = f8(w_hi * sw, 'e4m3') / sw
@@ -153,7 +164,7 @@ def main():
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
     print('%-34s %10s %10s %10s %10s %10s   (max-abs error / max-abs reference; bar 1e-4; fp64 accumulation)'
           % ('variant', 'stem', 'layer1.1', 'layer2.1', 'layer4.1', 'features'))
-    for variant in ('f16x3', 'lo_e4m3', 'lo_e5m2', 'both_lo_f8', 'f16x2_w', 'f16x2_a', 'f16x1',
+    for variant in ('f16x3', 'lo_e4m3', 'lo_e5m2', 'lo_e5m2_x64', 'lo_e4m3_s16', 'both_lo_f8', 'f16x2_w', 'f16x2_a', 'f16x1',
                     # the narrow MMA (A_lo.W_hi) dropped on the deepest layers only: "base|layer prefixes:variant for those layers"
                     'f16x3|layer4.1.conv2:f16x2_w', 'f16x3|layer4.1:f16x2_w', 'f16x3|layer4:f16x2_w', 'f16x3|layer3,layer4:f16x2_w',
                     'f16x3|layer4:lo_e5m2', 'f16x3|layer3,layer4:lo_e5m2'):
