@@ -1,6 +1,7 @@
 #!/bin/bash
 # First gpurun call of round 2: every kernel that was written after round 1's GPU budget was spent, against the shipped path.
-#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh'
+#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh'        (about 6-8 minutes of box time: 4 check runs of ~10 s, the parked
+#   tests ~2 min, 8 ncu launch lists of ~30 s)
 # 1. tools/halo_check.py: errors (features + every layer activation) and encoder timings of each variant, one process, JSON flushed after
 #    every stage (a hang leaves the name of the variant under "reached"); each run under its own timeout so that a hung kernel costs
 #    60 s, not the call.  Order: the conv1 pair-layout kernels (biggest predicted gain), the merged CTA-pair kernel, the combinations.
