@@ -113,6 +113,9 @@ int straps_multiclass_to_binary(const float* labels, int64_t n, float* out, void
  * smplx.lbs.batch_rodrigues (augmentation/smpl_augmentation.py:55-58, train/...:190,301,322, predict/predict_3D.py:134):
  * rot_vecs dev [n,3] axis-angle -> R dev [n,3,3]; angle = ||r + 1e-8||. */
 int straps_batch_rodrigues(const float* rot_vecs, int64_t n, float* R, void* stream);
+/* Its gradient (smplx builds this graph for axis-angle input, pose2rot=True: models/smpl_official.py:29 via the
+ * `smpl_model(betas=pred_shape)` call of train/train_synthetic_otf_rendering.py:206): dR dev [n,3,3] -> d_rot_vecs dev [n,3]. */
+int straps_batch_rodrigues_backward(const float* rot_vecs, const float* dR, int64_t n, float* d_rot_vecs, void* stream);
 /* utils/cam_utils.py:40-71 perspective_project_torch: points dev [B,N,3], rotation dev [B,3,3], translation dev [B,3],
  * cam_K dev [B,3,3] -> out dev [B,N,2] = (K ((R p + t) / (R p + t).z))[:2]. */
 int straps_perspective_project(const float* points, const float* rotation, const float* translation, const float* cam_K,

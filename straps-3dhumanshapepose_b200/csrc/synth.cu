@@ -35,6 +35,51 @@ __global__ void batch_rodrigues_kernel(const float* __restrict__ rv, long long n
     }
 }
 
+// Gradient of batch_rodrigues_kernel (smplx builds this graph whenever an axis-angle pose requires grad: the reference's
+// `smpl_model(betas=pred_shape)` call, train/train_synthetic_otf_rendering.py:206, runs with the module's own axis-angle
+// parameters under autograd).  With u = r + 1e-8, t = |u|, a = r / t, K = skew(a), R = I + sin(t) K + (1 - cos(t)) K.K:
+//   G = dL/dK = sin(t) dR + (1 - cos(t)) (dR K^T + K^T dR);   dL/da = (G21 - G12, G02 - G20, G10 - G01)
+//   dL/dt = cos(t) <dR, K> + sin(t) <dR, K.K>;   dL/dr = dL/da / t + (dL/dt - <dL/da, r> / t^2) u / t
+__global__ void batch_rodrigues_bwd_kernel(const float* __restrict__ rv, const float* __restrict__ dR, long long n,
+                                           float* __restrict__ drv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float r[3] = {rv[i * 3 + 0], rv[i * 3 + 1], rv[i * 3 + 2]};
+  const float u[3] = {r[0] + 1e-8f, r[1] + 1e-8f, r[2] + 1e-8f};
+  const float t = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+  const float it = 1.f / t;
+  const float ax = r[0] * it, ay = r[1] * it, az = r[2] * it;
+  const float c = cosf(t), s = sinf(t), omc = 1.f - c;
+  const float K[9] = {0.f, -az, ay, az, 0.f, -ax, -ay, ax, 0.f};
+  float g[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g[k] = dR[i * 9 + k];
+  float KK[9], G[9];
+  float dot_k = 0.f, dot_kk = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      KK[a * 3 + b] = K[a * 3 + 0] * K[0 * 3 + b] + K[a * 3 + 1] * K[1 * 3 + b] + K[a * 3 + 2] * K[2 * 3 + b];
+      dot_k += g[a * 3 + b] * K[a * 3 + b];
+      dot_kk += g[a * 3 + b] * KK[a * 3 + b];
+    }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      // (dR K^T)_ab = sum_m dR_am K_bm ;  (K^T dR)_ab = sum_m K_ma dR_mb
+      const float t1 = g[a * 3 + 0] * K[b * 3 + 0] + g[a * 3 + 1] * K[b * 3 + 1] + g[a * 3 + 2] * K[b * 3 + 2];
+      const float t2 = K[0 * 3 + a] * g[0 * 3 + b] + K[1 * 3 + a] * g[1 * 3 + b] + K[2 * 3 + a] * g[2 * 3 + b];
+      G[a * 3 + b] = s * g[a * 3 + b] + omc * (t1 + t2);
+    }
+  const float da[3] = {G[7] - G[5], G[2] - G[6], G[3] - G[1]};
+  const float dt = c * dot_k + s * dot_kk;
+  const float w = (dt - (da[0] * r[0] + da[1] * r[1] + da[2] * r[2]) * it * it) * it;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) drv[i * 3 + k] = da[k] * it + w * u[k];
+}
+
 // q = R p + t;  q /= q.z (all three components, as the reference does);  out = (K q)[:2]
 __global__ void perspective_kernel(const float* __restrict__ pts, const float* __restrict__ rot, const float* __restrict__ tr,
                                    const float* __restrict__ camK, int B, int N, float* __restrict__ out) {
@@ -72,6 +117,14 @@ extern "C" int straps_batch_rodrigues(const float* rot_vecs, int64_t n, float* R
   STRAPS_CHECK(rot_vecs && R, "straps_batch_rodrigues: null argument");
   if (n <= 0) return 0;
   batch_rodrigues_kernel<<<(unsigned)((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(rot_vecs, n, R);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int straps_batch_rodrigues_backward(const float* rot_vecs, const float* dR, int64_t n, float* d_rot_vecs, void* stream) {
+  STRAPS_CHECK(rot_vecs && dR && d_rot_vecs, "straps_batch_rodrigues_backward: null argument");
+  if (n <= 0) return 0;
+  batch_rodrigues_bwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(rot_vecs, dR, n, d_rot_vecs);
   STRAPS_LAUNCH_CHECK();
   return 0;
 }

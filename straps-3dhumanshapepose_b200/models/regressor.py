@@ -9,7 +9,6 @@ import torch.nn as nn
 from models.resnet import resnet18
 from models.ief_module import IEFModule
 from straps_b200.engine import RegressorEngine, needs_grad
-from straps_b200._lib import StrapsError
 
 
 class SingleInputRegressor(nn.Module):
@@ -31,9 +30,9 @@ class SingleInputRegressor(nn.Module):
         if needs_grad(self):
             # training step (reference train/...:186): batch-statistics BatchNorm, autograd through the library's backward
             params = self._engine.forward_train(input, self.ief_module.iterations)
+        elif self.image_encoder.training:
+            # train mode under torch.no_grad(): batch statistics + running-stat update, no graph (nn.BatchNorm2d semantics)
+            params = self._engine.forward_batch_stats(input, self.ief_module.iterations)
         else:
-            if self.training:
-                raise StrapsError('SingleInputRegressor: a train-mode forward under torch.no_grad() would use batch statistics in '
-                                  'the reference; call .eval() for inference')
             params = self._engine.forward(input, self.ief_module.iterations)
         return params[:, :3], params[:, 3:147], params[:, 147:]

@@ -68,6 +68,8 @@ class ResNet(nn.Module):
         """[B, C, 256, 256] -> [B, 512] (reference resnet.py:201-216)."""
         if needs_grad(self):
             return self._engine.forward_train(x, 0, want='feat')
+        if self.training:
+            return self._engine.forward_batch_stats(x, 0, want='feat')
         return self._engine.encoder_forward(x)
 
 

@@ -18,7 +18,7 @@ import torch.nn as nn
 
 import config
 from straps_b200 import ops
-from straps_b200.autograd import SmplForward
+from straps_b200.autograd import BatchRodrigues, SmplForward
 from straps_b200._lib import StrapsError
 
 ModelOutput = namedtuple('ModelOutput', ['vertices', 'joints', 'full_pose', 'betas', 'global_orient', 'body_pose',
@@ -124,18 +124,28 @@ class SMPL(nn.Module):
         return self._handles[key]
 
     def _forward_with_grad(self, betas, body_pose, global_orient, transl, return_verts, return_full_pose, pose2rot):
-        """Training path (train/train_synthetic_otf_rendering.py:196-199): rotation-matrix input, autograd through
-        the library's backward kernels (csrc/smpl_bwd.cu).  The default parameters the reference never optimises
-        (run_train.py:200) do not receive gradients here."""
-        if pose2rot:
-            raise StrapsError('SMPL.forward: gradients through the axis-angle (pose2rot=True) input are not built; the '
-                              'reference trains with rotation matrices (pose2rot=False)')
+        """Autograd path: the library's forward saves what csrc/smpl_bwd.cu needs; gradients reach every input that requires
+        them -- rotation matrices (train/train_synthetic_otf_rendering.py:196-199), axis-angle poses through the Rodrigues
+        backward kernel (pose2rot=True: `smpl_model(betas=pred_shape)`, train/...:206, runs on the module's own axis-angle
+        parameters), betas and transl -- as smplx's graph would."""
         B = max(betas.shape[0], global_orient.shape[0], body_pose.shape[0])
-        rotmats = torch.cat([global_orient.reshape(-1, 1, 3, 3), body_pose.reshape(-1, 23, 3, 3)], dim=1)
+        if pose2rot:
+            full = torch.cat([global_orient.reshape(-1, 1, 3), body_pose.reshape(-1, 23, 3)], dim=1)      # [B,24,3]
+            if full.requires_grad:
+                rotmats = BatchRodrigues.apply(full.reshape(-1, 3)).view(-1, 24, 3, 3)
+            else:
+                rotmats = ops.batch_rodrigues(full.reshape(-1, 3)).view(-1, 24, 3, 3)
+        else:
+            rotmats = torch.cat([global_orient.reshape(-1, 1, 3, 3), body_pose.reshape(-1, 23, 3, 3)], dim=1)
+        if rotmats.shape[0] != B:
+            rotmats = rotmats.expand(B, -1, -1, -1)
         if betas.shape[0] != B:
             betas = betas.expand(B, -1)
         verts, joints = SmplForward.apply(self._handle(betas.device), rotmats, betas)
-        if transl is not None and transl.shape[0] in (1, B) and (transl is not getattr(self, 'transl', None)):
+        if transl is not None:
+            if transl.shape[0] not in (1, B):
+                raise StrapsError('SMPL: transl has batch %d but the call has batch %d -- construct SMPL(batch_size=%d) '
+                                  '(reference run_train.py:109-110)' % (transl.shape[0], B, B))
             verts = verts + transl.unsqueeze(1)
             joints = joints + transl.unsqueeze(1)
         full_pose = torch.cat([global_orient, body_pose], dim=1) if return_full_pose else None
@@ -152,7 +162,7 @@ class SMPL(nn.Module):
             transl = self.transl
         if not betas.is_cuda:
             raise StrapsError('SMPL.forward needs CUDA tensors: the B200 path has no CPU fallback')
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (betas, body_pose, global_orient)):
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (betas, body_pose, global_orient, transl)):
             return self._forward_with_grad(betas, body_pose, global_orient, transl, return_verts, return_full_pose, pose2rot)
         verts, joints = self._handle(betas.device).forward(global_orient.detach(), body_pose.detach(), betas.detach(),
                                                            transl.detach() if transl is not None else None, pose2rot)

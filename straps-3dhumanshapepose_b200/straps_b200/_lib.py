@@ -31,6 +31,7 @@ SIGNATURES = {
     'straps_joints2d_to_heatmaps': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     'straps_multiclass_to_binary': (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp]),
     'straps_batch_rodrigues': (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp]),
+    'straps_batch_rodrigues_backward': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, _vp]),
     'straps_perspective_project': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     'straps_scale_shift': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     'straps_points_metrics': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]),

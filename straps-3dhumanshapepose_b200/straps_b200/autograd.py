@@ -18,6 +18,21 @@ class Rot6dToRotmat(torch.autograd.Function):
         return ops.rot6d_backward(x6, g).view(ctx.in_shape)
 
 
+class BatchRodrigues(torch.autograd.Function):
+    """axis-angle [n,3] -> rotation matrices [n,3,3] (smplx.lbs.batch_rodrigues), differentiable."""
+
+    @staticmethod
+    def forward(ctx, rot_vecs):
+        r = rot_vecs.contiguous()
+        ctx.save_for_backward(r)
+        return ops.batch_rodrigues(r)
+
+    @staticmethod
+    def backward(ctx, g):
+        (r,) = ctx.saved_tensors
+        return ops.batch_rodrigues_backward(r, g)
+
+
 class OrthographicProject(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points3d, cam):

@@ -114,12 +114,23 @@ class RegressorEngine(object):
         conv_w, bn, fc_w, fc_b = self._train_tensors(x.device)
         flat = list(conv_w) + [q[0] for q in bn] + [q[1] for q in bn] + list(fc_w) + list(fc_b)
         out = _RegressorTrain.apply(self, h, x, iters, want, *flat)
-        if self.encoder is not None:
-            for m in self.encoder.modules():
-                if isinstance(m, torch.nn.BatchNorm2d):
-                    m.num_batches_tracked += 1
-        self._train_steps += 1
+        self._after_batch_stat_forward()
         return out
+
+    def forward_batch_stats(self, x, iters, want='params'):
+        """Train-mode forward WITHOUT autograd (`regressor.train()` under torch.no_grad()): BatchNorm normalises with the batch
+        statistics and updates the running ones, as nn.BatchNorm2d does whenever `.training` is set (reference
+        models/resnet.py:201-216 under nn.Module.train()); nothing is recorded for a backward pass."""
+        h = self._sync(x.device, x.shape[0], self._c_in())
+        feat = h.encoder_train_forward(x, update_running_stats=True, mode=self.conv_mode)
+        self._after_batch_stat_forward()
+        return feat if want == 'feat' else h.ief_forward(feat, iters)
+
+    def _after_batch_stat_forward(self):
+        if self.encoder is not None:
+            # the 20 int64 `num_batches_tracked` counters (nn.BatchNorm2d under .train()) in ONE launch
+            torch._foreach_add_([m.num_batches_tracked for m in self.encoder.modules() if isinstance(m, torch.nn.BatchNorm2d)], 1)
+        self._train_steps += 1
 
 
 class _RegressorTrain(torch.autograd.Function):
@@ -127,6 +138,9 @@ class _RegressorTrain(torch.autograd.Function):
     def forward(ctx, engine, handle, x, iters, want, *params):
         feat = handle.encoder_train_forward(x, update_running_stats=True, mode=engine.conv_mode)
         ctx.handle, ctx.iters, ctx.want = handle, iters, want
+        # the activations and batch statistics the backward needs stay in the handle's workspace, which EVERY later encoder forward
+        # (train or inference) overwrites: remember which forward this graph belongs to
+        ctx.generation = handle.generation
         ctx.conv_shapes = [tuple(p.shape) for p in params[:20]]
         ctx.bn_channels = [p.shape[0] for p in params[20:40]]
         if want == 'feat':
@@ -139,6 +153,11 @@ class _RegressorTrain(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         h = ctx.handle
+        if ctx.generation != h.generation:
+            raise StrapsError('regressor backward: the encoder workspace has been overwritten by a later forward (generation %d, this '
+                              'graph was recorded at %d).  The B200 regressor keeps ONE set of activations per device: call '
+                              'backward() before the next forward of the same regressor (gradient accumulation = backward per '
+                              'micro-batch)' % (h.generation, ctx.generation))
         if ctx.want == 'feat':
             d_feat = g.contiguous()
             dfw = [None] * 3

@@ -112,6 +112,18 @@ def batch_rodrigues(rot_vecs):
     return out
 
 
+def batch_rodrigues_backward(rot_vecs, dR):
+    """Gradient of batch_rodrigues: rot_vecs [n,3], dR [n,3,3] -> [n,3]."""
+    _need_cuda(rot_vecs, 'rot_vecs')
+    _need_cuda(dR, 'grad')
+    r, g = rot_vecs.contiguous(), dR.contiguous()
+    out = torch.empty_like(r)
+    with torch.cuda.device(r.device):
+        check(_lib.lib().straps_batch_rodrigues_backward(_p(r), _p(g), r.shape[0], _p(out), _stream(r.device)),
+              'straps_batch_rodrigues_backward')
+    return out
+
+
 def perspective_project(points, rotation, translation, cam_K):
     """[B,N,3], [B,3,3], [B,3], [B,3,3] -> [B,N,2]  (reference utils/cam_utils.py:40-71)."""
     for n, t in (('points', points), ('rotation', rotation), ('translation', translation), ('cam_K', cam_K)):
@@ -305,6 +317,7 @@ class RegressorHandle(object):
             check(_lib.lib().straps_regressor_create(ctypes.byref(self._h), c_in, max_batch), 'straps_regressor_create')
         self.conv_names = [_lib.lib().straps_regressor_conv_name(self._h, i).decode() for i in range(20)]
         self._keep = None
+        self.generation = 0      # bumped by every call that overwrites the encoder workspace (see engine._RegressorTrain)
 
     def __del__(self):
         try:
@@ -344,6 +357,7 @@ class RegressorHandle(object):
         if x.shape[1:] != (self.c_in, 256, 256):
             raise StrapsError('encoder input must be [B,%d,256,256], got %s' % (self.c_in, tuple(x.shape)))
         feat = torch.empty((B, 512), dtype=torch.float32, device=x.device)
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(_lib.lib().straps_encoder_forward(self._h, _p(x), B, conv_mode_id(mode), _p(feat), _stream(self.device)),
                   'straps_encoder_forward')
@@ -365,6 +379,7 @@ class RegressorHandle(object):
         if x.shape[1:] != (self.c_in, 256, 256):
             raise StrapsError('regressor input must be [B,%d,256,256], got %s' % (self.c_in, tuple(x.shape)))
         params = out if out is not None else torch.empty((B, 157), dtype=torch.float32, device=x.device)
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(_lib.lib().straps_regressor_forward(self._h, _p(x), B, conv_mode_id(mode), iters, None, _p(params),
                                                       _stream(self.device)), 'straps_regressor_forward')
@@ -378,6 +393,7 @@ class RegressorHandle(object):
         if x.shape[1:] != (self.c_in, 256, 256):
             raise StrapsError('encoder input must be [B,%d,256,256], got %s' % (self.c_in, tuple(x.shape)))
         feat = torch.empty((B, 512), dtype=torch.float32, device=x.device)
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(_lib.lib().straps_encoder_train_forward(self._h, _p(x), B, 1 if update_running_stats else 0, conv_mode_id(mode), _p(feat),
                                                           _stream(self.device)), 'straps_encoder_train_forward')

@@ -21,11 +21,16 @@ class FlatBucket(object):
     """
 
     def __init__(self, parameters):
-        seen, plist = set(), []
+        # `all_params` keeps EVERY parameter handed in, frozen ones included, because torch.optim.Adam numbers its state by position
+        # in that list (run_train.py:200-201 passes regressor.parameters() + criterion.parameters(), i.e. also the log-variances of
+        # switched-off losses, requires_grad=False: losses/multi_task_loss.py:47-71).  Only trainable ones live in the flat buffers.
+        seen, self.all_params = set(), []
         for p in parameters:
-            if id(p) not in seen and p.requires_grad:
+            if id(p) not in seen:
                 seen.add(id(p))
-                plist.append(p)
+                self.all_params.append(p)
+        self.index = [i for i, p in enumerate(self.all_params) if p.requires_grad]      # optimiser-state index of plist[k]
+        plist = [self.all_params[i] for i in self.index]
         if not plist:
             raise ValueError('FlatBucket needs at least one parameter that requires grad')
         dev = plist[0].device
@@ -105,22 +110,22 @@ class DataParallelAdam(object):
         b = self.bucket
         state = {}
         if self.step_count > 0:
-            for i, (p, o) in enumerate(zip(b.plist, b.offsets)):
+            for i, p, o in zip(b.index, b.plist, b.offsets):       # frozen parameters have no entry, as in torch.optim.Adam
                 n = p.numel()
                 state[i] = {'step': torch.tensor(float(self.step_count)),
                             'exp_avg': self.exp_avg[o:o + n].view(p.shape).clone(),
                             'exp_avg_sq': self.exp_avg_sq[o:o + n].view(p.shape).clone()}
         group = {'lr': self.lr, 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': 0, 'amsgrad': False, 'maximize': False,
                  'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None, 'decoupled_weight_decay': False,
-                 'params': list(range(len(b.plist)))}
+                 'params': list(range(len(b.all_params)))}
         return {'state': state, 'param_groups': [group]}
 
     def load_state_dict(self, sd):
         b = self.bucket
         groups = sd['param_groups']
-        if len(groups) != 1 or len(groups[0]['params']) != len(b.plist):
+        if len(groups) != 1 or len(groups[0]['params']) != len(b.all_params):
             raise ValueError('optimiser state has %d parameter groups / %d parameters, expected 1 / %d'
-                             % (len(groups), len(groups[0]['params']) if groups else 0, len(b.plist)))
+                             % (len(groups), len(groups[0]['params']) if groups else 0, len(b.all_params)))
         g = groups[0]
         if g.get('weight_decay', 0) or g.get('amsgrad', False):
             raise ValueError('weight decay / amsgrad are not part of the reference configuration (run_train.py:200-201)')
@@ -128,7 +133,12 @@ class DataParallelAdam(object):
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         steps = set()
-        for i, (p, o) in enumerate(zip(b.plist, b.offsets)):
+        trainable = set(b.index)
+        for k in sd['state']:
+            if int(k) not in trainable:
+                raise ValueError('optimiser state holds moments for parameter %s, which is frozen (requires_grad=False) here: the '
+                                 'checkpoint was trained with another `losses_on`' % (k,))
+        for i, p, o in zip(b.index, b.plist, b.offsets):
             st = sd['state'].get(i, sd['state'].get(str(i)))
             if st is None:
                 continue

@@ -3,6 +3,7 @@ import numpy as np
 import torch
 
 from straps_b200 import ops
+from straps_b200._lib import StrapsError
 from straps_b200.autograd import OrthographicProject
 
 
@@ -28,7 +29,12 @@ def perspective_project_torch(points, rotation, translation, cam_K=None, focal_l
     if cam_K is None:
         K = torch.from_numpy(get_intrinsics_matrix(img_wh, img_wh, focal_length).astype(np.float32))
         cam_K = K[None].expand(batch_size, -1, -1).to(points.device)
-    return ops.perspective_project(points.detach(), rotation, translation, cam_K)
+    if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in (points, rotation, translation, cam_K)):
+        # the reference's version is differentiable but only ever runs under torch.no_grad() (train/...:112,141-143); returning a
+        # detached result here would silently zero a projection loss, so say so instead
+        raise StrapsError('perspective_project_torch: the B200 kernel has no backward (the reference only calls it under '
+                          'torch.no_grad() on the target side); detach the inputs or wrap the call in torch.no_grad()')
+    return ops.perspective_project(points, rotation, translation, cam_K)
 
 
 def convert_weak_perspective_to_camera_translation(cam_wp, focal_length, resolution):
