@@ -183,6 +183,16 @@ int straps_ief_forward(straps_regressor_t* r, const float* feat, int batch, int 
 /* Both: x -> params [B,157] (cam = [:, :3], pose6d = [:, 3:147], shape = [:, 147:]). */
 int straps_regressor_forward(straps_regressor_t* r, const float* x, int batch, int conv_mode,
                              int iters, float* feat_or_null, float* params, void* stream);
+/* The same with the proxy representation generated inside the stem's input pack (SURVEY.md 8f row N1 fused with the hot path):
+ * the reference builds x = cat([binary(seg_labels), heatmaps(joints2d)]) in fp32 (utils/label_conversions.py:48-55,90-127,
+ * train/train_synthetic_otf_rendering.py:178-182) and feeds it to the regressor; here x is never materialised.
+ * seg_labels dev [B,256,256] fp32 part labels (non-zero = body), joints2d dev [B,num_joints,2] pixel coordinates,
+ * table dev [(2*half_size)^2] = the reference's truncated Gaussian window (computed by the caller with the reference's own torch
+ * ops so that the values are bit-identical).  num_joints + 1 must equal the handle's input channels.  Tensor-core mode only.
+ * Bit-identical to straps_regressor_forward on the x the reference would have built. */
+int straps_regressor_forward_from_labels(straps_regressor_t* r, const float* seg_labels, const float* joints2d, int num_joints,
+                                         const float* table, int half_size, int batch, int iters, float* feat_or_null,
+                                         float* params, void* stream);
 
 /* ---- training path of the regressor (BASELINE config 3; reference train/...:186,230-233) ----
  * Train-mode forward of the encoder: BatchNorm uses batch statistics (biased variance), and -- when

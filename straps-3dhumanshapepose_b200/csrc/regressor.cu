@@ -472,6 +472,20 @@ extern "C" int straps_regressor_forward(straps_regressor_t* r, const float* x, i
   return straps_ief_forward(r, feat, batch, iters, params, stream);
 }
 
+extern "C" int straps_regressor_forward_from_labels(straps_regressor_t* r, const float* seg_labels, const float* joints2d, int num_joints,
+                                                    const float* table, int half_size, int batch, int iters, float* feat_or_null,
+                                                    float* params, void* stream) {
+  STRAPS_CHECK(r && seg_labels && joints2d && table && params, "straps_regressor_forward_from_labels: null argument");
+  STRAPS_CHECK(r->loaded, "straps_regressor_forward_from_labels: weights not loaded (call straps_regressor_load first)");
+  STRAPS_CHECK(batch >= 1 && batch <= r->max_batch, "straps_regressor_forward_from_labels: batch %d outside [1,%d]", batch, r->max_batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  r->last_mode = STRAPS_CONV_F16X3_TC;
+  if (ensure_packed(r, STRAPS_CONV_F16X3_TC, 1, st)) return 1;
+  float* feat = feat_or_null ? feat_or_null : r->feat_scratch;
+  if (tc_encoder_forward_from_labels(r, seg_labels, joints2d, num_joints, table, half_size, batch, feat, st)) return 1;
+  return straps_ief_forward(r, feat, batch, iters, params, stream);
+}
+
 extern "C" int straps_encoder_read_activation(straps_regressor_t* r, const char* name, int batch, float* out, int64_t* n,
                                               void* stream) {
   STRAPS_CHECK(r && name && out, "straps_encoder_read_activation: null argument");

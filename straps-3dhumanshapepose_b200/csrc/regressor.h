@@ -109,6 +109,8 @@ int tc_create(straps_regressor* r);
 void tc_destroy(straps_regressor* r);
 int tc_pack(straps_regressor* r, const float* const* conv_w, cudaStream_t st);
 int tc_encoder_forward(straps_regressor* r, const float* x, int batch, float* feat, cudaStream_t st);
+int tc_encoder_forward_from_labels(straps_regressor* r, const float* seg, const float* joints2d, int num_joints, const float* table,
+                                   int half_size, int batch, float* feat, cudaStream_t st);
 int tc_read_activation(straps_regressor* r, int buf, int batch, float* out, cudaStream_t st);
 // tensor-core training path (conv_tc.cu): forward convs with un-folded weights and data gradients as flipped-tap convolutions
 int tc_train_begin(straps_regressor* r, int batch, cudaStream_t st);                      // workspace, forward weight pack, tensor maps

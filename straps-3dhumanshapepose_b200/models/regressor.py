@@ -36,3 +36,18 @@ class SingleInputRegressor(nn.Module):
         else:
             params = self._engine.forward(input, self.ief_module.iterations)
         return params[:, :3], params[:, 3:147], params[:, 147:]
+
+    def forward_from_labels(self, seg_labels, joints2D, std=4):
+        """B200 extension (inference): part-segmentation labels [B,256,256] + 2-D joints [B,J,2] -> (cam, pose, shape).
+
+        Equals `self(torch.cat([convert_multiclass_to_binary_labels_torch(seg).unsqueeze(1),
+        convert_2Djoints_to_gaussian_heatmaps_torch(joints2D, 256, std)], dim=1))` bit for bit -- the input assembly of
+        reference train/train_synthetic_otf_rendering.py:178-182 -- but the 285 MB fp32 proxy representation is never written: the
+        stem's input pack generates it on the fly, so only the labels and the joints have to reach the device."""
+        from utils.label_conversions import _gaussian_table, _cuda_f32
+        if needs_grad(self) or self.image_encoder.training:
+            raise RuntimeError('forward_from_labels is an inference path: call .eval() and wrap the call in torch.no_grad()')
+        seg = _cuda_f32(seg_labels, 'seg_labels')
+        j2d = _cuda_f32(joints2D, 'joints2D')
+        params = self._engine.forward_from_labels(seg, j2d, _gaussian_table(std, seg.device), 2 * std, self.ief_module.iterations)
+        return params[:, :3], params[:, 3:147], params[:, 147:]

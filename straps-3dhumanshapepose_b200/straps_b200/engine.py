@@ -100,6 +100,10 @@ class RegressorEngine(object):
         h = self._sync(x.device, x.shape[0], self._c_in())
         return h.forward(x, self.conv_mode, iters)
 
+    def forward_from_labels(self, seg_labels, joints2d, table, half_size, iters):
+        h = self._sync(seg_labels.device, seg_labels.shape[0], self._c_in())
+        return h.forward_from_labels(seg_labels, joints2d, table, half_size, iters)
+
     def read_activation(self, name, batch):
         return self._handle.read_activation(name, batch)
 

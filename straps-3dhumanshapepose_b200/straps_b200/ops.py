@@ -385,6 +385,24 @@ class RegressorHandle(object):
                                                       _stream(self.device)), 'straps_regressor_forward')
         return params
 
+    def forward_from_labels(self, seg_labels, joints2d, table, half_size, iters=3, out=None):
+        """seg_labels [B,256,256], joints2d [B,J,2] (J + 1 = input channels) -> params [B,157]; the proxy representation is generated
+        inside the stem's input pack (straps_regressor_forward_from_labels)."""
+        _need_cuda(seg_labels, 'seg_labels')
+        _need_cuda(joints2d, 'joints2D')
+        seg_labels, joints2d = seg_labels.contiguous(), joints2d.contiguous()
+        B, J = seg_labels.shape[0], joints2d.shape[1]
+        if seg_labels.shape[1:] != (256, 256) or joints2d.shape != (B, J, 2) or J + 1 != self.c_in:
+            raise StrapsError('forward_from_labels expects seg_labels [B,256,256] and joints2D [B,%d,2], got %s and %s'
+                              % (self.c_in - 1, tuple(seg_labels.shape), tuple(joints2d.shape)))
+        params = out if out is not None else torch.empty((B, 157), dtype=torch.float32, device=seg_labels.device)
+        self.generation += 1
+        with torch.cuda.device(self.device):
+            check(_lib.lib().straps_regressor_forward_from_labels(self._h, _p(seg_labels), _p(joints2d), J, _p(table), int(half_size), B, iters,
+                                                                  None, _p(params), _stream(self.device)),
+                  'straps_regressor_forward_from_labels')
+        return params
+
     # ---- training path ----
     def encoder_train_forward(self, x, update_running_stats=True, mode=DEFAULT_CONV_MODE):
         _need_cuda(x, 'input')

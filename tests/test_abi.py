@@ -49,13 +49,10 @@ def test_shipped_kernels_carry_tcgen05_and_tma_sass():
     counts = sass_summary.summary(_lib.LIB_PATH)
     names = sass_summary.demangle(list(counts))
     by_name = {names[k].replace('(int)', '').replace('(bool)', '').split('(')[0].replace('void ', ''): v for k, v in counts.items()}
-    for bn in (64, 128):
-        # <BN, MT = 1, CL = 1, BK = 64, EPW = 4, every later switch off>: the instantiations the default path launches
-        shipped = [k for k in by_name if re.fullmatch(r'straps::conv_tc_kernel<%d, 1, 1, 64, 4(, 0)*>' % bn, k)]
-        assert len(shipped) == 1, (bn, sorted(k for k in by_name if 'conv_tc_kernel<' in k))
-        shipped = shipped[0]
+    for shipped in ('straps::conv_tc_kernel<64>', 'straps::conv_tc_kernel<128>', 'straps::conv1_s2d_kernel<1>', 'straps::conv1_s2d_kernel<0>',
+                    'straps::wgrad_tc_kernel<64>', 'straps::wgrad_tc_kernel<128>'):
+        assert shipped in by_name, (shipped, sorted(k for k in by_name if 'conv' in k or 'wgrad' in k))
         c = by_name[shipped]
-        assert c['UTCHMMA'] >= 8 and c['UTMALDG'] >= 4 and c['LDTM'] >= 2 and c['UTCBAR'] >= 2 and c['SYNCS'] >= 4, (shipped, dict(c))
-        assert c['ACQBULK'] == 0, shipped                      # the programmatic-dependent-launch wait is only in the PDL instantiations
+        assert c['UTCHMMA'] >= 8 and c['UTMALDG'] >= 3 and c['LDTM'] >= 2 and c['UTCBAR'] >= 2 and c['SYNCS'] >= 4, (shipped, dict(c))
     assert any(k.startswith('straps::lbs_kernel<') and v['UBLKCP'] > 0 for k, v in by_name.items())
     assert by_name['straps::ief_kernel']['UBLKCP'] > 0

@@ -7,7 +7,7 @@ Replayed exactly as the device code does it:
   producer                box {PITCH, 131 pairs} of padded row 2 oh + kh  ->  131 shared-memory lines of 64 elements
   MMA issuer              K step j = 0..10 of filter row kh: A = lines [j // 3, j // 3 + 128), elements [(j % 3) * 16, +16);
                           W = wrow[:, kh * 192 + 16 j : +16]   (weight chunk j // 4, byte offset (j % 4) * 32)
-and compared with torch's conv2d.  Also checks the shared-memory rotation of the PITCH = 64 pack kernel (write index -> read index).
+and compared with torch's conv2d; the fused max-pool epilogue is replayed per CTA as well.
 
     python tools/conv1_s2d_emulation.py      -> prints the max error; exits non-zero on a mismatch
 """
@@ -58,54 +58,41 @@ def conv1_s2d(x, w, pitch=64):
     return np.transpose(out, (0, 3, 1, 2))
 
 
-def check_pack_rotation():
-    """pack_input_s2d_kernel<64>: word `l` of pair `q` is written at q*32 + (((l>>2)+q)&7)*4 + (l&3); 16-byte unit i of the row is read
-    from (i & ~7) + (((i & 7) + (i >> 3)) & 7).  The composition must be the identity on the row."""
-    words = XS_PAIRS * 32
-    smem = np.full(words, -1, dtype=np.int64)
-    for q in range(XS_PAIRS):
-        for l in range(32):
-            smem[q * 32 + ((((l >> 2) + q) & 7) << 2) + (l & 3)] = q * 32 + l
-    assert (smem >= 0).all()
-    out = np.empty(words, dtype=np.int64)
-    for i in range(words // 4):
-        si = (i & ~7) + (((i & 7) + (i >> 3)) & 7)
-        out[4 * i:4 * i + 4] = smem[4 * si:4 * si + 4]
-    return bool((out == np.arange(words)).all())
-
-
 def check_fused_pool(grid=148, B=3):
-    """The POOL epilogue (STRAPS_TC_CONV1=s2dp) replayed per CTA: contiguous item ranges with the item above recomputed for its carry,
-    even lanes combining lanes -1 / +1 (pixel -1 = padding), carry = horizontally pooled odd conv row -> must equal max_pool2d(3, 2, 1)."""
+    """The POOL epilogue of conv1_s2d_kernel replayed per CTA: contiguous even-aligned ranges of conv rows with the odd row above
+    recomputed for its carry; even lanes combine lanes -1 / +1 (pixel -1 = padding); an even row joins the running vertical maximum,
+    an odd row completes pooled row (oh - 1) / 2 and becomes the row above of the next one -> must equal max_pool2d(3, 2, 1)."""
     rng = np.random.RandomState(1)
     y = np.maximum(rng.normal(0, 1, (B, 128, 128, 4)), 0)                      # relu(bn(conv1)) rows, NHWC
-    n_items = B * 64
-    per = -(-n_items // grid)
+    n_rows = B * 128
+    per = -(-n_rows // grid)
+    per += per & 1
     out = np.full((B, 64, 64, 4), np.nan)
     stored = 0
+
+    def hpool(v):                                                             # lanes 2j: max(v[2j-1], v[2j], v[2j+1])
+        up = np.vstack([np.full((1, v.shape[1]), -np.inf), v[:-1]])
+        dn = np.vstack([v[1:], np.full((1, v.shape[1]), -np.inf)])
+        return np.maximum(np.maximum(up, v), dn)[0::2]
     for cta in range(grid):
         first = cta * per
-        it1 = min(first + per, n_items)
-        it0 = first - (1 if (first & 63) != 0 and first < it1 else 0)
-        carry = np.full((64, 4), -np.inf)
+        it1 = min(first + per, n_rows)
+        it0 = first - (1 if (first & 127) != 0 and first < it1 else 0)
+        vmax = np.full((64, 4), -np.inf)
         for item in range(it0, it1):
-            b, pr = item >> 6, item & 63
-            y0, y1 = y[b, 2 * pr], y[b, 2 * pr + 1]
-            m = np.maximum(y0, y1)
-
-            def hpool(v):                                                     # lanes 2j: max(v[2j-1], v[2j], v[2j+1])
-                up = np.vstack([np.full((1, v.shape[1]), -np.inf), v[:-1]])
-                dn = np.vstack([v[1:], np.full((1, v.shape[1]), -np.inf)])
-                return np.maximum(np.maximum(up, v), dn)[0::2]
-            hm, h1 = hpool(m), hpool(y1)
-            o = hm if pr == 0 else np.maximum(hm, carry)
-            carry = h1
-            if item >= first:
-                assert np.isnan(out[b, pr]).all()
-                out[b, pr] = o
-                stored += 1
+            b, oh = item >> 7, item & 127
+            h = hpool(y[b, oh])
+            if oh & 1:
+                o = np.maximum(vmax, h)
+                vmax = h
+                if item >= first:
+                    assert np.isnan(out[b, oh >> 1]).all()
+                    out[b, oh >> 1] = o
+                    stored += 1
+            else:
+                vmax = h if oh == 0 else np.maximum(vmax, h)
     ref = F.max_pool2d(torch.from_numpy(np.transpose(y, (0, 3, 1, 2))), 3, 2, 1).numpy()
-    return stored == n_items and bool(np.array_equal(np.transpose(out, (0, 3, 1, 2)), ref))
+    return stored == B * 64 and bool(np.array_equal(np.transpose(out, (0, 3, 1, 2)), ref))
 
 
 def main():
@@ -119,14 +106,12 @@ def main():
         err = float(np.abs(got - ref).max())
         worst = max(worst, err)
         print('C=%d pitch=%d: max abs error %.2e (output %s)' % (C, pitch, err, got.shape))
-    rot = check_pack_rotation()
-    print('shared-memory rotation of the PITCH = 64 pack kernel is its own inverse:', rot)
-    a_now, w_now, a_new, w_new = 21 * 2 * 128 * 128, 21 * 2 * 64 * 128, 7 * 2 * LINES * 128, 21 * 128 * 128
-    print('bytes per output row: A %d -> %d KB, W %d -> %d KB (%d with two rows per item); TMA operations 84 -> 35'
-          % (a_now // 1024, a_new // 1024, w_now // 1024, w_new // 1024, w_new // 2048))
-    pool = check_fused_pool() and check_fused_pool(grid=148, B=64 // 8) and check_fused_pool(grid=5, B=1)
-    print('fused max-pool epilogue (contiguous item ranges + carried odd row) == max_pool2d(3, 2, 1):', pool)
-    if worst > 1e-9 or not rot or not pool:
+    a_now, w_now, a_new, w_new = 21 * 2 * 128 * 128, 21 * 2 * 64 * 128, 7 * 2 * LINES * 96, 21 * 128 * 128
+    print('bytes per output row: A %d -> %d KB, W %d -> %d KB; TMA operations 84 -> 35'
+          % (a_now // 1024, a_new // 1024, w_now // 1024, w_new // 1024))
+    pool = check_fused_pool() and check_fused_pool(grid=148, B=64 // 8) and check_fused_pool(grid=5, B=1) and check_fused_pool(grid=148, B=1)
+    print('fused max-pool epilogue (contiguous even-aligned row ranges + running vertical maximum) == max_pool2d(3, 2, 1):', pool)
+    if worst > 1e-9 or not pool:
         print('MISMATCH')
         sys.exit(1)
     print('pair-layout conv1 == conv2d (max abs error %.2e)' % worst)

@@ -1,6 +1,7 @@
 """Per-layer error report of the encoder (both conv modes) against the CPU oracle -- a debugging aid.
 Usage: python tools/diag_encoder.py [mode ...]    (run on a GPU box; prints one line per activation)"""
 import os
+os.environ.setdefault('STRAPS_TC_CONV1', 's2d')   # these diagnostics read the stem tensor, which the default fused-pool stem never writes
 import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

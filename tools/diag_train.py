@@ -1,5 +1,6 @@
 """Per-tensor gradient error report of the encoder training path against the CPU oracle's autograd (debugging aid)."""
 import os
+os.environ.setdefault('STRAPS_TC_CONV1', 's2d')   # these diagnostics read the stem tensor, which the default fused-pool stem never writes
 import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
