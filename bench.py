@@ -15,6 +15,9 @@ Prints ONE JSON line (rank 0).  Keys follow the driver contract:
              inside the timed region
   roofline   tensor-pipe roofline of the convolution stack (algorithmic FLOPs / measured time / measured bf16 peak)
   cpu_baseline  the oracle (CPU restatement of the reference path) timed on this box's host cores, bounded sample
+  train      BASELINE config 3 (N=1) / config 4 (N>1): the full training step -- forward, multi-task loss, backward, ONE NCCL all-reduce
+             of the flat gradient bucket, fused Adam -- in the shipped tensor-core mode, device-timed, max over ranks
+  lbs_sweep  BASELINE config 5 (N=1 only): the LBS kernels alone at B = 1 .. 4096, achieved GB/s of the algorithmic bytes vs measured HBM peak
 """
 import argparse
 import json
@@ -45,19 +48,66 @@ def algorithmic_mflop(c):
 
 
 def conv_traffic(batch, channels):
-    """DRAM bytes per conv_tc_kernel launch from the committed `ncu --set full` capture of this command (B=64, C=17 only)."""
-    p = os.path.join(REPO, 'profiles', 'r01_conv_traffic.json')
-    if batch == 64 and channels == 17 and os.path.exists(p):
-        return json.load(open(p))['dram_bytes_per_launch']
+    """DRAM bytes per convolution-kernel launch from the committed `ncu --set full` capture of this command (B=64, C=17 only);
+    regenerated whenever the convolution path changes (profiles/r02_conv_traffic.json, else null)."""
+    d = conv_traffic_r02()
+    if batch == 64 and channels == 17 and d is not None:
+        return d['dram_bytes_per_launch']
     return None
 
 
 def measured_peaks():
+    """(bf16 TFLOP/s, HBM GB/s, provenance).  The timed region is tens of milliseconds at maximum clocks, i.e. burst conditions, so the
+    tensor roofline is taken against the BURST cuBLAS figure of MEASURED_PEAKS.json (round-1 review), not the sustained one."""
     p = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1590.0)), d.get('hbm_gbs', 6650.0), 'measured'
-    return 1590.0, 6650.0, 'fallback'
+        return d.get('bf16_tflops', 1590.0), d.get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json: burst cuBLAS bf16, copy bandwidth)'
+    return 1590.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def conv_traffic_r02():
+    p = os.path.join(REPO, 'profiles', 'r02_conv_traffic.json')
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
+def workload_config(batch, channels, n_gpus, conv_mode):
+    """The same dict in both arms (the driver compares them)."""
+    return {'workload': 'encoder+3xIEF+rot6d+SMPL fwd, inference, B=%d per GPU, 256x256x%d (BASELINE configs[1])' % (batch, channels),
+            'global_batch': n_gpus * batch, 'batch_per_gpu': batch, 'channels': channels, 'parallelism': 'dp%d replicas, no collective' % n_gpus,
+            'l2': 'inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush'}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore the pinned host buffers it allocates next: first touch) to the NUMA node the GPU hangs off.
+    Round 1's e2e curve collapsed at 4-8 GPUs because every rank's 285 MB/step H2D copy read host memory of whichever node the
+    allocation happened to land on.  Best effort: returns what was done for the JSON line."""
+    info = {'bound': False}
+    try:
+        prop = torch.cuda.get_device_properties(index)
+        bus = '%04x:%02x:%02x.0' % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
+        info.update(pci=bus, node=node)
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus))
+        try:                                   # also prefer the node for page allocation (set_mempolicy(MPOL_PREFERRED)); x86-64 syscall 238
+            import ctypes
+            mask = ctypes.c_ulong(1 << node)
+            rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+            info['mempolicy'] = 'preferred' if rc == 0 else 'errno %d' % ctypes.get_errno()
+        except Exception as e:                 # noqa: BLE001
+            info['mempolicy'] = 'unavailable (%s)' % type(e).__name__
+    except Exception as e:                     # noqa: BLE001 -- sysfs layout differs, containers hide it: the run goes on unbound
+        info['error'] = '%s: %s' % (type(e).__name__, str(e)[:80])
+    return info
 
 
 class ClockSampler(object):
@@ -136,8 +186,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': bps, 'unit': 'bodies/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'encoder+3xIEF+rot6d+SMPL fwd, inference, 256x256x%d' % args.channels,
-                       'batch_per_step': sample, 'l2': 'n/a (CPU)'},
+            'config': workload_config(args.batch, args.channels, args.gpus, args.conv_mode),
             'cpu_baseline': {'value': bps, 'unit': 'bodies/s', 'cores': cores, 'kind': 'port',
                              'sample': 'median of %d steps of one B=%d batch (oracle = CPU PyTorch restatement of the '
                                        'reference path, all host threads)' % (max(1, args.steps), sample)},
@@ -149,6 +198,138 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+LBS_CONST_BYTES, LBS_BODY_BYTES = 20587320, 84664      # algorithmic bytes of one LBS launch = constants + per body
+
+
+def lbs_sweep(dev, batches, peak_hbm):
+    """BASELINE config 5: the LBS kernels alone (SMPL.forward with rotation matrices), device time from CUDA-graph replays with the L2
+    flushed before every launch (a graph of the flushes alone is subtracted), achieved GB/s of the algorithmic bytes."""
+    import config
+    from models.smpl_official import SMPL
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)          # 256 MB > 126 MB L2
+    rows = []
+    for B in batches:
+        smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(dev)
+        rng = np.random.RandomState(B)
+        betas = torch.from_numpy(rng.normal(0, 1, (B, 10)).astype(np.float32)).to(dev)
+        R = rot6d_to_rotmat(torch.from_numpy(rng.normal(0, 1, (B, 144)).astype(np.float32)).to(dev)).view(B, 24, 3, 3)
+        go, bp = R[:, :1], R[:, 1:]
+        K = 10
+
+        def timed_graph(with_fwd, with_flush):
+            g = torch.cuda.CUDAGraph()
+            st = torch.cuda.Stream(device=dev)
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st), torch.no_grad():
+                for _ in range(2):
+                    smpl(body_pose=bp, global_orient=go, betas=betas, pose2rot=False)
+                with torch.cuda.graph(g, stream=st):
+                    for _ in range(K):
+                        if with_flush:
+                            flush.zero_()
+                        if with_fwd:
+                            smpl(body_pose=bp, global_orient=go, betas=betas, pose2rot=False)
+            torch.cuda.current_stream(dev).wait_stream(st)
+            g.replay()
+            torch.cuda.synchronize(dev)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(3):
+                g.replay()
+            t1.record()
+            torch.cuda.synchronize(dev)
+            return t0.elapsed_time(t1) / (3 * K)
+        flush_ms = timed_graph(False, True)
+        cold_ms = max(timed_graph(True, True) - flush_ms, 1e-6)
+        warm_ms = timed_graph(True, False)
+        nbytes = LBS_CONST_BYTES + LBS_BODY_BYTES * B
+        rows.append({'batch': B, 'us_cold_l2': cold_ms * 1e3, 'us_back_to_back': warm_ms * 1e3, 'bodies_per_s': B / (warm_ms * 1e-3),
+                     'algorithmic_bytes': nbytes, 'achieved_gbs': nbytes / (cold_ms * 1e-3) / 1e9,
+                     'frac': nbytes / (cold_ms * 1e-3) / 1e9 / peak_hbm})
+        del smpl
+    return {'config': 'BASELINE configs[4]: SMPL LBS-only (lbs kernels + joints kernel), rotation-matrix input, L2 flushed between launches',
+            'bound': 'hbm', 'peak': peak_hbm, 'unit': 'GB/s', 'rows': rows}
+
+
+def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_over_ranks):
+    """BASELINE config 3 (world 1) / config 4 (world > 1): reference train/train_synthetic_otf_rendering.py:186-233 without the renderer --
+    regressor.train() forward, rot6d, SMPL, projection, five-term multi-task loss, backward, ONE all-reduce (NCCL) of the flat fp32
+    gradient bucket, fused Adam (run_train.py:200-201) -- on device-resident synthetic inputs and targets."""
+    import config
+    from models.regressor import SingleInputRegressor
+    from models.smpl_official import SMPL
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    from utils.cam_utils import orthographic_project_torch
+    from utils.joints2d_utils import check_joints2d_visibility_torch
+    from losses.multi_task_loss import HomoscedasticUncertaintyWeightedMultiTaskLoss as Loss
+    from straps_b200.parallel import DataParallelAdam
+    from straps_b200 import _lib
+    tasks = ['verts', 'joints2D', 'joints3D', 'pose_params', 'shape_params']
+    weights = {'verts': 1.0, 'joints2D': 0.1, 'pose_params': 0.1, 'shape_params': 0.1, 'joints3D': 1.0}      # run_train.py:53-54
+    torch.manual_seed(1)
+    reg = SingleInputRegressor(C, 18, 3, conv_mode=conv_mode).to(dev).train()
+    crit = Loss(tasks, init_loss_weights=weights).to(dev)
+    smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(dev)
+    opt = DataParallelAdam(list(reg.parameters()) + list(crit.parameters()), lr=1e-4)
+    rng = np.random.RandomState(500 + rank)
+    with torch.no_grad():                                   # target side (train/...:121-145), once: seeded random pose / shape
+        t_betas = torch.from_numpy(rng.normal(0, 1, (B, 10)).astype(np.float32)).to(dev)
+        t_R = rot6d_to_rotmat(torch.from_numpy(rng.normal(0, 1, (B, 144)).astype(np.float32)).to(dev)).view(B, 24, 3, 3)
+        t_out = smpl(body_pose=t_R[:, 1:], global_orient=t_R[:, :1], betas=t_betas, pose2rot=False)
+        t_j2d = torch.from_numpy(rng.uniform(-20, 276, (B, 17, 2)).astype(np.float32)).to(dev)
+        labels = {'verts': t_out.vertices, 'joints2D': t_j2d,
+                  'joints3D': t_out.joints[:, config.ALL_JOINTS_TO_H36M_MAP, :][:, config.H36M_TO_J14, :].contiguous(),
+                  'shape_params': t_betas, 'pose_params_rot_matrices': t_R,
+                  'vis': check_joints2d_visibility_torch(t_j2d, config.REGRESSOR_IMG_WH)}
+
+    def step():
+        opt.zero_grad()
+        cam, pose, shape = reg(x_dev)
+        R = rot6d_to_rotmat(pose.contiguous()).view(-1, 24, 3, 3)
+        out = smpl(body_pose=R[:, 1:], global_orient=R[:, 0].unsqueeze(1), betas=shape, pose2rot=False)
+        outs = {'verts': out.vertices, 'joints2D': orthographic_project_torch(out.joints[:, config.ALL_JOINTS_TO_COCO_MAP, :], cam),
+                'joints3D': out.joints[:, config.ALL_JOINTS_TO_H36M_MAP, :][:, config.H36M_TO_J14, :], 'shape_params': shape,
+                'pose_params_rot_matrices': R}
+        loss, _ = crit(labels, outs)
+        loss.backward()
+        opt.step()                                          # all-reduce(sum) of the bucket + Adam with 1/world folded in
+        return loss
+    for _ in range(3):
+        loss = step()
+    barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    launches = (_lib.launch_count() - n0) / steps
+    # identical replicas after the updates: every rank's parameter bucket must hash the same
+    same = None
+    if world > 1:
+        import torch.distributed as dist
+        h = opt.bucket.params.double().sum().reshape(1)
+        hs = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        same = bool(all(torch.equal(hs[0], t) for t in hs))
+    flops = 3 * algorithmic_mflop(C) * 1e6 * B             # SURVEY.md 8d: forward + data gradient + weight gradient
+    peak_tf = measured_peaks()[0]
+    out = {'config': 'BASELINE configs[%d]: training step (encoder+IEF+rot6d+SMPL+projection+multi-task loss, no renderer), B=%d per GPU, '
+                     '%d GPU(s), conv mode %s, %s, fused Adam'
+                     % (3 if world > 1 else 2, B, world, conv_mode,
+                        'one NCCL all-reduce of %d fp32 gradients per step' % opt.bucket.numel if world > 1 else 'no collective (1 GPU)'),
+           'ms_per_step': ms, 'value': world * B / (ms * 1e-3), 'unit': 'bodies/s', 'steps': steps, 'global_batch': world * B,
+           'library_launches_per_step': launches, 'final_loss': float(loss),
+           'allreduce_elements': opt.bucket.numel if world > 1 else 0, 'replicas_identical_after_update': same,
+           'algorithmic_tflops_per_gpu': flops / (ms * 1e-3) / 1e12, 'frac_of_bf16_peak': flops / (ms * 1e-3) / 1e12 / peak_tf}
+    del reg, crit, smpl, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -156,6 +337,7 @@ def run_gpu(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bind_to_gpu_numa_node(local) if not args.no_numa_bind else {'bound': False, 'note': '--no-numa-bind'}
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     from straps_b200 import synthetic_assets, synthetic_inputs, _lib
@@ -193,6 +375,13 @@ def run_gpu(args):
             return float(t.item())
         return ms
 
+    def min_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return float(t.item())
+        return v
+
     with torch.no_grad():
         for _ in range(max(3, args.warmup)):
             hot_path(x_dev)
@@ -203,7 +392,6 @@ def run_gpu(args):
             sampler.start()
         n0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        enc_ms = 0.0
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         e0.record()
         for i in range(args.steps):
@@ -252,34 +440,61 @@ def run_gpu(args):
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        # ---- the host->device copy alone, all ranks at once: the ceiling of the fp32-tensor e2e (285 MB per step per rank) ----
+        barrier()
+        e0.record()
+        for i in range(10):
+            stage[i % 2].copy_(x_host, non_blocking=True)
+        e1.record()
+        barrier()
+        h2d_gbs = x_host.numel() * 4 * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        h2d_min, h2d_max = min_over_ranks(h2d_gbs), -min_over_ranks(-h2d_gbs)
+        del stage
 
         # ---- extra: the proxy representation is synthesised ON THE DEVICE from what a caller really has on
-        # the host -- part-segmentation labels and 2-D joints (reference train/...:178-182) -- so only 16.8 MB + 8.7 KB cross PCIe.
+        # the host -- part-segmentation labels and 2-D joints (reference train/...:178-182) -- so only 16.8 MB + 8.7 KB cross PCIe,
+        # and since round 2 it is generated INSIDE the stem's input pack (SingleInputRegressor.forward_from_labels: no fp32 tensor).
         ms_kp = None
-        if C in (17, 18):
-            from utils.label_conversions import convert_2Djoints_to_gaussian_heatmaps_torch, convert_multiclass_to_binary_labels_torch
+        if C in (17, 18) and args.conv_mode == 'f16x3_tc':
             rng = np.random.RandomState(7 + rank)
             seg_host = torch.from_numpy((x_host[:, 0].numpy() * rng.randint(1, 7, (B, 1, 1))).astype(np.float32)).pin_memory()
             j2d_host = torch.from_numpy(rng.uniform(8, 247, (B, C - 1, 2)).astype(np.float32)).pin_memory()
-            seg_dev, j2d_dev = torch.empty_like(seg_host, device=dev), torch.empty_like(j2d_host, device=dev)
+            seg_dev = [torch.empty_like(seg_host, device=dev) for _ in range(2)]
+            j2d_dev = [torch.empty_like(j2d_host, device=dev) for _ in range(2)]
+            for ev_ in free:
+                ev_.record(cur)
 
-            def kp_step():
-                seg_dev.copy_(seg_host, non_blocking=True)
-                j2d_dev.copy_(j2d_host, non_blocking=True)
-                x_in = torch.cat([convert_multiclass_to_binary_labels_torch(seg_dev).unsqueeze(1),
-                                  convert_2Djoints_to_gaussian_heatmaps_torch(j2d_dev, 256)], dim=1)
-                res = hot_path(x_in)
-                for h, d in zip(out_host, res):
+            def kp_step(i):
+                sidx = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[sidx])
+                    seg_dev[sidx].copy_(seg_host, non_blocking=True)
+                    j2d_dev[sidx].copy_(j2d_host, non_blocking=True)
+                    ready[sidx].record(copy_stream)
+                cur.wait_event(ready[sidx])
+                cam, pose, shape = reg.forward_from_labels(seg_dev[sidx], j2d_dev[sidx])
+                free[sidx].record(cur)
+                R = rot6d_to_rotmat(pose.contiguous()).view(-1, 24, 3, 3)
+                out = smpl(body_pose=R[:, 1:], global_orient=R[:, 0].unsqueeze(1), betas=shape, pose2rot=False)
+                for h, d in zip(out_host, (cam, out.vertices, out.joints)):
                     h.copy_(d, non_blocking=True)
-            for _ in range(3):
-                kp_step()
+            for i in range(4):
+                kp_step(i)
             barrier()
             e0.record()
-            for _ in range(args.steps):
-                kp_step()
+            for i in range(args.steps):
+                kp_step(i)
             e1.record()
             barrier()
             ms_kp = max_over_ranks(e0.elapsed_time(e1))
+
+    peak_tf, peak_hbm, peak_kind = measured_peaks()
+    sweep = None
+    if world == 1 and not args.no_lbs_sweep:
+        sweep = lbs_sweep(dev, [1, 8, 64, 256, 1024, 4096], peak_hbm)
+    train = None
+    if args.train_steps > 0:
+        train = train_bench(dev, rank, world, B, C, args.conv_mode, args.train_steps, x_dev, barrier, max_over_ranks)
 
     if rank != 0:
         if world > 1:
@@ -288,37 +503,41 @@ def run_gpu(args):
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
     e2e = world * B / (ms_e2e / args.steps * 1e-3)
-    peak_tf, peak_hbm, peak_kind = measured_peaks()
     flops = algorithmic_mflop(C) * 1e6 * B
     achieved_tf = flops / (enc_ms * 1e-3) / 1e12
     cpu = None
-    if world == 1 or True:
+    if world == 1:
         sample = min(B, args.cpu_sample)
         bps, sec, cores = cpu_path(sample, C, args.cpu_reps, 1)
         cpu = {'value': bps, 'unit': 'bodies/s', 'cores': cores, 'kind': 'port',
                'sample': 'median of %d passes over one B=%d batch of the same workload (oracle = CPU PyTorch '
                          'restatement of the reference path, %d threads)' % (args.cpu_reps, sample, cores)}
+    traffic = conv_traffic_r02() if (B == 64 and C == 17) else None
+    cfg = workload_config(B, C, world, args.conv_mode)
     line = {'metric': METRIC, 'value': value, 'unit': 'bodies/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(3, args.warmup), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'fp16x3 split (fp32-equivalent) convs, fp32 elsewhere' if args.conv_mode == 'f16x3_tc' else 'f32',
-            'data': 'synthetic',
-            'config': {'workload': 'encoder+3xIEF+rot6d+SMPL fwd, inference, B=%d/GPU, 256x256x%d (BASELINE configs[1])' % (B, C),
-                       'global_batch': world * B, 'conv_mode': args.conv_mode, 'parallelism': 'dp%d replicas, no collective' % world,
-                       'l2': 'inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush'},
+            'data': 'synthetic', 'config': cfg, 'conv_mode': args.conv_mode,
             'e2e': {'value': e2e, 'unit': 'bodies/s', 'h2d_bytes_per_step': int(x_host.numel() * 4),
-                    'd2h_bytes_per_step': int(sum(h.numel() for h in out_host) * 4)},
+                    'd2h_bytes_per_step': int(sum(h.numel() for h in out_host) * 4),
+                    'h2d_copy_alone_gbs_per_rank': {'min': h2d_min, 'max': h2d_max,
+                                                    'ceiling_bodies_per_s': world * B * h2d_min * 1e9 / (x_host.numel() * 4)},
+                    'numa': numa},
             'e2e_from_keypoints': None if ms_kp is None else {
                 'value': world * B / (ms_kp / args.steps * 1e-3), 'unit': 'bodies/s',
                 'h2d_bytes_per_step': int(B * 256 * 256 * 4 + B * (C - 1) * 2 * 4), 'd2h_bytes_per_step': int(sum(h.numel() for h in out_host) * 4),
-                'note': 'input synthesised on device from host segmentation labels + 2-D joints (utils/label_conversions drop-in, SURVEY 8f N1)'},
+                'note': 'SingleInputRegressor.forward_from_labels: host segmentation labels + 2-D joints; the proxy representation is generated '
+                        'inside the stem input pack (SURVEY 8f N1), double-buffered like e2e'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': achieved_tf / peak_tf, 'traffic': conv_traffic(B, C), 'peak_kind': peak_kind + ' (sustained cuBLAS bf16)',
-                         'kernel': 'conv_tc_kernel (20 launches/step) + input pack/pools = encoder', 'encoder_ms': enc_ms,
-                         'algorithmic_gflop_per_step': flops / 1e9,
-                         'traffic_unit': 'DRAM bytes per conv_tc_kernel launch (dram__bytes_read+write, mean of the 20 launches of a step)',
-                         'note': 'algorithmic FLOPs (1 pass); the f16x3 mode issues 3 MMA passes'},
-            'cpu_baseline': cpu, 'clocks': clocks, 'torch': torch.__version__}
+                         'frac': achieved_tf / peak_tf,
+                         'traffic': traffic['dram_bytes_per_launch'] if traffic else None, 'peak_kind': peak_kind,
+                         'kernel': 'encoder = pack + conv1_s2d_kernel (stem, max pool fused) + 19 conv_tc_kernel launches + avgpool',
+                         'encoder_ms': enc_ms, 'algorithmic_gflop_per_step': flops / 1e9,
+                         'traffic_unit': 'DRAM bytes per convolution-kernel launch (dram__bytes_read+write, mean over the 20 convolution launches '
+                                         'of a step; profiles/r02_conv_traffic.json)',
+                         'note': 'algorithmic FLOPs (1 pass) over the whole encoder time; the f16x3 mode issues 3 MMA passes, so 0.333 is the cap'},
+            'cpu_baseline': cpu, 'train': train, 'lbs_sweep': sweep, 'clocks': clocks, 'torch': torch.__version__}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -335,6 +554,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-sample', type=int, default=64, help='bodies per CPU-baseline pass')
     ap.add_argument('--cpu-reps', type=int, default=3)
+    ap.add_argument('--train-steps', type=int, default=10, help='timed steps of the training-step arm (0 = skip)')
+    ap.add_argument('--no-lbs-sweep', action='store_true')
+    ap.add_argument('--no-numa-bind', action='store_true', help='leave the process unbound (A/B of the NUMA binding)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -74,3 +74,85 @@ def test_load_rejects_mismatched_state(assets_root):
     sd = torch.optim.Adam(_model(1)[0:1].parameters()).state_dict()
     with pytest.raises(ValueError):
         o.load_state_dict(sd)
+
+
+def _check_against_fixture(ckpt, names):
+    """The rebuilt checkpoint equals the one the UNMODIFIED reference wrote (tests/golden/checkpoint_ref.json, metadata only)."""
+    import json
+    import checkpoint_oracle as CK
+    from conftest import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, 'checkpoint_ref.json')))
+    got = json.loads(json.dumps(CK.metadata(ckpt)))
+    assert names == ref['param_names'] and got['keys'] == ref['keys']
+    assert got['optimiser_param_groups'] == ref['optimiser_param_groups']
+    assert sorted(got['optimiser_state']) == sorted(ref['optimiser_state'])
+
+    def close(a, b, what):
+        assert a['shape'] == b['shape'] and a['dtype'] == b['dtype'], what
+        assert abs(a['abs_sum'] - b['abs_sum']) <= 1e-4 * max(abs(b['abs_sum']), 1e-12), (what, a, b)     # another CPU may round differently
+    for k, v in ref['model_state_dict'].items():
+        close(got['model_state_dict'][k], v, k)
+    for k, v in ref['criterion_state_dict'].items():
+        close(got['criterion_state_dict'][k], v, k)
+    for i, st in ref['optimiser_state'].items():
+        assert got['optimiser_state'][i]['step'] == st['step']
+        close(got['optimiser_state'][i]['exp_avg'], st['exp_avg'], 'exp_avg %s' % i)
+        close(got['optimiser_state'][i]['exp_avg_sq'], st['exp_avg_sq'], 'exp_avg_sq %s' % i)
+    return ref
+
+
+def test_reference_checkpoint_with_frozen_log_variances_resumes(assets_root, additional_dir):
+    """SURVEY.md 8f row N3 for real: a checkpoint in the reference's format -- SingleInputRegressor + optim.Adam(regressor U criterion)
+    + criterion with a SUBSET of losses on (run_train.py:194-209, losses/multi_task_loss.py:47-71), reproduced bit for bit from the
+    reference's own run by oracle/checkpoint_oracle.py -- loads into the drop-in regressor, criterion and DataParallelAdam, and what
+    DataParallelAdam writes back loads into torch.optim.Adam.  (The GPU half, tests/test_gpu_checkpoint.py, also takes the next step.)"""
+    import checkpoint_oracle as CK
+    from models.regressor import SingleInputRegressor
+    from losses.multi_task_loss import HomoscedasticUncertaintyWeightedMultiTaskLoss as Loss
+    from straps_b200.parallel import DataParallelAdam
+    from utils.checkpoint_utils import resume_from_checkpoint, save_checkpoint
+    ckpt, names = CK.build(additional_dir)
+    ref = _check_against_fixture(ckpt, names)
+    path = os.path.join(SCRATCH, 'reference_style_epoch3.tar')
+    os.makedirs(SCRATCH, exist_ok=True)
+    torch.save(ckpt, path)
+
+    reg = SingleInputRegressor(CK.C_IN, 18, 3)
+    crit = Loss(CK.LOSSES_ON, init_loss_weights=None)           # wrong initial log-variances on purpose: the checkpoint restores them
+    params = list(reg.parameters()) + list(crit.parameters())
+    assert [n for n, _ in reg.named_parameters()] + [n for n, _ in crit.named_parameters()] == names
+    opt = DataParallelAdam(params, lr=5.0)
+    assert len(opt.bucket.all_params) == 71 and len(opt.bucket.plist) == 69          # the two frozen log-variances keep their index
+    resume_from_checkpoint(path, reg, opt, crit)
+    assert opt.step_count == CK.STEPS and opt.lr == pytest.approx(CK.LR)
+    osd = ckpt['optimiser_state_dict']
+    for i, p, o in zip(opt.bucket.index, opt.bucket.plist, opt.bucket.offsets):
+        assert torch.equal(opt.exp_avg[o:o + p.numel()].view(p.shape), osd['state'][i]['exp_avg']), names[i]
+        assert torch.equal(opt.exp_avg_sq[o:o + p.numel()].view(p.shape), osd['state'][i]['exp_avg_sq']), names[i]
+    for k, v in ckpt['model_state_dict'].items():
+        assert torch.equal(reg.state_dict()[k], v), k
+    for k, v in ckpt['criterion_state_dict'].items():
+        assert torch.equal(crit.state_dict()[k], v), k
+    frozen = [names.index('joints3D_log_var'), names.index('pose_params_log_var')]
+    assert all(str(i) not in ref['optimiser_state'] for i in frozen)
+
+    # and back: what the drop-in writes is what torch.optim.Adam (i.e. the reference) reads
+    out = os.path.join(SCRATCH, 'b200_written_epoch3.tar')
+    save_checkpoint(out, 3, 2, ckpt['best_epoch_val_metrics'], reg, reg.state_dict(), opt, crit)
+    back = torch.load(out, weights_only=False)
+    assert sorted(back['optimiser_state_dict']['state']) == sorted(osd['state'])
+    assert back['optimiser_state_dict']['param_groups'][0]['params'] == list(range(71))
+    t_opt = torch.optim.Adam([torch.nn.Parameter(p.detach().clone(), requires_grad=p.requires_grad) for p in params], lr=1.0)
+    t_opt.load_state_dict(back['optimiser_state_dict'])
+    assert t_opt.param_groups[0]['lr'] == pytest.approx(CK.LR)
+    for i, st in osd['state'].items():
+        assert torch.equal(t_opt.state[t_opt.param_groups[0]['params'][i]]['exp_avg'], st['exp_avg'])
+    # a checkpoint trained with ANOTHER losses_on must be refused loudly, not silently misplaced
+    crit_all = Loss(['verts', 'joints2D', 'joints3D', 'pose_params', 'shape_params'])
+    reg2 = SingleInputRegressor(CK.C_IN, 18, 3)
+    opt_all = DataParallelAdam(list(reg2.parameters()) + list(crit_all.parameters()))
+    opt_all.load_state_dict(osd)                                  # superset of trainable parameters: fine, missing states stay zero
+    crit_few = Loss(['verts'])
+    opt_few = DataParallelAdam(list(reg2.parameters()) + list(crit_few.parameters()))
+    with pytest.raises(ValueError):
+        opt_few.load_state_dict(osd)
