@@ -4,15 +4,16 @@
 // models/resnet.py:61-77,201-216 in STRAPS_CONV_F16X3_TC mode.
 //
 // Numerics: the north-star bar is 1e-4 relative fp32, which a single TF32 or bf16 pass misses.
-// Every operand is therefore carried as a 2-term fp16 split x = hi + lo (hi = fp16(x), lo = fp16(x - hi): 11 + 11
-// mantissa bits) and each K-block issues three kind::f16 MMAs with fp32 accumulation in TMEM:
+// Every operand is therefore carried as a 2-term fp16 split x = hi + 2^-11 lo (hi = fp16(x), lo = fp16(2^11 (x - hi)): 11 + 11
+// mantissa bits; split_f16 in regressor.h) and each K-block issues three kind::f16 MMAs with fp32 accumulation in TMEM:
 //   A_hi.W_hi + A_hi.W_lo + A_lo.W_hi      (dropped lo.lo term and split residual: ~2^-22 relative).
 // A first version used a bf16 split (8 + 8 bits): 4e-6 error per layer, 5e-5 at the features after 17 layers -- too
 // close to the bar; fp16 has the mantissa and, with the two range guards below, the range:
 //   * weights (BatchNorm scale folded in) are multiplied per output channel by a power of two that puts the row
 //     maximum in [2^13, 2^14) so that hi AND lo stay fp16-normal; the exact inverse is applied in the epilogue;
-//   * activations are clamped to +-65504 before the split (post-BatchNorm ResNet activations are O(1..100)); small
-//     activations make `lo` fp16-subnormal, which costs at most 3e-8 ABSOLUTE error.
+//   * activations are clamped to +-65504 before the split (post-BatchNorm ResNet activations are O(1..100)); the low term is
+//     stored scaled by 2^11, so it is fp16-normal wherever the high term is (tests/test_gpu_numeric_range.py drives layers
+//     down to 1e-3 and up to 6e4; an unscaled lo went subnormal below 0.125 and cost 3e-8 ABSOLUTE).
 //
 // HBM layout
 //   activations   NHWC, two fp16 planes per tensor: [hi: B,H,W,C][lo: B,H,W,C]  (same bytes as fp32)
@@ -276,10 +277,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
-          y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
-          y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
-          y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
-          y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+          y[q * 4 + 0] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 0]), LO_UNSCALE, __uint_as_float(v[q * 4 + 0])), u4.x, s4.x);
+          y[q * 4 + 1] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 1]), LO_UNSCALE, __uint_as_float(v[q * 4 + 1])), u4.y, s4.y);
+          y[q * 4 + 2] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 2]), LO_UNSCALE, __uint_as_float(v[q * 4 + 2])), u4.z, s4.z);
+          y[q * 4 + 3] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 3]), LO_UNSCALE, __uint_as_float(v[q * 4 + 3])), u4.w, s4.w);
         }
         if (valid && TC_EPI_IO(p)) {
           if (p.res_hi) {
@@ -288,8 +289,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               const uint32_t hw[4] = {rh[q].x, rh[q].y, rh[q].z, rh[q].w}, lw[4] = {rl[q].x, rl[q].y, rl[q].z, rl[q].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                y[q * 8 + e * 2 + 0] += f16lo_to_f(hw[e]) + f16lo_to_f(lw[e]);
-                y[q * 8 + e * 2 + 1] += f16hi_to_f(hw[e]) + f16hi_to_f(lw[e]);
+                y[q * 8 + e * 2 + 0] += fmaf(f16lo_to_f(lw[e]), LO_UNSCALE, f16lo_to_f(hw[e]));
+                y[q * 8 + e * 2 + 1] += fmaf(f16hi_to_f(lw[e]), LO_UNSCALE, f16hi_to_f(hw[e]));
               }
             }
           }
@@ -548,10 +549,10 @@ conv1_s2d_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 s4 = __ldg(sh4 + q), u4 = __ldg(us4 + q);
-        y[q * 4 + 0] = fmaf(__uint_as_float(v[q * 4 + 0]) + __uint_as_float(vl[q * 4 + 0]), u4.x, s4.x);
-        y[q * 4 + 1] = fmaf(__uint_as_float(v[q * 4 + 1]) + __uint_as_float(vl[q * 4 + 1]), u4.y, s4.y);
-        y[q * 4 + 2] = fmaf(__uint_as_float(v[q * 4 + 2]) + __uint_as_float(vl[q * 4 + 2]), u4.z, s4.z);
-        y[q * 4 + 3] = fmaf(__uint_as_float(v[q * 4 + 3]) + __uint_as_float(vl[q * 4 + 3]), u4.w, s4.w);
+        y[q * 4 + 0] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 0]), LO_UNSCALE, __uint_as_float(v[q * 4 + 0])), u4.x, s4.x);
+        y[q * 4 + 1] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 1]), LO_UNSCALE, __uint_as_float(v[q * 4 + 1])), u4.y, s4.y);
+        y[q * 4 + 2] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 2]), LO_UNSCALE, __uint_as_float(v[q * 4 + 2])), u4.z, s4.z);
+        y[q * 4 + 3] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 3]), LO_UNSCALE, __uint_as_float(v[q * 4 + 3])), u4.w, s4.w);
       }
       if (p.relu) {
 #pragma unroll
@@ -874,7 +875,7 @@ __global__ void split_to_nchw_kernel(const __half* __restrict__ hi, const __half
   const int c = t % C;
   const size_t b = t / C;
   const size_t s = ((b * H + h) * W + w) * C + c;
-  x[i] = __half2float(hi[s]) + __half2float(lo[s]);
+  x[i] = unsplit_f16(hi[s], lo[s]);
 }
 __global__ void f32_nhwc_to_nchw_kernel(const float* __restrict__ y, int C, int H, int W, float* __restrict__ x, size_t total) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1516,7 +1517,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            atomicAdd(dst + (size_t)(c0 + j) * p.k_eff, __uint_as_float(v[j]) + __uint_as_float(vl[j]));
+            atomicAdd(dst + (size_t)(c0 + j) * p.k_eff, fmaf(__uint_as_float(vl[j]), LO_UNSCALE, __uint_as_float(v[j])));
         }
       }
       tc_fence_before();
@@ -1795,7 +1796,7 @@ __global__ void unsplit_input_kernel(const __half* __restrict__ hi, const __half
   float v = 0.f;
   if (c < XP_C) {
     const size_t s = ((b * XP_H + h + 3) * XP_W + w + 3) * XP_C + c;
-    v = __half2float(hi[s]) + __half2float(lo[s]);
+    v = unsplit_f16(hi[s], lo[s]);
   }
   out[i] = v;
 }

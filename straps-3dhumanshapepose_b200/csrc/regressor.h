@@ -49,11 +49,20 @@ struct ConvArgs {
   int transposed;      // 1 = data-gradient gather (rows are input pixels, `in` is dY)
 };
 
-// 2-term fp16 split used by the tensor-core path (conv_tc.cu): x = hi + lo
+// 2-term fp16 split used by the tensor-core path (conv_tc.cu): x = hi + lo * 2^-11.
+// The low term is stored SCALED by 2^11 (since round 2): |x - hi| <= 2^-11 |x|, so lo has the magnitude of x instead of sitting 11
+// binades lower -- it stays fp16-NORMAL wherever hi is (a plain lo = fp16(x - hi) goes subnormal for |x| < 0.125 and costs 3e-8
+// ABSOLUTE, i.e. 3e-5 relative on a layer whose activations peak at 1e-3: round-1 review) and cannot overflow.  Every lo plane
+// (activations, weights, gradients) follows this convention, so both cross terms A_hi.W_lo and A_lo.W_hi carry the same factor 2^11
+// and the epilogues combine the two accumulators as acc_hi + 2^-11 acc_lo.  For data that was normal before, results are unchanged
+// bit for bit (power-of-two scalings are exact).
+constexpr float LO_SCALE = 2048.f, LO_UNSCALE = 1.f / 2048.f;
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
-  lo = __float2half_rn(v - __half2float(hi));
+  lo = __float2half_rn(fminf(fmaxf((v - __half2float(hi)) * LO_SCALE, -65504.f), 65504.f));
 }
+// x back from its two halves
+__device__ __forceinline__ float unsplit_f16(__half hi, __half lo) { return fmaf(__half2float(lo), LO_UNSCALE, __half2float(hi)); }
 __device__ __forceinline__ uint32_t pack_f16(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }

@@ -42,15 +42,17 @@ def _perturbed(sdg, seed=5, rel=NOISE_REL):
     return out
 
 
-def _check_grads(got, ref, noise, what):
+def _check_grads(got, ref, noise, what, gtol=GTOL):
     """got / ref: dict name -> tensor; noise: list of dicts = the oracle's gradients under independent 3e-7 perturbations."""
-    bad = {}
+    bad, worst = {}, (0.0, None)
     for k, r in ref.items():
         floor = max([rel_err(n[k].numpy(), r.numpy()) for n in noise]) if noise else 0.0
-        tol = max(GTOL, NOISE_FACTOR * floor)
+        tol = max(gtol, NOISE_FACTOR * floor)
         e = rel_err(got[k], r.numpy())
+        worst = max(worst, (e, k))
         if not e < tol:
             bad[k] = (e, tol)
+    print('%s: worst relative gradient error %.2e (%s)' % (what, worst[0], worst[1]))
     assert not bad, (what, bad)
 
 
@@ -213,14 +215,16 @@ def test_tensor_core_backward_matches_fp32_backward_on_the_same_activations(C, B
     e_32 = rel_err(dw_32[0].cpu().numpy(), truth_32)
     print('tensor-core vs fp32 gradients: worst relative difference over 59 tensors %.2e; conv1.weight vs fp64: tensor-core %.2e, fp32 %.2e'
           % (worst, e_tc, e_32))
-    assert worst < 2e-4, worst      # measured 4e-5 (B=4, 16) and 1.1e-4 (B=64: bn1.bias, a 1M-term sum at the end of the whole chain)
+    # measured 4e-5 (B=4, 16) and 1.1e-4 (B=64: bn1.bias, a 1M-term sum at the end of the whole chain): the small batches are held to
+    # the contract's 1e-4, the bench batch to 2e-4
+    assert worst < (1e-4 if B <= 16 else 2e-4), worst
     assert e_tc < 3e-4 and e_tc < 1.5 * e_32 + 2e-5, (e_tc, e_32)
     with pytest.raises(Exception):      # the tensor-core backward needs the planes of a tensor-core forward
         h.encoder_train_forward(x, update_running_stats=False, mode='fp32_simt')
         h.encoder_backward(g, shapes, chans, mode='f16x3_tc')
 
 
-@pytest.mark.parametrize('B,mode', [(4, 'fp32_simt'), (16, 'fp32_simt'), (64, 'fp32_simt'), (64, 'f16x3_tc')])
+@pytest.mark.parametrize('B,mode', [(4, 'fp32_simt'), (4, 'f16x3_tc'), (16, 'fp32_simt'), (64, 'fp32_simt'), (64, 'f16x3_tc')])
 def test_config3_training_step_gradients(B, mode, assets_root, additional_dir, smpl_oracle):
     """encoder + IEF + rot6d + SMPL + projection + the five-term multi-task loss: every parameter gradient."""
     import config
@@ -292,7 +296,9 @@ def test_config3_training_step_gradients(B, mode, assets_root, additional_dir, s
         for d, (sdn, lvn) in zip(noise, noise_runs):
             d[t + '_log_var'] = lvn[t].grad
     assert len(ref) == 71            # 71 gradient tensors in the bucket
-    _check_grads(got, ref, noise, 'config3 B=%d' % B)
+    # B = 4 with these seeds is flip-free (no ReLU / max-pool decision differs from the oracle's): all 71 tensors are held to the
+    # contract's plain 1e-4 in both convolution modes; the larger batches use the oracle's own noise floor
+    _check_grads(got, ref, noise, 'config3 B=%d %s' % (B, mode), gtol=RTOL if B == 4 else GTOL)
 
 
 def test_fused_adam_matches_torch_adam():
