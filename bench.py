@@ -295,18 +295,30 @@ def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_ov
         loss.backward()
         opt.step()                                          # all-reduce(sum) of the bucket + Adam with 1/world folded in
         return loss
-    for _ in range(3):
-        loss = step()
-    barrier()
-    n0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss = step()
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
-    launches = (_lib.launch_count() - n0) / steps
+    def timed(fn):
+        for _ in range(3):
+            out = fn()
+        barrier()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, (_lib.launch_count() - n0) / steps, out
+    ms_eager, launches, loss = timed(step)
+    # the same step captured as CUDA graph(s) and replayed (straps_b200.graphs.GraphedTrainStep; the all-reduce stays outside the capture)
+    ms_graph, graph_note = None, None
+    try:
+        from straps_b200.graphs import GraphedTrainStep
+        gstep = GraphedTrainStep(step, opt)
+        ms_graph, _, loss = timed(gstep)
+    except Exception as e:                                  # noqa: BLE001 -- the eager figure stands on its own
+        graph_note = '%s: %s' % (type(e).__name__, str(e)[:300])
+        if world > 1:
+            raise                                           # a half-captured rank would dead-lock the others at the next collective
+    ms = ms_graph if ms_graph is not None else ms_eager
     # identical replicas after the updates: every rank's parameter bucket must hash the same
     same = None
     if world > 1:
@@ -322,7 +334,9 @@ def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_ov
                      % (3 if world > 1 else 2, B, world, conv_mode,
                         'one NCCL all-reduce of %d fp32 gradients per step' % opt.bucket.numel if world > 1 else 'no collective (1 GPU)'),
            'ms_per_step': ms, 'value': world * B / (ms * 1e-3), 'unit': 'bodies/s', 'steps': steps, 'global_batch': world * B,
-           'library_launches_per_step': launches, 'final_loss': float(loss),
+           'mode': 'CUDA-graph replay of the whole step (GraphedTrainStep)' if ms_graph is not None else 'eager PyTorch loop',
+           'ms_per_step_eager': ms_eager, 'ms_per_step_graphed': ms_graph, 'graph_note': graph_note,
+           'library_launches_per_step': launches, 'final_loss': float(loss.detach()), 'optimiser_steps': opt.step_count,
            'allreduce_elements': opt.bucket.numel if world > 1 else 0, 'replicas_identical_after_update': same,
            'algorithmic_tflops_per_gpu': flops / (ms * 1e-3) / 1e12, 'frac_of_bf16_peak': flops / (ms * 1e-3) / 1e12 / peak_tf}
     del reg, crit, smpl, opt

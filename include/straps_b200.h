@@ -225,6 +225,11 @@ int straps_ief_backward(straps_regressor_t* r, const float* feat, const float* s
  * multiplied by grad_scale first (1/world_size after the summing all-reduce).  step counts from 1. */
 int straps_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int step,
                      float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* The same step with the step count on the device: *step_counter (dev int64) is incremented first and the bias corrections are
+ * derived from it inside the kernel, so the call can be captured in a CUDA graph and replayed (a host-side `step` would be frozen
+ * into the graph).  Same formula as straps_adam_step(step = the incremented value); beta^t is evaluated on the device. */
+int straps_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_counter,
+                         float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* Fused multi-task loss, forward + backward seeds -- losses/multi_task_loss.py:73-119 (+ utils/joints2d_utils.py:23-33 as the
  * joints2D row mask).  preds / targets / grads: 5 dev pointers each in the order verts, joints2D [rows,2], joints3D, shape_params,

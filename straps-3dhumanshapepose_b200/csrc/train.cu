@@ -43,35 +43,66 @@ struct TrainState {
 // ------------------------------------------------------------------------------------------------
 // BatchNorm kernels (NHWC: channel = fastest index)
 // ------------------------------------------------------------------------------------------------
-// pass 0: sum(x) ; pass 1: sum((x - mean)^2).  grid (chunks, C/64), block 256 = 64 channels x 4 pixel lanes
-__global__ void __launch_bounds__(256) bn_stat_kernel(const float* __restrict__ x, long long npix, int C, const float* __restrict__ mean,
-                                                      double* __restrict__ acc) {
-  __shared__ float red[4][64];
-  const int c = blockIdx.y * 64 + (threadIdx.x & 63), lane4 = threadIdx.x >> 6;
-  const float mu = mean ? mean[c] : 0.f;
-  float s = 0.f;
-  for (long long p = (long long)blockIdx.x * 4 + lane4; p < npix; p += (long long)gridDim.x * 4) {
-    const float v = x[p * C + c] - mu;
-    s += mean ? v * v : v;
+// ONE pass over the pre-BN tensor: per channel S1 = sum(x - pivot), S2 = sum((x - pivot)^2) with pivot = the channel's first element
+// (a sample of the distribution, so |mean - pivot| ~ sigma and S2 - S1^2 / n does not cancel).  Threads read float4 (4 channels) of
+// 4 pixels per iteration, keep fp32 partials over at most 64 elements, fold them into fp64 registers, and the block adds its fp64
+// totals to acc[0..C) / acc[512..512+C) with one atomic per channel.  (Round 1 ran two passes with scalar loads: 2.5 TB/s.)
+// grid (chunks), block 256 = (C / 4 channel quads) x (1024 / C pixel lanes).
+__global__ void __launch_bounds__(256) bn_stat_kernel(const float* __restrict__ x, long long npix, int C, double* __restrict__ acc) {
+  __shared__ double red[2][256][4];
+  const int tq = C >> 2;                       // threads per pixel
+  const int lanes = 256 / tq;                  // pixels per block iteration
+  const int q = threadIdx.x % tq, pl = threadIdx.x / tq;
+  const float4 pv = *reinterpret_cast<const float4*>(x + 4 * q);
+  double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  int pending = 0;
+  const long long stride = (long long)gridDim.x * lanes;
+  for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long pp = p + u * stride;
+      v[u] = (pp < npix) ? *reinterpret_cast<const float4*>(x + pp * C + 4 * q) : pv;      // pivot contributes zero
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float a = v[u].x - pv.x, b = v[u].y - pv.y, c = v[u].z - pv.z, d = v[u].w - pv.w;
+      s1[0] += a; s1[1] += b; s1[2] += c; s1[3] += d;
+      s2[0] = fmaf(a, a, s2[0]); s2[1] = fmaf(b, b, s2[1]); s2[2] = fmaf(c, c, s2[2]); s2[3] = fmaf(d, d, s2[3]);
+    }
+    if (++pending == 16) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { d1[k] += (double)s1[k]; d2[k] += (double)s2[k]; s1[k] = 0.f; s2[k] = 0.f; }
+      pending = 0;
+    }
   }
-  red[lane4][threadIdx.x & 63] = s;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { red[0][threadIdx.x][k] = d1[k] + (double)s1[k]; red[1][threadIdx.x][k] = d2[k] + (double)s2[k]; }
   __syncthreads();
-  if (threadIdx.x < 64) atomicAdd(&acc[c], (double)((red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x])));
+  {                                            // C <= 256: one channel per thread; C = 512 takes two rounds
+    for (int c = threadIdx.x; c < C; c += 256) {
+      double t1 = 0, t2 = 0;
+      for (int l = 0; l < lanes; ++l) { t1 += red[0][l * tq + (c >> 2)][c & 3]; t2 += red[1][l * tq + (c >> 2)][c & 3]; }
+      atomicAdd(&acc[c], t1);
+      atomicAdd(&acc[512 + c], t2);
+    }
+  }
 }
-__global__ void bn_mean_kernel(const double* __restrict__ acc, long long npix, int C, float* __restrict__ mean) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) mean[c] = (float)(acc[c] / (double)npix);
-}
-__global__ void bn_finalize_kernel(const double* __restrict__ acc2, long long npix, int C, const float* __restrict__ mean,
+// mean = pivot + S1 / n;  M2 = S2 - S1^2 / n (fp64);  biased variance normalises, the unbiased one feeds the running estimate
+__global__ void bn_finalize_kernel(const double* __restrict__ acc, const float* __restrict__ x, long long npix, int C, float* __restrict__ mean,
                                    float* __restrict__ invstd, float* __restrict__ rmean, float* __restrict__ rvar, float momentum) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double var = acc2[c] / (double)npix;                       // biased: used for normalisation
-  invstd[c] = (float)(1.0 / sqrt(var + 1e-5));
+  const double s1 = acc[c], s2 = acc[512 + c], n = (double)npix;
+  const double mu = (double)x[c] + s1 / n;
+  double m2 = s2 - s1 * s1 / n;
+  if (m2 < 0) m2 = 0;
+  mean[c] = (float)mu;
+  invstd[c] = (float)(1.0 / sqrt(m2 / n + 1e-5));
   if (rmean) {
-    const double unbiased = acc2[c] / (double)(npix - 1);
-    rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean[c];
-    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mu;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)(m2 / (n - 1.0));
   }
 }
 // y = (x - mean) * invstd * gamma + beta (+ res) (ReLU)
@@ -97,28 +128,46 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
     reinterpret_cast<uint2*>(y_lo)[i] = make_uint2(pack_f16(l[0], l[1]), pack_f16(l[2], l[3]));
   }
 }
-// sums over pixels of dy and dy * xhat, with dy = gout * (act > 0) when act != null.  acc[0..C) = sum dy, acc[C..2C) = sum dy xhat
+// sums over pixels of dy and dy * xhat, with dy = gout * (act > 0) when act != null.  acc[0..C) = sum dy, acc[C..2C) = sum dy xhat.
+// Same thread layout as bn_stat_kernel: float4 (4 channels) x 4 pixels per iteration, block = (C / 4) quads x (1024 / C) pixel lanes.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ gout, const float* __restrict__ act,
                                                             const float* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, long long npix, int C,
                                                             float* __restrict__ acc) {
-  __shared__ float red[2][4][64];
-  const int c = blockIdx.y * 64 + (threadIdx.x & 63), lane4 = threadIdx.x >> 6;
-  const float mu = mean[c], is = invstd[c];
-  float s0 = 0.f, s1 = 0.f;
-  for (long long p = (long long)blockIdx.x * 4 + lane4; p < npix; p += (long long)gridDim.x * 4) {
-    float dy = gout[p * C + c];
-    if (act && !(act[p * C + c] > 0.f)) dy = 0.f;
-    s0 += dy;
-    s1 += dy * (x[p * C + c] - mu) * is;
+  __shared__ float red[2][256][4];
+  const int tq = C >> 2, lanes = 256 / tq;
+  const int q = threadIdx.x % tq, pl = threadIdx.x / tq;
+  const float4 mu = *reinterpret_cast<const float4*>(mean + 4 * q), is = *reinterpret_cast<const float4*>(invstd + 4 * q);
+  float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+  const long long stride = (long long)gridDim.x * lanes;
+  for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += 4 * stride) {
+    float4 dy[4], xv[4], av[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long pp = p + u * stride;
+      const bool in = pp < npix;
+      const size_t o = (size_t)(in ? pp : 0) * C + 4 * q;
+      dy[u] = in ? *reinterpret_cast<const float4*>(gout + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xv[u] = *reinterpret_cast<const float4*>(x + o);
+      av[u] = act ? *reinterpret_cast<const float4*>(act + o) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float d0 = (av[u].x > 0.f) ? dy[u].x : 0.f, d1 = (av[u].y > 0.f) ? dy[u].y : 0.f;
+      const float d2 = (av[u].z > 0.f) ? dy[u].z : 0.f, d3 = (av[u].w > 0.f) ? dy[u].w : 0.f;
+      s0[0] += d0; s0[1] += d1; s0[2] += d2; s0[3] += d3;
+      s1[0] += d0 * (xv[u].x - mu.x) * is.x; s1[1] += d1 * (xv[u].y - mu.y) * is.y;
+      s1[2] += d2 * (xv[u].z - mu.z) * is.z; s1[3] += d3 * (xv[u].w - mu.w) * is.w;
+    }
   }
-  red[0][lane4][threadIdx.x & 63] = s0;
-  red[1][lane4][threadIdx.x & 63] = s1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { red[0][threadIdx.x][k] = s0[k]; red[1][threadIdx.x][k] = s1[k]; }
   __syncthreads();
-  if (threadIdx.x < 64) {
-    const int t = threadIdx.x;
-    atomicAdd(&acc[c], (red[0][0][t] + red[0][1][t]) + (red[0][2][t] + red[0][3][t]));
-    atomicAdd(&acc[C + c], (red[1][0][t] + red[1][1][t]) + (red[1][2][t] + red[1][3][t]));
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int l = 0; l < lanes; ++l) { t0 += red[0][l * tq + (c >> 2)][c & 3]; t1 += red[1][l * tq + (c >> 2)][c & 3]; }
+    atomicAdd(&acc[c], t0);
+    atomicAdd(&acc[C + c], t1);
   }
 }
 // dx = gamma * invstd * (dy - sum_dy/N - xhat * sum_dy_xhat/N);   optionally also writes the masked dy and the max |dx|.
@@ -364,6 +413,29 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// The same update with the step count kept ON THE DEVICE (a captured CUDA graph replays with fixed kernel arguments, so the bias
+// corrections cannot come from the host): adam_tick_kernel advances the counter, adam_dev_kernel derives 1 - beta^t from it.
+__global__ void adam_tick_kernel(long long* __restrict__ step) { *step += 1; }
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, const long long* __restrict__ step, float lr, float b1, float b2, float eps, float gscale) {
+  __shared__ float sbc[2];
+  if (threadIdx.x == 0) {
+    const float t = (float)*step;
+    sbc[0] = 1.f - powf(b1, t);
+    sbc[1] = 1.f - powf(b2, t);
+  }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float bc1 = sbc[0], bc2 = sbc[1];
+  const float gi = g[i] * gscale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
 static int gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C, int ldc, int M, int N, int K, float beta,
                 cudaStream_t st) {
   gemm_kernel<<<dim3(ceil_div(N, 32), ceil_div(M, 32)), 256, 0, st>>>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta);
@@ -456,15 +528,12 @@ static int bn_forward(straps_regressor* r, TrainState* t, int ci, int B, const f
   __half* out_hi = tc ? tc_train_plane(r, out_buf, 0) : nullptr;
   __half* out_lo = tc ? tc_train_plane(r, out_buf, 1) : nullptr;
   const long long npix = (long long)B * c.hout * c.wout;
-  const int chunks = (int)std::min<long long>(1024, (npix + 63) / 64);
+  const int lanes = 1024 / c.cout;                                      // pixels per block iteration of bn_stat_kernel
+  const int chunks = (int)std::max<long long>(1, std::min<long long>(1184, npix / (16LL * lanes)));
   STRAPS_CUDA(cudaMemsetAsync(t->dstat, 0, 1024 * sizeof(double), st));
-  bn_stat_kernel<<<dim3(chunks, c.cout / 64), 256, 0, st>>>(t->raw[ci], npix, c.cout, nullptr, t->dstat);
+  bn_stat_kernel<<<chunks, 256, 0, st>>>(t->raw[ci], npix, c.cout, t->dstat);
   STRAPS_LAUNCH_CHECK();
-  bn_mean_kernel<<<ceil_div(c.cout, 128), 128, 0, st>>>(t->dstat, npix, c.cout, t->mean[ci]);
-  STRAPS_LAUNCH_CHECK();
-  bn_stat_kernel<<<dim3(chunks, c.cout / 64), 256, 0, st>>>(t->raw[ci], npix, c.cout, t->mean[ci], t->dstat + 512);
-  STRAPS_LAUNCH_CHECK();
-  bn_finalize_kernel<<<ceil_div(c.cout, 128), 128, 0, st>>>(t->dstat + 512, npix, c.cout, t->mean[ci], t->invstd[ci],
+  bn_finalize_kernel<<<ceil_div(c.cout, 128), 128, 0, st>>>(t->dstat, t->raw[ci], npix, c.cout, t->mean[ci], t->invstd[ci],
                                                            update_running ? c.rmean : nullptr, update_running ? c.rvar : nullptr, 0.1f);
   STRAPS_LAUNCH_CHECK();
   const long long n4 = npix * c.cout / 4;
@@ -480,11 +549,11 @@ static int bn_backward(straps_regressor* r, TrainState* t, int ci, int B, const 
                        float* dgamma, float* dbeta, cudaStream_t st) {
   const ConvSpec& c = r->conv[ci];
   const long long npix = (long long)B * c.hout * c.wout;
-  const int chunks = (int)std::min<long long>(1024, (npix + 63) / 64);
+  const int chunks = (int)std::max<long long>(1, std::min<long long>(1184, npix / (16LL * (1024 / c.cout))));
   STRAPS_CUDA(cudaMemsetAsync(t->fstat, 0, 1024 * sizeof(float), st));
   unsigned* maxbits = (t->mode == STRAPS_CONV_F16X3_TC) ? tc_train_dy_max(r) : nullptr;
   if (maxbits) STRAPS_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(unsigned), st));
-  bn_bwd_reduce_kernel<<<dim3(chunks, c.cout / 64), 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], npix, c.cout, t->fstat);
+  bn_bwd_reduce_kernel<<<chunks, 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], npix, c.cout, t->fstat);
   STRAPS_LAUNCH_CHECK();
   const long long n4 = npix * c.cout / 4;
   bn_bwd_apply_kernel<<<(unsigned)((n4 + 1023) / 1024), 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], c.gamma, t->fstat, npix,
@@ -718,6 +787,19 @@ extern "C" int straps_adam_step(float* params, const float* grads, float* exp_av
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                                         eps, bc1, bc2, grad_scale);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int straps_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_counter,
+                                    float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  STRAPS_CHECK(params && grads && exp_avg && exp_avg_sq && step_counter, "straps_adam_step_dev: null argument");
+  if (n <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  adam_tick_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(step_counter));
+  STRAPS_LAUNCH_CHECK();
+  adam_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, reinterpret_cast<const long long*>(step_counter),
+                                                             lr, beta1, beta2, eps, grad_scale);
   STRAPS_LAUNCH_CHECK();
   return 0;
 }

@@ -55,6 +55,8 @@ SIGNATURES = {
                                            ctypes.POINTER(_vp), _vp, _vp]),
     'straps_adam_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
+    'straps_adam_step_dev': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, _vp, ctypes.c_float, ctypes.c_float,
+                                            ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
     'straps_multitask_loss': (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), c_i64_p, _vp, ctypes.c_int,
                                              ctypes.c_float, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
     'straps_encoder_read_activation': (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int, _vp, c_i64_p, _vp]),

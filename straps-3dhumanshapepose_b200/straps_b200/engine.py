@@ -145,6 +145,7 @@ class _RegressorTrain(torch.autograd.Function):
         # the activations and batch statistics the backward needs stay in the handle's workspace, which EVERY later encoder forward
         # (train or inference) overwrites: remember which forward this graph belongs to
         ctx.generation = handle.generation
+        ctx.params = params          # the nn.Parameters themselves: their gradient slots (straps_b200.parallel.FlatBucket) are looked up in backward
         ctx.conv_shapes = [tuple(p.shape) for p in params[:20]]
         ctx.bn_channels = [p.shape[0] for p in params[20:40]]
         if want == 'feat':
@@ -162,14 +163,19 @@ class _RegressorTrain(torch.autograd.Function):
                               'graph was recorded at %d).  The B200 regressor keeps ONE set of activations per device: call '
                               'backward() before the next forward of the same regressor (gradient accumulation = backward per '
                               'micro-batch)' % (h.generation, ctx.generation))
+        # A parameter re-homed into a flat gradient bucket carries its slot (a view of the bucket); while it has no .grad yet the
+        # kernels write the gradient straight into the slot and autograd adopts it as .grad -- no per-parameter accumulate launch
+        # (71 of them per step before), and the bucket is complete the moment the backward kernels finish.
+        slot = [getattr(p, '_straps_grad_slot', None) if (torch.is_tensor(p) and p.grad is None) else None for p in ctx.params]
         if ctx.want == 'feat':
             d_feat = g.contiguous()
             dfw = [None] * 3
             dfb = [None] * 3
         else:
             feat, saved = ctx.saved_tensors
-            d_feat, dfw, dfb = h.ief_backward(feat, saved, g, ctx.iters)
-        dws, dbn = h.encoder_backward(d_feat, ctx.conv_shapes, ctx.bn_channels)
+            d_feat, dfw, dfb = h.ief_backward(feat, saved, g, ctx.iters, out_w=slot[60:63], out_b=slot[63:66])
+        dws, dbn = h.encoder_backward(d_feat, ctx.conv_shapes, ctx.bn_channels, out_w=slot[:20],
+                                      out_bn=list(zip(slot[20:40], slot[40:60])))
         grads = list(dws) + [p[0] for p in dbn] + [p[1] for p in dbn] + list(dfw) + list(dfb)
         return (None, None, None, None, None) + tuple(grads)
 

@@ -51,3 +51,64 @@ class GraphedCallable(object):
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
         return self._static_out
+
+
+class GraphedTrainStep(object):
+    """One whole training step -- forward, loss, backward, gradient exchange, Adam -- captured as CUDA graph(s) and replayed.
+
+    `step_fn(*inputs)` must run the step exactly as the reference's loop body does (train/train_synthetic_otf_rendering.py:186-233):
+    `optimiser.zero_grad(); loss, ... = criterion(...); loss.backward(); optimiser.step()` with a
+    straps_b200.parallel.DataParallelAdam `optimiser`, and return the tensors the caller wants to read (e.g. the loss).  The step
+    launches ~500 kernels for ~9 ms of GPU work; eager PyTorch spends another ~1.5 ms in launch gaps and autograd bookkeeping,
+    which replay removes.  Everything the step touches is graph-safe: the library allocates its workspaces on first use (the
+    warm-up steps here), Adam's step count lives on the device, BatchNorm's counters are bumped by a captured foreach kernel.
+
+    world_size 1: one graph.  world_size > 1: the all-reduce stays OUTSIDE the capture (NCCL work is enqueued on the replaying stream
+    between the two graphs): graph A = zero_grad + forward + backward + gather, collective, graph B = Adam.  The split is done by
+    the optimiser: `step_fn` is captured with `optimiser.defer_exchange()` active.
+    """
+
+    def __init__(self, step_fn, optimiser, *example_inputs, warmup=3):
+        from .parallel import DataParallelAdam
+        if not isinstance(optimiser, DataParallelAdam):
+            raise StrapsError('GraphedTrainStep needs a straps_b200.parallel.DataParallelAdam (device-side step count, flat buckets)')
+        for t in example_inputs:
+            if not torch.is_tensor(t) or not t.is_cuda:
+                raise StrapsError('GraphedTrainStep captures functions of CUDA tensors (got %r)' % (type(t),))
+        self._opt = optimiser
+        self._static_in = [t.detach().clone() for t in example_inputs]
+        dev = optimiser.bucket.params.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(2, warmup)):          # workspaces, tensor maps, allocator warm-up; these are REAL training steps
+                step_fn(*self._static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._split = optimiser.world > 1
+        self._graph = torch.cuda.CUDAGraph()
+        optimiser._deferred = self._split
+        try:
+            with torch.cuda.graph(self._graph):
+                self._static_out = step_fn(*self._static_in)
+        finally:
+            optimiser._deferred = False
+        self._graph_b = None
+        if self._split:
+            self._graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_b, pool=self._graph.pool()):
+                optimiser.apply_update()
+            # the capture ran the forward/backward once without the update: finish that step so the replicas stay in step
+            optimiser.exchange()
+            self._graph_b.replay()
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self._static_in, inputs):
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        if self._split:
+            self._opt.exchange()
+            self._graph_b.replay()
+        self._opt.bucket.bump_versions()             # host-side bookkeeping the replay skipped: the packed weight copies are stale
+        return self._static_out

@@ -99,6 +99,20 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-3, betas=(0.9, 0.9
               'straps_adam_step')
 
 
+def adam_step_dev(params, grads, exp_avg, exp_avg_sq, step_counter, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    """adam_step with the step count in `step_counter` (CUDA int64, 1 element; incremented by the call): CUDA-graph capturable."""
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        _need_cuda(t, 'adam buffer')
+        if not t.is_contiguous():
+            raise StrapsError('adam buffers must be contiguous')
+    if not step_counter.is_cuda or step_counter.dtype != torch.int64 or step_counter.numel() != 1:
+        raise StrapsError('adam_step_dev: step_counter must be a CUDA int64 tensor with one element')
+    with torch.cuda.device(params.device):
+        check(_lib.lib().straps_adam_step_dev(_p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), _p(step_counter),
+                                              float(lr), float(betas[0]), float(betas[1]), float(eps), float(grad_scale),
+                                              _stream(params.device)), 'straps_adam_step_dev')
+
+
 # ---- SURVEY 8f N2: target side of the synthetic loop ----
 def batch_rodrigues(rot_vecs):
     """[n,3] axis-angle -> [n,3,3]  (smplx.lbs.batch_rodrigues; reference call sites augmentation/smpl_augmentation.py:55-58)."""
@@ -417,13 +431,15 @@ class RegressorHandle(object):
                                                           _stream(self.device)), 'straps_encoder_train_forward')
         return feat
 
-    def encoder_backward(self, dfeat, conv_shapes, bn_channels, mode=None):
-        """-> (list of 20 OIHW weight gradients, list of 20 (d_weight, d_bias)).  mode None = the mode of the forward."""
+    def encoder_backward(self, dfeat, conv_shapes, bn_channels, mode=None, out_w=None, out_bn=None):
+        """-> (list of 20 OIHW weight gradients, list of 20 (d_weight, d_bias)).  mode None = the mode of the forward.
+        out_w / out_bn: optional pre-allocated destinations (None entries are allocated here); every gradient is OVERWRITTEN."""
         dfeat = dfeat.contiguous()
         B = dfeat.shape[0]
-        dws = [torch.empty(s, dtype=torch.float32, device=self.device) for s in conv_shapes]
-        dbn = [(torch.empty(c, dtype=torch.float32, device=self.device), torch.empty(c, dtype=torch.float32, device=self.device))
-               for c in bn_channels]
+        new = lambda s: torch.empty(s, dtype=torch.float32, device=self.device)
+        dws = [out_w[i] if out_w is not None and out_w[i] is not None else new(s) for i, s in enumerate(conv_shapes)]
+        dbn = [((out_bn[i][0] if out_bn is not None and out_bn[i][0] is not None else new(c)),
+                (out_bn[i][1] if out_bn is not None and out_bn[i][1] is not None else new(c))) for i, c in enumerate(bn_channels)]
         flat_bn = [t for pair in dbn for t in pair]
         arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         with torch.cuda.device(self.device):
@@ -442,12 +458,14 @@ class RegressorHandle(object):
                   'straps_ief_forward_train')
         return params, saved
 
-    def ief_backward(self, feat, saved, d_params, iters=3):
+    def ief_backward(self, feat, saved, d_params, iters=3, out_w=None, out_b=None):
         feat, d_params = feat.contiguous(), d_params.contiguous()
         B, dev = feat.shape[0], feat.device
         d_feat = torch.empty((B, 512), dtype=torch.float32, device=dev)
-        dw = [torch.empty(s, dtype=torch.float32, device=dev) for s in ((512, 669), (512, 512), (157, 512))]
-        db = [torch.empty(s, dtype=torch.float32, device=dev) for s in (512, 512, 157)]
+        dw = [out_w[i] if out_w is not None and out_w[i] is not None else torch.empty(s, dtype=torch.float32, device=dev)
+              for i, s in enumerate(((512, 669), (512, 512), (157, 512)))]
+        db = [out_b[i] if out_b is not None and out_b[i] is not None else torch.empty(s, dtype=torch.float32, device=dev)
+              for i, s in enumerate((512, 512, 157))]
         scratch = torch.empty((B * 1850,), dtype=torch.float32, device=dev)
         arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         with torch.cuda.device(self.device):

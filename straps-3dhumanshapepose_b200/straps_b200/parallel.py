@@ -40,26 +40,44 @@ class FlatBucket(object):
         self.grads = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.offsets = []
         o = 0
+        self.slots = []
         with torch.no_grad():
             for p in plist:
                 n = p.numel()
                 self.params[o:o + n].copy_(p.data.reshape(-1))
                 p.data = self.params[o:o + n].view(p.shape)
-                p.grad = self.grads[o:o + n].view(p.shape)
+                slot = self.grads[o:o + n].view(p.shape)
+                p.grad = slot
+                # the library's backward kernels write a fresh gradient straight into this view (straps_b200.engine._RegressorTrain)
+                p._straps_grad_slot = slot
+                self.slots.append(slot)
                 self.offsets.append(o)
                 o += n
 
     def zero_grad(self):
+        """One memset of the bucket; every .grad is dropped (set-to-none), so the next backward WRITES its gradients into the slots
+        instead of accumulating into them (gather() below puts anything that arrived some other way into place)."""
         self.grads.zero_()
-        for p, o in zip(self.plist, self.offsets):     # a set_to_none zero_grad elsewhere must not detach the views
-            if p.grad is None or p.grad.data_ptr() != self.grads.data_ptr() + 4 * o:
-                p.grad = self.grads[o:o + p.numel()].view(p.shape)
+        for p in self.plist:
+            p.grad = None
+
+    def gather(self):
+        """After backward: make the flat bucket hold every gradient and every .grad a view of it.  Gradients the library wrote into
+        their slot (and autograd adopted) are already there; anything else -- a tensor autograd allocated itself, an accumulated
+        gradient, a set_to_none zero_grad by foreign code -- is copied in."""
+        base = self.grads.data_ptr()
+        for p, o, slot in zip(self.plist, self.offsets, self.slots):
+            g = p.grad
+            if g is None:
+                p.grad = slot                   # no gradient this step: the slot is zero since zero_grad()
+            elif g.data_ptr() != base + 4 * o:
+                slot.copy_(g)
+                p.grad = slot
 
     def bump_versions(self):
-        """The fused optimiser writes through the flat buffer: tell the engines that the weights changed."""
-        with torch.no_grad():
-            for p in self.plist:
-                p.add_(0)
+        """The fused optimiser writes through the flat buffer: tell the engines that the weights changed (version counters only --
+        round 1 did this with 67 `p.add_(0)` launches that re-wrote all 47.6 MB of parameters)."""
+        torch.autograd.graph.increment_version(self.plist)
 
 
 class DataParallelAdam(object):
@@ -71,33 +89,57 @@ class DataParallelAdam(object):
         self.group = process_group
         self.exp_avg = torch.zeros_like(self.bucket.params)
         self.exp_avg_sq = torch.zeros_like(self.bucket.params)
-        self.step_count = 0
+        # the step count lives on the device for CUDA buckets (bias corrections inside the kernel: the step is CUDA-graph capturable)
+        self._step_host = 0
+        self._step_dev = torch.zeros(1, dtype=torch.int64, device=self.bucket.params.device) if self.bucket.params.is_cuda else None
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         if broadcast and self.world > 1:
             dist.broadcast(self.bucket.params, src=0, group=process_group)     # identical replicas
 
-    def zero_grad(self):
+    @property
+    def step_count(self):
+        return int(self._step_dev.item()) if self._step_dev is not None else self._step_host
+
+    @step_count.setter
+    def step_count(self, v):
+        if self._step_dev is not None:
+            self._step_dev.fill_(int(v))
+        self._step_host = int(v)
+
+    def zero_grad(self, set_to_none=True):
         self.bucket.zero_grad()
 
-    def all_reduce(self):
-        """THE one collective of the step: sum the flat gradient bucket over ranks."""
+    def exchange(self):
+        """THE one collective of the step: sum the flat gradient bucket over ranks (NCCL all-reduce over NVLink / NVSwitch)."""
         if self.world > 1:
             dist.all_reduce(self.bucket.grads, op=dist.ReduceOp.SUM, group=self.group)
 
+    def all_reduce(self):
+        self.bucket.gather()
+        self.exchange()
+
+    _deferred = False        # set by straps_b200.graphs.GraphedTrainStep while it captures the step in two graphs around the collective
+
     def step(self):
+        if self._deferred:
+            self.bucket.gather()             # captured with the backward; exchange() + apply_update() are driven by the graph wrapper
+            return
         self.all_reduce()
-        self.step_count += 1
+        self.apply_update()
+
+    def apply_update(self):
         b = self.bucket
         if b.params.is_cuda:
-            ops.adam_step(b.params, b.grads, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas, self.eps,
-                          grad_scale=1.0 / self.world)
+            ops.adam_step_dev(b.params, b.grads, self.exp_avg, self.exp_avg_sq, self._step_dev, self.lr, self.betas, self.eps,
+                              grad_scale=1.0 / self.world)
         else:
+            self._step_host += 1
             # host-side restatement used by the gloo CPU tests of the bucket / collective logic only
             g = b.grads / self.world
             self.exp_avg.mul_(self.betas[0]).add_(g, alpha=1 - self.betas[0])
             self.exp_avg_sq.mul_(self.betas[1]).addcmul_(g, g, value=1 - self.betas[1])
-            bc1 = 1 - self.betas[0] ** self.step_count
-            bc2 = 1 - self.betas[1] ** self.step_count
+            bc1 = 1 - self.betas[0] ** self._step_host
+            bc2 = 1 - self.betas[1] ** self._step_host
             denom = self.exp_avg_sq.sqrt() / (bc2 ** 0.5) + self.eps
             b.params.addcdiv_(self.exp_avg, denom, value=-self.lr / bc1)
         b.bump_versions()
@@ -109,10 +151,11 @@ class DataParallelAdam(object):
         views of the flat moments), so `checkpoint['optimiser_state_dict']` interchanges with the reference's files."""
         b = self.bucket
         state = {}
-        if self.step_count > 0:
+        step_count = self.step_count
+        if step_count > 0:
             for i, p, o in zip(b.index, b.plist, b.offsets):       # frozen parameters have no entry, as in torch.optim.Adam
                 n = p.numel()
-                state[i] = {'step': torch.tensor(float(self.step_count)),
+                state[i] = {'step': torch.tensor(float(step_count)),
                             'exp_avg': self.exp_avg[o:o + n].view(p.shape).clone(),
                             'exp_avg_sq': self.exp_avg_sq[o:o + n].view(p.shape).clone()}
         group = {'lr': self.lr, 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': 0, 'amsgrad': False, 'maximize': False,

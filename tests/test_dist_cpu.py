@@ -83,7 +83,16 @@ def test_bucket_views_and_shard():
     assert b.numel == 15 and torch.equal(lin.weight.detach(), w0)
     lin(torch.ones(2, 4)).sum().backward()
     assert torch.equal(b.grads[:12].view(3, 4), lin.weight.grad) and float(b.grads.abs().sum()) > 0
+    # zero_grad drops every .grad (the next backward WRITES its gradients); gather() puts whatever autograd produced into the bucket
     b.zero_grad()
+    assert lin.weight.grad is None and float(b.grads.abs().sum()) == 0
+    lin(torch.ones(2, 4)).sum().backward()
+    assert lin.weight.grad.data_ptr() != b.grads.data_ptr()          # autograd allocated its own tensor ...
+    b.gather()
+    assert lin.weight.grad.data_ptr() == b.grads.data_ptr()          # ... gather() copied it into the slot and re-homed .grad
+    assert torch.equal(b.grads[:12].view(3, 4), torch.ones(3, 4) * 2) and torch.equal(b.grads[12:], torch.ones(3) * 2)
+    b.zero_grad()
+    b.gather()                                                       # no backward at all: zero gradients, views restored
     assert float(lin.weight.grad.abs().sum()) == 0 and lin.weight.grad.data_ptr() == b.grads.data_ptr()
     x = torch.arange(12).view(6, 2)
     assert shard(x, 1, 3).tolist() == [[4, 5], [6, 7]]

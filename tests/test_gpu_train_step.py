@@ -1,0 +1,144 @@
+"""GPU: the optimiser side of the training step (BASELINE config 3 / 4; run_train.py:200-201, train/...:230-233).
+
+* DataParallelAdam with the library writing gradients straight into the flat bucket (no per-parameter accumulate kernels) and
+  the step count on the device lands where torch.optim.Adam lands on an identical replica;
+* gradient accumulation over two backward passes still accumulates (the slot shortcut only applies to a fresh gradient);
+* GraphedTrainStep (the whole step captured as a CUDA graph and replayed) follows the eager loop.
+Tolerance: parameters after a few steps within 1e-5 of their magnitude (the weight-gradient kernels add partial tiles with fp32
+atomics, so two runs of the SAME code differ in the last bits; Adam's ratio m / sqrt(v) is then compared in aggregate)."""
+import numpy as np
+import pytest
+import torch
+
+import straps_oracle as O
+from conftest import rel_err, WEIGHT_SEED
+from straps_b200 import synthetic_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+W = {'verts': 1.0, 'joints2D': 0.1, 'pose_params': 0.1, 'shape_params': 0.1, 'joints3D': 1.0}
+TASKS = ['verts', 'joints2D', 'joints3D', 'pose_params', 'shape_params']
+C, B, LR = 17, 4, 1e-4
+
+
+def _setup(seed_targets=3):
+    import config
+    from models.regressor import SingleInputRegressor
+    from models.smpl_official import SMPL
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    from utils.joints2d_utils import check_joints2d_visibility_torch
+    from losses.multi_task_loss import HomoscedasticUncertaintyWeightedMultiTaskLoss as Loss
+    sd = O.make_regressor_state(C, seed=WEIGHT_SEED)
+    reg = SingleInputRegressor(C, 18, 3)
+    reg.load_state_dict(sd)
+    reg = reg.to(DEV).train()
+    crit = Loss(TASKS, init_loss_weights=W).to(DEV)
+    smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(DEV)
+    rng = np.random.RandomState(seed_targets)
+    x = torch.from_numpy(synthetic_inputs.make_proxy_batch(B, C, seed=21)).to(DEV)
+    with torch.no_grad():
+        t_betas = torch.from_numpy(rng.normal(0, 1, (B, 10)).astype(np.float32)).to(DEV)
+        t_R = rot6d_to_rotmat(torch.from_numpy(rng.normal(0, 1, (B, 144)).astype(np.float32)).to(DEV)).view(B, 24, 3, 3)
+        t_out = smpl(body_pose=t_R[:, 1:], global_orient=t_R[:, :1], betas=t_betas, pose2rot=False)
+        t_j2d = torch.from_numpy(rng.uniform(-20, 276, (B, 17, 2)).astype(np.float32)).to(DEV)
+        labels = {'verts': t_out.vertices, 'joints2D': t_j2d,
+                  'joints3D': t_out.joints[:, config.ALL_JOINTS_TO_H36M_MAP, :][:, config.H36M_TO_J14, :].contiguous(),
+                  'shape_params': t_betas, 'pose_params_rot_matrices': t_R,
+                  'vis': check_joints2d_visibility_torch(t_j2d, config.REGRESSOR_IMG_WH)}
+    return reg, crit, smpl, x, labels
+
+
+def _loss(reg, crit, smpl, x, labels):
+    import config
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    from utils.cam_utils import orthographic_project_torch
+    cam, pose, shape = reg(x)
+    R = rot6d_to_rotmat(pose.contiguous()).view(-1, 24, 3, 3)
+    out = smpl(body_pose=R[:, 1:], global_orient=R[:, 0].unsqueeze(1), betas=shape, pose2rot=False)
+    outs = {'verts': out.vertices, 'joints2D': orthographic_project_torch(out.joints[:, config.ALL_JOINTS_TO_COCO_MAP, :], cam),
+            'joints3D': out.joints[:, config.ALL_JOINTS_TO_H36M_MAP, :][:, config.H36M_TO_J14, :], 'shape_params': shape,
+            'pose_params_rot_matrices': R}
+    return crit(labels, outs)[0]
+
+
+def _flat(reg, crit):
+    return torch.cat([p.detach().reshape(-1) for p in list(reg.parameters()) + list(crit.parameters())]).cpu()
+
+
+def _updates_agree(a, b, start, steps):
+    """Parameters agree to 1e-5 of their magnitude and the mean update error is a small fraction of steps * lr."""
+    assert rel_err(a.numpy(), b.numpy()) < 1e-5
+    assert float(((a - start) - (b - start)).abs().mean()) < 0.02 * steps * LR
+
+
+def test_flat_bucket_adam_matches_torch_adam(assets_root):
+    from straps_b200.parallel import DataParallelAdam
+    reg_a, crit_a, smpl, x, labels = _setup()
+    reg_b, crit_b, _, _, _ = _setup()
+    start = _flat(reg_a, crit_a)
+    opt_a = DataParallelAdam(list(reg_a.parameters()) + list(crit_a.parameters()), lr=LR)
+    opt_b = torch.optim.Adam(list(reg_b.parameters()) + list(crit_b.parameters()), lr=LR)
+    for step in range(3):
+        opt_a.zero_grad()
+        _loss(reg_a, crit_a, smpl, x, labels).backward()
+        if step == 0:
+            # the encoder / IEF gradients were written straight into their slots and adopted by autograd: no copy
+            base = opt_a.bucket.grads.data_ptr()
+            in_place = [p.grad is not None and p.grad.data_ptr() == base + 4 * o for p, o in zip(opt_a.bucket.plist, opt_a.bucket.offsets)]
+            assert sum(in_place) >= 66, sum(in_place)
+        opt_a.step()
+        opt_b.zero_grad()
+        _loss(reg_b, crit_b, smpl, x, labels).backward()
+        opt_b.step()
+    assert opt_a.step_count == 3
+    _updates_agree(_flat(reg_a, crit_a), _flat(reg_b, crit_b), start, 3)
+    sd = opt_a.state_dict()
+    assert float(sd['state'][0]['step']) == 3.0 and len(sd['state']) == 71
+
+
+def test_gradient_accumulation_still_accumulates(assets_root):
+    from straps_b200.parallel import DataParallelAdam
+    reg, crit, smpl, x, labels = _setup()
+    opt = DataParallelAdam(list(reg.parameters()) + list(crit.parameters()), lr=LR)
+    opt.zero_grad()
+    _loss(reg, crit, smpl, x, labels).backward()
+    opt.bucket.gather()
+    g1 = opt.bucket.grads.clone()
+    _loss(reg, crit, smpl, x, labels).backward()          # no zero_grad in between: .grad exists, so this pass must ADD
+    opt.bucket.gather()
+    assert rel_err(opt.bucket.grads.cpu().numpy(), (2 * g1).cpu().numpy()) < 1e-4
+
+
+def test_graphed_training_step_follows_the_eager_loop(assets_root):
+    from straps_b200.parallel import DataParallelAdam
+    from straps_b200.graphs import GraphedTrainStep
+    reg_a, crit_a, smpl, x, labels = _setup()
+    reg_b, crit_b, _, _, _ = _setup()
+    start = _flat(reg_a, crit_a)
+    opt_a = DataParallelAdam(list(reg_a.parameters()) + list(crit_a.parameters()), lr=LR)
+    opt_b = DataParallelAdam(list(reg_b.parameters()) + list(crit_b.parameters()), lr=LR)
+
+    def make_step(reg, crit, opt):
+        def step():
+            opt.zero_grad()
+            loss = _loss(reg, crit, smpl, x, labels)
+            loss.backward()
+            opt.step()
+            return loss
+        return step
+    step_a, step_b = make_step(reg_a, crit_a, opt_a), make_step(reg_b, crit_b, opt_b)
+    gstep = GraphedTrainStep(step_a, opt_a, warmup=2)          # 2 real warm-up steps + 1 captured (not executed)
+    losses = [float(gstep()) for _ in range(3)]
+    for _ in range(5):
+        loss_b = step_b()
+    assert opt_a.step_count == 5 and opt_b.step_count == 5
+    assert abs(losses[-1] - float(loss_b)) < 1e-4 * abs(float(loss_b))
+    assert losses[0] > losses[-1]                              # it trains
+    _updates_agree(_flat(reg_a, crit_a), _flat(reg_b, crit_b), start, 5)
+    n_bn = int(reg_a.state_dict()['image_encoder.bn1.num_batches_tracked'])
+    assert n_bn == 5, n_bn
+    # eval-mode inference after replays sees the replayed weights and running statistics
+    reg_a.eval(); reg_b.eval()
+    with torch.no_grad():
+        pa, pb = reg_a(x)[1], reg_b(x)[1]
+    assert rel_err(pa.cpu().numpy(), pb.cpu().numpy()) < 1e-4

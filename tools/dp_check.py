@@ -96,6 +96,7 @@ def main():
     # ---- correctness of the exchange on step 0
     x, tg = step_inputs(0)
     loss = forward_backward(x, tg)
+    opt.bucket.gather()
     local_grads = opt.bucket.grads.clone()
     opt.all_reduce()
     reduced = opt.bucket.grads.clone()
