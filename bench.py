@@ -88,16 +88,28 @@ def bind_to_gpu_numa_node(index):
         bus = '%04x:%02x:%02x.0' % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
         node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
         info.update(pci=bus, node=node)
-        if node < 0:
-            return info
         cpus = set()
-        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
-            a, _, b = part.partition('-')
-            cpus.update(range(int(a), int(b or a) + 1))
+        if node >= 0:
+            for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+                a, _, b = part.partition('-')
+                cpus.update(range(int(a), int(b or a) + 1))
+        else:
+            # sysfs hides the topology (containers, some VMs): ask NVML for the GPU's ideal CPU set instead
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+            info['source'] = 'nvml'
+            if len(cpus) >= (os.cpu_count() or 1):
+                info['note'] = 'NVML reports no CPU locality for this GPU (single NUMA domain)'
+                return info
         cpus &= os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)
             info.update(bound=True, cpus=len(cpus))
+        if node < 0:
+            return info
         try:                                   # also prefer the node for page allocation (set_mempolicy(MPOL_PREFERRED)); x86-64 syscall 238
             import ctypes
             mask = ctypes.c_ulong(1 << node)
@@ -252,7 +264,7 @@ def lbs_sweep(dev, batches, peak_hbm):
             'bound': 'hbm', 'peak': peak_hbm, 'unit': 'GB/s', 'rows': rows}
 
 
-def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_over_ranks):
+def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_over_ranks, no_graph=False):
     """BASELINE config 3 (world 1) / config 4 (world > 1): reference train/train_synthetic_otf_rendering.py:186-233 without the renderer --
     regressor.train() forward, rot6d, SMPL, projection, five-term multi-task loss, backward, ONE all-reduce (NCCL) of the flat fp32
     gradient bucket, fused Adam (run_train.py:200-201) -- on device-resident synthetic inputs and targets."""
@@ -265,6 +277,7 @@ def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_ov
     from losses.multi_task_loss import HomoscedasticUncertaintyWeightedMultiTaskLoss as Loss
     from straps_b200.parallel import DataParallelAdam
     from straps_b200 import _lib
+    from straps_b200.ops import select_joints
     tasks = ['verts', 'joints2D', 'joints3D', 'pose_params', 'shape_params']
     weights = {'verts': 1.0, 'joints2D': 0.1, 'pose_params': 0.1, 'shape_params': 0.1, 'joints3D': 1.0}      # run_train.py:53-54
     torch.manual_seed(1)
@@ -288,8 +301,8 @@ def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_ov
         cam, pose, shape = reg(x_dev)
         R = rot6d_to_rotmat(pose.contiguous()).view(-1, 24, 3, 3)
         out = smpl(body_pose=R[:, 1:], global_orient=R[:, 0].unsqueeze(1), betas=shape, pose2rot=False)
-        outs = {'verts': out.vertices, 'joints2D': orthographic_project_torch(out.joints[:, config.ALL_JOINTS_TO_COCO_MAP, :], cam),
-                'joints3D': out.joints[:, config.ALL_JOINTS_TO_H36M_MAP, :][:, config.H36M_TO_J14, :], 'shape_params': shape,
+        outs = {'verts': out.vertices, 'joints2D': orthographic_project_torch(select_joints(out.joints, config.ALL_JOINTS_TO_COCO_MAP), cam),
+                'joints3D': select_joints(out.joints, config.ALL_JOINTS_TO_H36M_MAP, config.H36M_TO_J14), 'shape_params': shape,
                 'pose_params_rot_matrices': R}
         loss, _ = crit(labels, outs)
         loss.backward()
@@ -311,12 +324,14 @@ def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_ov
     # the same step captured as CUDA graph(s) and replayed (straps_b200.graphs.GraphedTrainStep; the all-reduce stays outside the capture)
     ms_graph, graph_note = None, None
     try:
+        if no_graph:
+            raise RuntimeError('skipped (--no-train-graph)')
         from straps_b200.graphs import GraphedTrainStep
         gstep = GraphedTrainStep(step, opt)
         ms_graph, _, loss = timed(gstep)
     except Exception as e:                                  # noqa: BLE001 -- the eager figure stands on its own
         graph_note = '%s: %s' % (type(e).__name__, str(e)[:300])
-        if world > 1:
+        if world > 1 and not no_graph:
             raise                                           # a half-captured rank would dead-lock the others at the next collective
     ms = ms_graph if ms_graph is not None else ms_eager
     # identical replicas after the updates: every rank's parameter bucket must hash the same
@@ -508,7 +523,7 @@ def run_gpu(args):
         sweep = lbs_sweep(dev, [1, 8, 64, 256, 1024, 4096], peak_hbm)
     train = None
     if args.train_steps > 0:
-        train = train_bench(dev, rank, world, B, C, args.conv_mode, args.train_steps, x_dev, barrier, max_over_ranks)
+        train = train_bench(dev, rank, world, B, C, args.conv_mode, args.train_steps, x_dev, barrier, max_over_ranks, no_graph=args.no_train_graph)
 
     if rank != 0:
         if world > 1:
@@ -570,6 +585,7 @@ def main():
     ap.add_argument('--cpu-reps', type=int, default=3)
     ap.add_argument('--train-steps', type=int, default=10, help='timed steps of the training-step arm (0 = skip)')
     ap.add_argument('--no-lbs-sweep', action='store_true')
+    ap.add_argument('--no-train-graph', action='store_true', help='time the eager training loop only (ncu launch lists: replays hide the kernels)')
     ap.add_argument('--no-numa-bind', action='store_true', help='leave the process unbound (A/B of the NUMA binding)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -23,6 +23,7 @@
 //   regressed rows are CSR dot products over the just-written (L2 resident) vertices.
 #include "smpl.h"
 #include <cmath>
+#include <cstdlib>
 
 namespace straps {
 
@@ -417,6 +418,7 @@ extern "C" int straps_smpl_create(straps_smpl_t** out, const float* v_template, 
                "straps_smpl_create: null argument");
   straps_smpl* m = new straps_smpl();
   memset(&m->d, 0, sizeof(SmplDev));
+  m->tc_apk = nullptr; m->tc_ainv = nullptr; m->tc_scratch = nullptr; m->tc_scratch_bytes = 0;
   // --- kinematic tree -> levels
   int depth[NJ];
   for (int j = 0; j < NJ; ++j) {
@@ -503,6 +505,13 @@ extern "C" int straps_smpl_create(straps_smpl_t** out, const float* v_template, 
   rc |= upload(m, ptr, &m->d.csr_ptr);
   rc |= upload(m, idx, &m->d.csr_idx);
   rc |= upload(m, val, &m->d.csr_val);
+  if (!rc && sparse4) {          // operands of the tensor-core LBS (batches >= 32)
+    std::vector<unsigned char> apk;
+    std::vector<float> ainv;
+    smpl_tc_pack(v_template, shapedirs, posedirs, apk, ainv);
+    rc |= upload(m, apk, &m->tc_apk);
+    rc |= upload(m, ainv, &m->tc_ainv);
+  }
   if (rc) { straps_smpl_destroy(m); return 1; }
   *out = m;
   return 0;
@@ -511,6 +520,7 @@ extern "C" int straps_smpl_create(straps_smpl_t** out, const float* v_template, 
 extern "C" void straps_smpl_destroy(straps_smpl_t* m) {
   if (!m) return;
   for (void* p : m->allocs) cudaFree(p);
+  if (m->tc_scratch) cudaFree(m->tc_scratch);
   delete m;
 }
 
@@ -543,6 +553,20 @@ static int smpl_forward_impl(const straps_smpl_t* m, const float* global_orient,
   a.go_stride = go_stride; a.bp_stride = bp_stride; a.betas_stride = betas_stride;
   a.B = batch; a.pose2rot = pose2rot; a.verts = vertices; a.joints = joints;
   a.save_vposed = save_vposed; a.save_A = save_A;
+  // batches >= 32 with the usual <= 4 skinning weights per vertex: blend shapes on the tensor cores (smpl_tc.cu);
+  // STRAPS_LBS=simt keeps the CUDA-core kernel (parity tests compare the two)
+  {
+    const char* e = getenv("STRAPS_LBS");
+    if (batch >= 32 && m->sparse4 && m->tc_apk && !(e && e[0] == 's')) {
+      if (smpl_tc_forward(const_cast<straps_smpl*>(m), global_orient, go_stride, body_pose, bp_stride, betas, betas_stride, transl, batch,
+                          pose2rot, vertices, joints, save_vposed, save_A, st))
+        return 1;
+      const int warps = batch * (STRAPS_NUM_EXTRA_PICKS + STRAPS_NUM_EXTRA_ROWS);
+      joints_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(m->d, vertices, joints, batch);
+      STRAPS_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   // bodies per CTA: enough CTAs to fill 148 SMs at small batch, 8-way register tiling once the batch allows it
   int rc;
   if (batch >= 32) rc = launch_lbs<8>(m, a, st);

@@ -44,4 +44,18 @@ struct straps_smpl {
   straps::SmplDev d;
   int sparse4;
   std::vector<void*> allocs;
+  // tensor-core LBS (smpl_tc.cu): [posedirs ; shapedirs ; v_template] packed once as swizzled fp16 hi / lo images + row unscales,
+  // and a per-call scratch (Bm images + skinning transforms) that grows with the largest batch seen
+  const unsigned char* tc_apk;
+  const float* tc_ainv;
+  void* tc_scratch;
+  size_t tc_scratch_bytes;
 };
+
+namespace straps {
+int smpl_tc_pack(const float* v_template, const float* shapedirs, const float* posedirs, std::vector<unsigned char>& apk,
+                 std::vector<float>& ainv);
+int smpl_tc_forward(straps_smpl* m, const float* global_orient, int64_t go_stride, const float* body_pose, int64_t bp_stride,
+                    const float* betas, int64_t betas_stride, const float* transl, int batch, int pose2rot, float* vertices,
+                    float* joints, float* save_vposed, float* save_A, cudaStream_t st);
+}  // namespace straps

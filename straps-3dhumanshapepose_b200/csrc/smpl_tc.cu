@@ -1,0 +1,416 @@
+// smpl_tc.cu -- SMPL linear blend skinning with the blend shapes on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces, for batches >= 32, the CUDA-core lbs_kernel of smpl.cu on the path smplx.lbs.lbs (called from the
+// reference's models/smpl_official.py:29).  lbs_kernel spends 621 FMA per (vertex, body) on the pose-corrective term
+// pf[B,207] @ posedirs[207,20670] and is bound by instruction issue (2.35 warp instructions per FMA; round-1 review, weak #4):
+// 0.03 of the HBM roofline at B = 4096.  That term -- and the shape blend and the template with it -- is a GEMM:
+//
+//   v_posed[b, (v,c)] = sum_k  Apk[(v,c), k] * Bm[b, k]      k = 0..206 pose feature (R_j - I), 207..216 betas, 217 the constant 1
+//                                                            Apk = [posedirs ; shapedirs ; v_template], K padded to 256
+//
+// Kernel 1 (smpl_chain_kernel, 8 bodies per CTA): rotations (Rodrigues or given), pre-reduced rest joints, the 24-joint kinematic
+//   chain (the code of lbs_kernel's prologue, same arithmetic order) -> skinning transforms A[b][24][3x4] and the 24 posed joints;
+//   also writes Bm as fp16 hi / lo (scaled by 2^10) directly in the SWIZZLE_128B shared-memory image the MMA reads.
+// Kernel 2 (lbs_tc_kernel, CTA = 128 vertices x 64 bodies): for each coordinate plane c an M = 128, N = 64 accumulator in TMEM;
+//   K runs over 14 steps of 16 with the 3-pass fp16 split (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi: 22 mantissa bits, plain low halves:
+//   the rows of Apk are pre-scaled by a power of two so that both halves are fp16-normal).  Apk is packed ONCE at create time as
+//   ready-made swizzled 16 KB images, so operands arrive by plain bulk-async copies (no tensor maps): A through a 4-stage ring,
+//   Bm (64 KB) and the group's transforms (72 KB) up front.  Epilogue (all 8 warps): TMEM -> v_posed, 4-sparse skinning with the
+//   transforms in shared memory, + transl, coalesced stores of the vertices (and of v_posed for the training path).
+// Roofline: HBM by contract (20,587,320 B + 84,664 B per body per launch); tensor work 3 x 2 x 224 x 20736 FLOP per body.
+#include "smpl.h"
+#include <cuda_fp16.h>
+#include <cmath>
+#include <cstring>
+
+namespace straps {
+
+constexpr int TC_K = 256;                                   // padded K
+constexpr int TC_KREAL = NPF + STRAPS_NUM_BETAS + 1;        // 218
+constexpr int TC_KSTEPS = (TC_KREAL + 15) / 16;             // 14
+constexpr int TC_CHUNKS = 4;                                // K chunks of 64 elements (one SWIZZLE_128B row each)
+constexpr int TC_NB = 64;                                   // bodies per CTA = MMA N
+constexpr int TC_A_IMG = TV * 128;                          // bytes of one [128 vertices x 64 K] fp16 image
+constexpr int TC_B_IMG = TC_NB * 128;                       // bytes of one [64 bodies x 64 K] fp16 image
+constexpr int TC_STAGES_PER_TILE = TC_CHUNKS * 3 * 2;       // (chunk, plane, hi | lo) = 24 A images per vertex tile
+constexpr int TC_NA = 4;                                    // A ring stages
+constexpr float TC_BSCALE = 1024.f;                         // Bm is multiplied by 2^10 before its fp16 split
+constexpr int TC_T_BYTES = TC_NB * NJ * 12 * 4;             // transforms of one body group: 73,728 B
+constexpr int TC_B_BYTES = TC_CHUNKS * 2 * TC_B_IMG;        // Bm images of one body group: 65,536 B
+constexpr int TC_OFF_B = TC_NA * TC_A_IMG;
+constexpr int TC_OFF_T = TC_OFF_B + TC_B_BYTES;
+constexpr int TC_OFF_BAR = TC_OFF_T + TC_T_BYTES;
+constexpr int TC_SMEM = TC_OFF_BAR + 256 + 1024;
+constexpr int TC_THREADS = 256;
+static_assert(TC_SMEM <= 232448, "lbs_tc_kernel shared memory");
+static_assert(TC_KREAL <= TC_K && TC_KSTEPS <= TC_CHUNKS * 4, "K padding");
+
+struct LbsTcArgs {
+  const unsigned char* apk;     // [54][24] images of TC_A_IMG bytes
+  const float* ainv;            // [54][3][128] 1 / (row scale * TC_BSCALE)
+  const unsigned char* bimg;    // [groups][4][2] images of TC_B_IMG bytes
+  const float* aout;            // [groups * 64][24][12]
+  const int* widx;
+  const float* wval;
+  const float* transl;          // [B][3] or null
+  int B;
+  float* verts;
+  float* save_vposed;           // or null
+};
+
+__device__ __forceinline__ void tc_rodrigues(const float r[3], float* R) {
+  // smplx.lbs.batch_rodrigues: the epsilon goes inside the norm; same code as smpl.cu
+  float x = r[0] + 1e-8f, y = r[1] + 1e-8f, z = r[2] + 1e-8f;
+  float angle = sqrtf(x * x + y * y + z * z);
+  float ax = r[0] / angle, ay = r[1] / angle, az = r[2] / angle;
+  float c = cosf(angle), s = sinf(angle);
+  float K[9] = {0.f, -az, ay, az, 0.f, -ax, -ay, ax, 0.f};
+  float omc = 1.f - c;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float kk = K[i * 3 + 0] * K[0 * 3 + j] + K[i * 3 + 1] * K[1 * 3 + j] + K[i * 3 + 2] * K[2 * 3 + j];
+      R[i * 3 + j] = (i == j ? 1.f : 0.f) + s * K[i * 3 + j] + omc * kk;
+    }
+}
+
+struct ChainArgs {
+  const float* go;
+  const float* bp;
+  const float* betas;
+  const float* transl;
+  long long go_stride, bp_stride, betas_stride;
+  int B, B_pad, pose2rot;
+  float* joints;                // [B][90][3]: rows 0..23 written here
+  float* aout;                  // [B_pad][24][12]
+  unsigned char* bimg;
+  float* save_A;                // training: the same transforms again in the caller's tensor, or null
+};
+
+constexpr int CH_TB = 8;        // bodies per CTA of the chain kernel
+
+__global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const ChainArgs a) {
+  __shared__ float sR[CH_TB][NJ][9];
+  __shared__ float sJ[CH_TB][NJ][3];
+  __shared__ float sG[CH_TB][NJ][12];
+  __shared__ float sbeta[CH_TB][STRAPS_NUM_BETAS];
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * CH_TB;
+  const int nb = max(0, min(CH_TB, a.B - b0));
+  for (int i = tid; i < CH_TB * STRAPS_NUM_BETAS; i += 128) {
+    int b = i / STRAPS_NUM_BETAS, l = i % STRAPS_NUM_BETAS;
+    sbeta[b][l] = (b < nb) ? a.betas[(size_t)(b0 + b) * a.betas_stride + l] : 0.f;
+  }
+  if (a.pose2rot) {
+    for (int i = tid; i < CH_TB * NJ; i += 128) {
+      int b = i / NJ, j = i % NJ;
+      float r[3] = {0.f, 0.f, 0.f};
+      if (b < nb) {
+        const float* src = (j == 0) ? a.go + (size_t)(b0 + b) * a.go_stride : a.bp + (size_t)(b0 + b) * a.bp_stride + (j - 1) * 3;
+        r[0] = src[0]; r[1] = src[1]; r[2] = src[2];
+      }
+      tc_rodrigues(r, &sR[b][j][0]);
+    }
+  } else {
+    for (int i = tid; i < CH_TB * NJ * 9; i += 128) {
+      int b = i / (NJ * 9), r = i % (NJ * 9), j = r / 9, e = r % 9;
+      float v = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
+      if (b < nb) v = (j == 0) ? a.go[(size_t)(b0 + b) * a.go_stride + e] : a.bp[(size_t)(b0 + b) * a.bp_stride + (j - 1) * 9 + e];
+      sR[b][j][e] = v;
+    }
+  }
+  __syncthreads();
+  // Bm = [R_j - I (j = 1..23) | betas | 1 | 0...] * 2^10, fp16 hi / lo, in the swizzled image of its body group
+  for (int i = tid; i < CH_TB * TC_K; i += 128) {
+    const int b = i / TC_K, k = i % TC_K;
+    const int gb = b0 + b;
+    if (gb >= a.B_pad) continue;
+    float v = 0.f;
+    if (b < nb) {
+      if (k < NPF) { const int e = k % 9; v = sR[b][1 + k / 9][e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f); }
+      else if (k < NPF + STRAPS_NUM_BETAS) v = sbeta[b][k - NPF];
+      else if (k == NPF + STRAPS_NUM_BETAS) v = 1.f;
+    }
+    v = fminf(fmaxf(v * TC_BSCALE, -65504.f), 65504.f);
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const int g = gb / TC_NB, r = gb % TC_NB, kc = k >> 6, u = (k & 63) >> 3, e = k & 7;
+    const size_t off = ((size_t)(g * TC_CHUNKS + kc) * 2) * TC_B_IMG + (size_t)r * 128 + (size_t)((u ^ (r & 7)) << 4) + (size_t)e * 2;
+    *reinterpret_cast<__half*>(a.bimg + off) = h;
+    *reinterpret_cast<__half*>(a.bimg + off + TC_B_IMG) = l;
+  }
+  for (int i = tid; i < CH_TB * NJ * 3; i += 128) {
+    int b = i / (NJ * 3), jc = i % (NJ * 3);
+    float acc = 0.f;
+#pragma unroll
+    for (int l = 0; l < STRAPS_NUM_BETAS; ++l) acc = fmaf(m.js[jc * STRAPS_NUM_BETAS + l], sbeta[b][l], acc);
+    sJ[b][jc / 3][jc % 3] = m.jt[jc] + acc;
+  }
+  __syncthreads();
+  for (int lvl = 0; lvl < m.nlevels; ++lvl) {
+    const int j0 = m.lvl_start[lvl], nj = m.lvl_start[lvl + 1] - j0;
+    for (int i = tid; i < CH_TB * nj * 3; i += 128) {
+      int b = i / (nj * 3), q = i % (nj * 3), j = m.lvl_joint[j0 + q / 3], r = q % 3;
+      int p = m.parents[j];
+      const float* Rj = &sR[b][j][0];
+      float* g = &sG[b][j][r * 4];
+      if (p < 0) {
+        g[0] = Rj[r * 3 + 0]; g[1] = Rj[r * 3 + 1]; g[2] = Rj[r * 3 + 2]; g[3] = sJ[b][j][r];
+      } else {
+        const float* gp = &sG[b][p][r * 4];
+        float rel0 = sJ[b][j][0] - sJ[b][p][0];
+        float rel1 = sJ[b][j][1] - sJ[b][p][1];
+        float rel2 = sJ[b][j][2] - sJ[b][p][2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g[c] = gp[0] * Rj[0 * 3 + c] + gp[1] * Rj[1 * 3 + c] + gp[2] * Rj[2 * 3 + c];
+        g[3] = gp[0] * rel0 + gp[1] * rel1 + gp[2] * rel2 + gp[3];
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < CH_TB * NJ * 3; i += 128) {
+    int b = i / (NJ * 3), q = i % (NJ * 3), j = q / 3, r = q % 3;
+    const int gb = b0 + b;
+    if (gb >= a.B_pad) continue;
+    const float* g = &sG[b][j][r * 4];
+    const float t = g[3] - (g[0] * sJ[b][j][0] + g[1] * sJ[b][j][1] + g[2] * sJ[b][j][2]);
+    const float4 row = (b < nb) ? make_float4(g[0], g[1], g[2], t) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(a.aout + ((size_t)gb * NJ + j) * 12 + r * 4) = row;
+    if (b < nb) {
+      if (a.save_A) *reinterpret_cast<float4*>(a.save_A + ((size_t)gb * NJ + j) * 12 + r * 4) = row;
+      const float tr = a.transl ? a.transl[(size_t)gb * 3 + r] : 0.f;
+      a.joints[((size_t)gb * STRAPS_NUM_SUPERSET_JOINTS + j) * 3 + r] = g[3] + tr;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
+  uint64_t* a_full = bars;                 // [TC_NA]
+  uint64_t* a_empty = bars + TC_NA;        // [TC_NA]
+  uint64_t* b_full = bars + 2 * TC_NA;
+  uint64_t* t_full = b_full + 1;
+  uint64_t* acc_full = t_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, group = blockIdx.y;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < TC_NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    mbar_init(b_full, 1); mbar_init(t_full, 1); mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem0 = smem_u32(smem);
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // ================= producer: Bm and the transforms up front, then the 24 A images of this vertex tile =================
+      mbar_arrive_expect_tx(b_full, TC_B_BYTES);
+      bulk_g2s(smem + TC_OFF_B, a.bimg + (size_t)group * TC_B_BYTES, TC_B_BYTES, b_full);
+      mbar_arrive_expect_tx(t_full, TC_T_BYTES);
+      bulk_g2s(smem + TC_OFF_T, a.aout + (size_t)group * TC_NB * NJ * 12, TC_T_BYTES, t_full);
+      const unsigned char* src = a.apk + (size_t)tile * TC_STAGES_PER_TILE * TC_A_IMG;
+      uint32_t st = 0, ph = 1;
+      for (int s = 0; s < TC_STAGES_PER_TILE; ++s) {
+        mbar_wait(&a_empty[st], ph);
+        mbar_arrive_expect_tx(&a_full[st], TC_A_IMG);
+        bulk_g2s(smem + st * TC_A_IMG, src + (size_t)s * TC_A_IMG, TC_A_IMG, &a_full[st]);
+        if (++st == TC_NA) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      // ================= MMA issuer: per K chunk and plane, A_hi.[B_hi, B_lo] then A_lo.B_hi into the plane's accumulator =================
+      constexpr uint32_t idesc = umma_idesc_f16(TV, TC_NB);
+      const uint32_t adesc0 = umma_desc_sw128_lo(smem0), bdesc0 = umma_desc_sw128_lo(smem0 + TC_OFF_B);
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      uint32_t st = 0, ph = 0;
+      for (int kc = 0; kc < TC_CHUNKS; ++kc) {
+        const int nks = min(4, TC_KSTEPS - 4 * kc);
+        const uint32_t b_hi = bdesc0 + (uint32_t)(kc * 2) * (TC_B_IMG >> 4), b_lo = b_hi + (TC_B_IMG >> 4);
+        for (int c = 0; c < 3; ++c) {
+          const uint32_t d = tmem_base + c * TC_NB;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&a_full[st], ph);
+            tc_fence_after();
+            const uint32_t ad = adesc0 + st * (TC_A_IMG >> 4);
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint32_t ko = ks * 2;                                   // +32 bytes along K inside the swizzle row
+              if (h == 0) {
+                umma_f16_lohi(d, ad + ko, b_hi + ko, idesc, (kc | ks) != 0);
+                umma_f16_lohi(d, ad + ko, b_lo + ko, idesc, 1);
+              } else {
+                umma_f16_lohi(d, ad + ko, b_hi + ko, idesc, 1);
+              }
+            }
+            umma_commit(&a_empty[st]);
+            if (++st == TC_NA) { st = 0; ph ^= 1; }
+          }
+        }
+      }
+      umma_commit(acc_full);
+    }
+  }
+  __syncwarp();
+
+  // ================= epilogue, all 8 warps: v_posed from TMEM, 4-sparse skinning, stores =================
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
+  const int v = tile * TV + row;                        // < VPAD: the packed arrays are zero padded
+  const int4 ji = *reinterpret_cast<const int4*>(a.widx + v * 4);
+  const float4 jw = *reinterpret_cast<const float4*>(a.wval + v * 4);
+  const int wj[4] = {ji.x, ji.y, ji.z, ji.w};
+  const float ww[4] = {jw.x, jw.y, jw.z, jw.w};
+  float ainv[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) ainv[c] = a.ainv[(tile * 3 + c) * TV + row];
+  mbar_wait(t_full, 0);
+  mbar_wait(acc_full, 0);
+  tc_fence_after();
+  uint32_t d0[32], d1[32], d2[32];
+  const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + half * 32;
+  tmem_ld_32x32(tacc, d0);
+  tmem_ld_32x32(tacc + TC_NB, d1);
+  tmem_ld_32x32(tacc + 2 * TC_NB, d2);
+  tmem_ld_wait();
+  const float4* T = reinterpret_cast<const float4*>(smem + TC_OFF_T);
+  const int body0 = half * 32;
+  const bool vok = v < V;
+#pragma unroll
+  for (int b = 0; b < 32; ++b) {
+    const int body = body0 + b;
+    const int gb = group * TC_NB + body;
+    if (gb < a.B) {
+      const float vp0 = __uint_as_float(d0[b]) * ainv[0], vp1 = __uint_as_float(d1[b]) * ainv[1], vp2 = __uint_as_float(d2[b]) * ainv[2];
+      float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4* tj = T + ((size_t)body * NJ + wj[e]) * 3;
+        const float4 r0 = tj[0], r1 = tj[1], r2 = tj[2];
+        const float w = ww[e];
+        T0.x = fmaf(w, r0.x, T0.x); T0.y = fmaf(w, r0.y, T0.y); T0.z = fmaf(w, r0.z, T0.z); T0.w = fmaf(w, r0.w, T0.w);
+        T1.x = fmaf(w, r1.x, T1.x); T1.y = fmaf(w, r1.y, T1.y); T1.z = fmaf(w, r1.z, T1.z); T1.w = fmaf(w, r1.w, T1.w);
+        T2.x = fmaf(w, r2.x, T2.x); T2.y = fmaf(w, r2.y, T2.y); T2.z = fmaf(w, r2.z, T2.z); T2.w = fmaf(w, r2.w, T2.w);
+      }
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      if (a.transl) { t0 = __ldg(a.transl + (size_t)gb * 3); t1 = __ldg(a.transl + (size_t)gb * 3 + 1); t2 = __ldg(a.transl + (size_t)gb * 3 + 2); }
+      if (vok) {
+        float* o = a.verts + ((size_t)gb * V + v) * 3;
+        o[0] = T0.x * vp0 + T0.y * vp1 + T0.z * vp2 + T0.w + t0;
+        o[1] = T1.x * vp0 + T1.y * vp1 + T1.z * vp2 + T1.w + t1;
+        o[2] = T2.x * vp0 + T2.y * vp1 + T2.z * vp2 + T2.w + t2;
+        if (a.save_vposed) {
+          float* sv = a.save_vposed + ((size_t)gb * V + v) * 3;
+          sv[0] = vp0; sv[1] = vp1; sv[2] = vp2;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+}  // namespace straps
+
+using namespace straps;
+
+// ---- host side: pack Apk once, run the two kernels ----
+static inline uint16_t f2h_bits(float f) {          // round-to-nearest-even fp32 -> fp16 bits (cuda_fp16.h host path)
+  const __half h = __float2half_rn(f);
+  uint16_t b;
+  memcpy(&b, &h, 2);
+  return b;
+}
+static inline float h2f_bits(uint16_t b) {
+  __half h;
+  memcpy(&h, &b, 2);
+  return __half2float(h);
+}
+
+// Apk[(v, c), k] rows scaled to [2^13, 2^14), split into fp16 hi / lo, laid out as the SWIZZLE_128B images lbs_tc_kernel streams:
+// image (tile, kc, c, h) = 128 rows of 128 bytes, 16-byte unit u of row r at physical unit u ^ (r & 7).
+int straps::smpl_tc_pack(const float* v_template, const float* shapedirs, const float* posedirs, std::vector<unsigned char>& apk,
+                         std::vector<float>& ainv) {
+  apk.assign((size_t)NTILES * TC_STAGES_PER_TILE * TC_A_IMG, 0);
+  ainv.assign((size_t)NTILES * 3 * TV, 0.f);
+  std::vector<float> rowv(TC_K);
+  for (int v = 0; v < V; ++v)
+    for (int c = 0; c < 3; ++c) {
+      float mx = 0.f;
+      for (int k = 0; k < TC_K; ++k) {
+        float x = 0.f;
+        if (k < NPF) x = posedirs[(size_t)k * V * 3 + v * 3 + c];
+        else if (k < NPF + STRAPS_NUM_BETAS) x = shapedirs[((size_t)v * 3 + c) * STRAPS_NUM_BETAS + (k - NPF)];
+        else if (k == NPF + STRAPS_NUM_BETAS) x = v_template[v * 3 + c];
+        rowv[k] = x;
+        mx = std::max(mx, std::fabs(x));
+      }
+      int e = 0;
+      if (mx > 0.f) { std::frexp(mx, &e); e = 14 - e; }                        // mx * 2^e in [2^13, 2^14)
+      const float sc = std::ldexp(1.f, e);
+      const int tile = v / TV, r = v % TV;
+      ainv[((size_t)tile * 3 + c) * TV + r] = 1.f / (sc * TC_BSCALE);
+      for (int k = 0; k < TC_K; ++k) {
+        const float x = rowv[k] * sc;
+        const uint16_t hb = f2h_bits(x);
+        const uint16_t lb = f2h_bits(x - h2f_bits(hb));
+        const int kc = k >> 6, u = (k & 63) >> 3, el = k & 7;
+        const size_t img = ((size_t)tile * TC_STAGES_PER_TILE + (size_t)(kc * 3 + c) * 2) * TC_A_IMG;
+        const size_t off = (size_t)r * 128 + (size_t)((u ^ (r & 7)) << 4) + (size_t)el * 2;
+        memcpy(&apk[img + off], &hb, 2);
+        memcpy(&apk[img + TC_A_IMG + off], &lb, 2);
+      }
+    }
+  return 0;
+}
+
+int straps::smpl_tc_forward(straps_smpl* m, const float* global_orient, int64_t go_stride, const float* body_pose, int64_t bp_stride,
+                            const float* betas, int64_t betas_stride, const float* transl, int batch, int pose2rot, float* vertices,
+                            float* joints, float* save_vposed, float* save_A, cudaStream_t st) {
+  const int groups = (batch + TC_NB - 1) / TC_NB;
+  const int b_pad = groups * TC_NB;
+  const size_t need = (size_t)groups * TC_B_BYTES + (size_t)b_pad * NJ * 12 * sizeof(float);
+  if (need > m->tc_scratch_bytes) {
+    // grows with the largest batch seen (first call / warm-up; never inside a CUDA-graph capture of a warmed-up shape)
+    STRAPS_CUDA(cudaStreamSynchronize(st));
+    if (m->tc_scratch) cudaFree(m->tc_scratch);
+    m->tc_scratch = nullptr;
+    m->tc_scratch_bytes = 0;
+    STRAPS_CUDA(cudaMalloc(&m->tc_scratch, need));
+    m->tc_scratch_bytes = need;
+  }
+  unsigned char* bimg = static_cast<unsigned char*>(m->tc_scratch);
+  float* aout = reinterpret_cast<float*>(bimg + (size_t)groups * TC_B_BYTES);
+  ChainArgs ca;
+  ca.go = global_orient; ca.bp = body_pose; ca.betas = betas; ca.transl = transl;
+  ca.go_stride = go_stride; ca.bp_stride = bp_stride; ca.betas_stride = betas_stride;
+  ca.B = batch; ca.B_pad = b_pad; ca.pose2rot = pose2rot; ca.joints = joints; ca.aout = aout; ca.bimg = bimg; ca.save_A = save_A;
+  smpl_chain_kernel<<<b_pad / CH_TB, 128, 0, st>>>(m->d, ca);
+  STRAPS_LAUNCH_CHECK();
+  static PerDeviceOnce attr_once;
+  const int dev = current_device();
+  if (attr_once.need(dev)) {
+    STRAPS_CUDA(cudaFuncSetAttribute(lbs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    attr_once.done(dev);
+  }
+  LbsTcArgs la;
+  la.apk = m->tc_apk; la.ainv = m->tc_ainv; la.bimg = bimg; la.aout = aout; la.widx = m->d.widx; la.wval = m->d.wval;
+  la.transl = transl; la.B = batch; la.verts = vertices; la.save_vposed = save_vposed;
+  lbs_tc_kernel<<<dim3(NTILES, groups), TC_THREADS, TC_SMEM, st>>>(la);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
+}

@@ -218,6 +218,25 @@ def rows_metric(pred, target, sum_slot, dim, pred_add=0.0, pred_mul=1.0, squared
                                             1 if squared else 0, _p(sum_slot), _stream(pred.device)), 'straps_rows_metric')
 
 
+_JOINT_INDEX = {}
+
+
+def select_joints(joints, *index_lists):
+    """`joints[:, a, :][:, b, :]...` with the index lists of config.py (ALL_JOINTS_TO_COCO_MAP, ALL_JOINTS_TO_H36M_MAP, H36M_TO_J14;
+    the reference indexes with the Python lists themselves, train/train_synthetic_otf_rendering.py:207-215) as ONE index_select with a
+    cached device index: same values, but no host->device copy of the list per call (which breaks CUDA-graph capture) and an
+    index_add backward instead of the sort-based index_put of advanced indexing."""
+    key = (tuple(tuple(int(i) for i in l) for l in index_lists), joints.device)
+    idx = _JOINT_INDEX.get(key)
+    if idx is None:
+        composed = list(key[0][0])
+        for l in key[0][1:]:
+            composed = [composed[i] for i in l]
+        idx = torch.tensor(composed, dtype=torch.long, device=joints.device)
+        _JOINT_INDEX[key] = idx
+    return joints.index_select(1, idx)
+
+
 def accumulate(src, scale, dst):
     """dst[:n] += scale * src  (src CUDA float32 [n], dst CUDA float64)."""
     _need_cuda(src, 'src')

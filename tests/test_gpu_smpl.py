@@ -166,3 +166,71 @@ def test_proxy_representation_synthesis_bit_exact(assets_root):
     # the reference assembles the regressor input like this (train/...:178-182)
     x = torch.cat([b.unsqueeze(1)[:4], hm], dim=1)
     assert x.shape == (4, 18, 256, 256)
+
+
+def _lbs_mode(mode):
+    """STRAPS_LBS is read by the library on every SMPL forward: 'simt' keeps the CUDA-core kernel, unset = tensor cores for B >= 32."""
+    import os
+    if mode is None:
+        os.environ.pop('STRAPS_LBS', None)
+    else:
+        os.environ['STRAPS_LBS'] = mode
+
+
+@pytest.mark.parametrize('B', [32, 40, 64, 127, 200])
+def test_tensor_core_lbs_against_oracle_and_cuda_core_kernel(assets_root, smpl_oracle, B):
+    """Batches >= 32 take smpl_tc.cu (blend shapes as a 3-pass fp16-split tcgen05 GEMM).  Held to 1e-5 against the oracle
+    (smplx lbs()) -- ten times tighter than north_star -- and compared with the CUDA-core kernel on the same
+    inputs; ragged body groups (B not a multiple of 64), axis-angle input and transl included."""
+    smpl = _smpl(B)
+    betas, pose6d, aa = smpl_inputs(B, 900 + B)
+    betas *= 2.0                                           # +-6 sigma shapes: large Bm entries
+    transl = np.random.RandomState(B).normal(0, 1, (B, 3)).astype(np.float32)
+    R, v, j = _oracle_rotmats(smpl_oracle, pose6d, betas)
+    Rg, bg, tg = R.to(DEV), torch.from_numpy(betas).to(DEV), torch.from_numpy(transl).to(DEV)
+    t = torch.from_numpy(transl)[:, None]
+    try:
+        outs = {}
+        for mode in (None, 'simt'):
+            _lbs_mode(mode)
+            with torch.no_grad():
+                o = smpl(body_pose=Rg[:, 1:], global_orient=Rg[:, :1], betas=bg, transl=tg, pose2rot=False)
+                oa = smpl(body_pose=torch.from_numpy(aa[:, 3:]).to(DEV), global_orient=torch.from_numpy(aa[:, :3]).to(DEV), betas=bg)
+            outs[mode] = (o.vertices.cpu(), o.joints.cpu(), oa.vertices.cpu(), oa.joints.cpu())
+    finally:
+        _lbs_mode(None)
+    with torch.no_grad():
+        va, ja = smpl_oracle.forward(betas=torch.from_numpy(betas), body_pose=torch.from_numpy(aa[:, 3:]),
+                                     global_orient=torch.from_numpy(aa[:, :3]), pose2rot=True)
+    tc, simt = outs[None], outs['simt']
+    assert rel_err(tc[0].numpy(), (v + t).numpy()) < 1e-5
+    assert rel_err(tc[1].numpy(), (j + t).numpy()) < 1e-5
+    assert rel_err(tc[2].numpy(), va.numpy()) < 1e-5
+    assert rel_err(tc[3].numpy(), ja.numpy()) < 1e-5
+    for a, b in zip(tc, simt):
+        assert rel_err(a.numpy(), b.numpy()) < 3e-6
+    assert rel_err(tc[1][:, :24].numpy(), simt[1][:, :24].numpy()) < 1e-6   # chain kernel = the CUDA-core kernel's prologue
+
+
+def test_tensor_core_lbs_training_outputs(assets_root):
+    """The training path saves v_posed and the skinning transforms for the backward kernels: same values from both forward kernels,
+    and the gradients that follow from them agree."""
+    B = 64
+    smpl = _smpl(B)
+    betas, pose6d, _ = smpl_inputs(B, 77)
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    grads = {}
+    try:
+        for mode in (None, 'simt'):
+            _lbs_mode(mode)
+            p = torch.from_numpy(pose6d).to(DEV).requires_grad_(True)
+            b = torch.from_numpy(betas).to(DEV).requires_grad_(True)
+            R = rot6d_to_rotmat(p).view(B, 24, 3, 3)
+            out = smpl(body_pose=R[:, 1:], global_orient=R[:, :1], betas=b, pose2rot=False)
+            w = torch.linspace(-1, 1, 6890 * 3, device=DEV).view(1, 6890, 3)
+            ((out.vertices * w).sum() + (out.joints ** 2).sum()).backward()
+            grads[mode] = (p.grad.cpu(), b.grad.cpu(), out.vertices.detach().cpu())
+    finally:
+        _lbs_mode(None)
+    for a, b in zip(grads[None], grads['simt']):
+        assert rel_err(a.numpy(), b.numpy()) < 1e-5

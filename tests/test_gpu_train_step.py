@@ -52,11 +52,12 @@ def _loss(reg, crit, smpl, x, labels):
     import config
     from utils.rigid_transform_utils import rot6d_to_rotmat
     from utils.cam_utils import orthographic_project_torch
+    from straps_b200.ops import select_joints
     cam, pose, shape = reg(x)
     R = rot6d_to_rotmat(pose.contiguous()).view(-1, 24, 3, 3)
     out = smpl(body_pose=R[:, 1:], global_orient=R[:, 0].unsqueeze(1), betas=shape, pose2rot=False)
-    outs = {'verts': out.vertices, 'joints2D': orthographic_project_torch(out.joints[:, config.ALL_JOINTS_TO_COCO_MAP, :], cam),
-            'joints3D': out.joints[:, config.ALL_JOINTS_TO_H36M_MAP, :][:, config.H36M_TO_J14, :], 'shape_params': shape,
+    outs = {'verts': out.vertices, 'joints2D': orthographic_project_torch(select_joints(out.joints, config.ALL_JOINTS_TO_COCO_MAP), cam),
+            'joints3D': select_joints(out.joints, config.ALL_JOINTS_TO_H36M_MAP, config.H36M_TO_J14), 'shape_params': shape,
             'pose_params_rot_matrices': R}
     return crit(labels, outs)[0]
 
