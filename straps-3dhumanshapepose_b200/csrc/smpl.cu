@@ -418,7 +418,7 @@ extern "C" int straps_smpl_create(straps_smpl_t** out, const float* v_template, 
                "straps_smpl_create: null argument");
   straps_smpl* m = new straps_smpl();
   memset(&m->d, 0, sizeof(SmplDev));
-  m->tc_apk = nullptr; m->tc_ainv = nullptr; m->tc_scratch = nullptr; m->tc_scratch_bytes = 0;
+  m->tc_apk = nullptr; m->tc_ainv = nullptr; m->tc_wk = nullptr; m->tc_at_base = nullptr; m->tc_scratch = nullptr; m->tc_scratch_bytes = 0;
   // --- kinematic tree -> levels
   int depth[NJ];
   for (int j = 0; j < NJ; ++j) {
@@ -505,12 +505,13 @@ extern "C" int straps_smpl_create(straps_smpl_t** out, const float* v_template, 
   rc |= upload(m, ptr, &m->d.csr_ptr);
   rc |= upload(m, idx, &m->d.csr_idx);
   rc |= upload(m, val, &m->d.csr_val);
-  if (!rc && sparse4) {          // operands of the tensor-core LBS (batches >= 32)
-    std::vector<unsigned char> apk;
+  if (!rc) {                     // operands of the tensor-core LBS (smpl_tc.cu; dense or sparse skinning weights alike)
+    std::vector<unsigned char> apk, wk;
     std::vector<float> ainv;
-    smpl_tc_pack(v_template, shapedirs, posedirs, apk, ainv);
+    smpl_tc_pack(v_template, shapedirs, posedirs, lbs_weights, apk, ainv, wk);
     rc |= upload(m, apk, &m->tc_apk);
     rc |= upload(m, ainv, &m->tc_ainv);
+    rc |= upload(m, wk, &m->tc_wk);
   }
   if (rc) { straps_smpl_destroy(m); return 1; }
   *out = m;
@@ -553,11 +554,12 @@ static int smpl_forward_impl(const straps_smpl_t* m, const float* global_orient,
   a.go_stride = go_stride; a.bp_stride = bp_stride; a.betas_stride = betas_stride;
   a.B = batch; a.pose2rot = pose2rot; a.verts = vertices; a.joints = joints;
   a.save_vposed = save_vposed; a.save_A = save_A;
-  // batches >= 32 with the usual <= 4 skinning weights per vertex: blend shapes on the tensor cores (smpl_tc.cu);
-  // STRAPS_LBS=simt keeps the CUDA-core kernel (parity tests compare the two)
+  // batches >= tc_min: blend shapes and skinning transforms on the tensor cores (smpl_tc.cu); STRAPS_LBS=simt keeps the CUDA-core
+  // kernel, STRAPS_LBS=tc uses the tensor cores at every batch size (parity tests and tools/bench_lbs.py compare the two)
   {
     const char* e = getenv("STRAPS_LBS");
-    if (batch >= 32 && m->sparse4 && m->tc_apk && !(e && e[0] == 's')) {
+    const int tc_min = (e && e[0] == 't') ? 1 : 32;
+    if (batch >= tc_min && m->tc_apk && !(e && e[0] == 's')) {
       if (smpl_tc_forward(const_cast<straps_smpl*>(m), global_orient, go_stride, body_pose, bp_stride, betas, betas_stride, transl, batch,
                           pose2rot, vertices, joints, save_vposed, save_A, st))
         return 1;

@@ -48,13 +48,15 @@ struct straps_smpl {
   // and a per-call scratch (Bm images + skinning transforms) that grows with the largest batch seen
   const unsigned char* tc_apk;
   const float* tc_ainv;
+  const unsigned char* tc_wk;
+  unsigned char* tc_at_base;
   void* tc_scratch;
   size_t tc_scratch_bytes;
 };
 
 namespace straps {
-int smpl_tc_pack(const float* v_template, const float* shapedirs, const float* posedirs, std::vector<unsigned char>& apk,
-                 std::vector<float>& ainv);
+int smpl_tc_pack(const float* v_template, const float* shapedirs, const float* posedirs, const float* lbs_weights,
+                 std::vector<unsigned char>& apk, std::vector<float>& ainv, std::vector<unsigned char>& wk);
 int smpl_tc_forward(straps_smpl* m, const float* global_orient, int64_t go_stride, const float* body_pose, int64_t bp_stride,
                     const float* betas, int64_t betas_stride, const float* transl, int batch, int pose2rot, float* vertices,
                     float* joints, float* save_vposed, float* save_A, cudaStream_t st);

@@ -9,15 +9,20 @@
 //                                                            Apk = [posedirs ; shapedirs ; v_template], K padded to 256
 //
 // Kernel 1 (smpl_chain_kernel, 8 bodies per CTA): rotations (Rodrigues or given), pre-reduced rest joints, the 24-joint kinematic
-//   chain (the code of lbs_kernel's prologue, same arithmetic order) -> skinning transforms A[b][24][3x4] and the 24 posed joints;
-//   also writes Bm as fp16 hi / lo (scaled by 2^10) directly in the SWIZZLE_128B shared-memory image the MMA reads.
-// Kernel 2 (lbs_tc_kernel, CTA = 128 vertices x 64 bodies): for each coordinate plane c an M = 128, N = 64 accumulator in TMEM;
-//   K runs over 14 steps of 16 with the 3-pass fp16 split (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi: 22 mantissa bits, plain low halves:
-//   the rows of Apk are pre-scaled by a power of two so that both halves are fp16-normal).  Apk is packed ONCE at create time as
-//   ready-made swizzled 16 KB images, so operands arrive by plain bulk-async copies (no tensor maps): A through a 4-stage ring,
-//   Bm (64 KB) and the group's transforms (72 KB) up front.  Epilogue (all 8 warps): TMEM -> v_posed, 4-sparse skinning with the
-//   transforms in shared memory, + transl, coalesced stores of the vertices (and of v_posed for the training path).
-// Roofline: HBM by contract (20,587,320 B + 84,664 B per body per launch); tensor work 3 x 2 x 224 x 20736 FLOP per body.
+//   chain (the code of lbs_kernel's prologue, same arithmetic order) -> the 24 posed joints and the skinning transforms A[b][24][3x4];
+//   writes BOTH tensor-core operands of its body group as ready-made swizzled shared-memory images: Bm (fp16 hi / lo, x 2^10,
+//   SWIZZLE_128B) and, per output row r, the transposed transforms AT_r[(body, column)][joint] (fp16 hi / lo, x 2^10, SWIZZLE_64B).
+// Kernel 2 (lbs_tc_kernel, CTA = 128 vertices x 64 bodies), two GEMMs into TMEM:
+//   (i)  blend: for each coordinate plane c an M = 128, N = 64 accumulator; K = 14 steps of 16 with the 3-pass fp16 split
+//        (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi: 22 mantissa bits; the rows of Apk are pre-scaled by a power of two so that both halves
+//        are fp16-normal).  Apk is packed ONCE at create time as swizzled 16 KB images, so operands arrive by plain bulk-async copies
+//        (no tensor maps) through a 5-stage ring.
+//   (ii) skinning transforms: T_r[v][(body, column)] = sum_j W[v][j] A[body][j][r][column] -- M = 128 vertices, N = 256, K = 24 (32),
+//        again 3 passes, one output row r at a time (TMEM holds 192 + 256 columns).  The first version of this kernel blended the
+//        transforms on the CUDA cores from shared memory (4 joints x 3 float4 per vertex and body): 12 bank-conflicted LDS.128 per
+//        output made the epilogue the whole cost (B = 4096: 563 us, 24 us per CTA against 3 us of MMAs).
+//   Epilogue (all 8 warps): v_posed from TMEM once (96 registers), then per row r: T_r from TMEM, 4 FMAs, + transl, store.
+// Roofline: HBM by contract (20,587,320 B + 84,664 B per body per launch); tensor work 3 x 2 x (224 x 20736 + 32 x 128 x 54 x 12) FLOP / body.
 #include "smpl.h"
 #include <cuda_fp16.h>
 #include <cmath>
@@ -25,33 +30,44 @@
 
 namespace straps {
 
-constexpr int TC_K = 256;                                   // padded K
+constexpr int TC_K = 256;                                   // padded K of the blend GEMM
 constexpr int TC_KREAL = NPF + STRAPS_NUM_BETAS + 1;        // 218
 constexpr int TC_KSTEPS = (TC_KREAL + 15) / 16;             // 14
 constexpr int TC_CHUNKS = 4;                                // K chunks of 64 elements (one SWIZZLE_128B row each)
-constexpr int TC_NB = 64;                                   // bodies per CTA = MMA N
+constexpr int TC_NB = 64;                                   // bodies per CTA = MMA N of the blend GEMM
 constexpr int TC_A_IMG = TV * 128;                          // bytes of one [128 vertices x 64 K] fp16 image
 constexpr int TC_B_IMG = TC_NB * 128;                       // bytes of one [64 bodies x 64 K] fp16 image
 constexpr int TC_STAGES_PER_TILE = TC_CHUNKS * 3 * 2;       // (chunk, plane, hi | lo) = 24 A images per vertex tile
-constexpr int TC_NA = 4;                                    // A ring stages
-constexpr float TC_BSCALE = 1024.f;                         // Bm is multiplied by 2^10 before its fp16 split
-constexpr int TC_T_BYTES = TC_NB * NJ * 12 * 4;             // transforms of one body group: 73,728 B
+constexpr int TC_NA = 5;                                    // A ring stages
+constexpr float TC_BSCALE = 1024.f;                         // Bm and the transforms are multiplied by 2^10 before their fp16 split
+constexpr float TC_WSCALE = 16384.f;                        // skinning weights (<= 1) by 2^14
 constexpr int TC_B_BYTES = TC_CHUNKS * 2 * TC_B_IMG;        // Bm images of one body group: 65,536 B
+// skinning-transform GEMM: K = 32 joint slots (24 used) = one SWIZZLE_64B row of 64 bytes
+constexpr int TC_TK = 32;
+constexpr int TC_TN = TC_NB * 4;                            // 256 = (body, column of the 3x4 transform)
+constexpr int TC_W_IMG = TV * 64;                           // [128 vertices x 32 joints] fp16: 8 KB
+constexpr int TC_W_BYTES = 2 * TC_W_IMG;                    // hi + lo
+constexpr int TC_AT_IMG = TC_TN * 64;                       // [256 x 32 joints] fp16: 16 KB
+constexpr int TC_AT_BYTES = 2 * TC_AT_IMG;                  // hi + lo of one output row r
+constexpr int TC_AT_GROUP = 3 * TC_AT_BYTES;                // 98,304 B per body group in HBM
 constexpr int TC_OFF_B = TC_NA * TC_A_IMG;
-constexpr int TC_OFF_T = TC_OFF_B + TC_B_BYTES;
-constexpr int TC_OFF_BAR = TC_OFF_T + TC_T_BYTES;
+constexpr int TC_OFF_W = TC_OFF_B + TC_B_BYTES;
+constexpr int TC_OFF_AT = TC_OFF_W + TC_W_BYTES;            // two slots: rows 0 and 1 up front, row 2 re-uses slot 0
+constexpr int TC_OFF_BAR = TC_OFF_AT + 2 * TC_AT_BYTES;
 constexpr int TC_SMEM = TC_OFF_BAR + 256 + 1024;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 320;                             // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_COL_T = 3 * TC_NB;                         // TMEM: columns [0, 192) v_posed planes, [192, 448) T_r
 static_assert(TC_SMEM <= 232448, "lbs_tc_kernel shared memory");
 static_assert(TC_KREAL <= TC_K && TC_KSTEPS <= TC_CHUNKS * 4, "K padding");
+static_assert(NJ <= TC_TK && TC_COL_T + TC_TN <= 512, "transform GEMM shape");
 
 struct LbsTcArgs {
   const unsigned char* apk;     // [54][24] images of TC_A_IMG bytes
   const float* ainv;            // [54][3][128] 1 / (row scale * TC_BSCALE)
+  const unsigned char* wk;      // [54][2] images of TC_W_IMG bytes
   const unsigned char* bimg;    // [groups][4][2] images of TC_B_IMG bytes
-  const float* aout;            // [groups * 64][24][12]
-  const int* widx;
-  const float* wval;
+  const unsigned char* atimg;   // [groups][3][2] images of TC_AT_IMG bytes
   const float* transl;          // [B][3] or null
   int B;
   float* verts;
@@ -75,6 +91,14 @@ __device__ __forceinline__ void tc_rodrigues(const float r[3], float* R) {
     }
 }
 
+__device__ __forceinline__ void tc_split_store(unsigned char* hi_img, size_t lo_distance, size_t off, float v) {
+  v = fminf(fmaxf(v, -65504.f), 65504.f);
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  *reinterpret_cast<__half*>(hi_img + off) = h;
+  *reinterpret_cast<__half*>(hi_img + off + lo_distance) = l;
+}
+
 struct ChainArgs {
   const float* go;
   const float* bp;
@@ -83,9 +107,9 @@ struct ChainArgs {
   long long go_stride, bp_stride, betas_stride;
   int B, B_pad, pose2rot;
   float* joints;                // [B][90][3]: rows 0..23 written here
-  float* aout;                  // [B_pad][24][12]
   unsigned char* bimg;
-  float* save_A;                // training: the same transforms again in the caller's tensor, or null
+  unsigned char* atimg;
+  float* save_A;                // training: the transforms as fp32 [B][24][12] in the caller's tensor, or null
 };
 
 constexpr int CH_TB = 8;        // bodies per CTA of the chain kernel
@@ -121,7 +145,7 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
     }
   }
   __syncthreads();
-  // Bm = [R_j - I (j = 1..23) | betas | 1 | 0...] * 2^10, fp16 hi / lo, in the swizzled image of its body group
+  // Bm = [R_j - I (j = 1..23) | betas | 1 | 0...] * 2^10, fp16 hi / lo, in the SWIZZLE_128B image of its body group
   for (int i = tid; i < CH_TB * TC_K; i += 128) {
     const int b = i / TC_K, k = i % TC_K;
     const int gb = b0 + b;
@@ -132,13 +156,9 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
       else if (k < NPF + STRAPS_NUM_BETAS) v = sbeta[b][k - NPF];
       else if (k == NPF + STRAPS_NUM_BETAS) v = 1.f;
     }
-    v = fminf(fmaxf(v * TC_BSCALE, -65504.f), 65504.f);
-    const __half h = __float2half_rn(v);
-    const __half l = __float2half_rn(v - __half2float(h));
     const int g = gb / TC_NB, r = gb % TC_NB, kc = k >> 6, u = (k & 63) >> 3, e = k & 7;
     const size_t off = ((size_t)(g * TC_CHUNKS + kc) * 2) * TC_B_IMG + (size_t)r * 128 + (size_t)((u ^ (r & 7)) << 4) + (size_t)e * 2;
-    *reinterpret_cast<__half*>(a.bimg + off) = h;
-    *reinterpret_cast<__half*>(a.bimg + off + TC_B_IMG) = l;
+    tc_split_store(a.bimg, TC_B_IMG, off, v * TC_BSCALE);
   }
   for (int i = tid; i < CH_TB * NJ * 3; i += 128) {
     int b = i / (NJ * 3), jc = i % (NJ * 3);
@@ -169,16 +189,27 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
     }
     __syncthreads();
   }
+  // skinning transforms A = [G_rot | G_t - G_rot J_rest]: fp32 for the training path, and as the B operand of the transform GEMM --
+  // image (group, r, hi | lo) = 256 rows n = (body in group) * 4 + column, 64 bytes each (32 joint slots), SWIZZLE_64B: the 16-byte
+  // unit u of row n sits at physical unit u ^ ((n >> 1) & 3).  Joint slots 24..31 stay zero from the memset at allocation.
   for (int i = tid; i < CH_TB * NJ * 3; i += 128) {
     int b = i / (NJ * 3), q = i % (NJ * 3), j = q / 3, r = q % 3;
     const int gb = b0 + b;
     if (gb >= a.B_pad) continue;
     const float* g = &sG[b][j][r * 4];
     const float t = g[3] - (g[0] * sJ[b][j][0] + g[1] * sJ[b][j][1] + g[2] * sJ[b][j][2]);
-    const float4 row = (b < nb) ? make_float4(g[0], g[1], g[2], t) : make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(a.aout + ((size_t)gb * NJ + j) * 12 + r * 4) = row;
-    if (b < nb) {
-      if (a.save_A) *reinterpret_cast<float4*>(a.save_A + ((size_t)gb * NJ + j) * 12 + r * 4) = row;
+    const bool live = b < nb;
+    const float row[4] = {live ? g[0] : 0.f, live ? g[1] : 0.f, live ? g[2] : 0.f, live ? t : 0.f};
+    const int grp = gb / TC_NB, bl = gb % TC_NB;
+    unsigned char* img = a.atimg + (size_t)grp * TC_AT_GROUP + (size_t)r * TC_AT_BYTES;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const int n = bl * 4 + c4;
+      const size_t off = (size_t)n * 64 + (size_t)(((j >> 3) ^ ((n >> 1) & 3)) << 4) + (size_t)(j & 7) * 2;
+      tc_split_store(img, TC_AT_IMG, off, row[c4] * TC_BSCALE);
+    }
+    if (live) {
+      if (a.save_A) *reinterpret_cast<float4*>(a.save_A + ((size_t)gb * NJ + j) * 12 + r * 4) = make_float4(row[0], row[1], row[2], row[3]);
       const float tr = a.transl ? a.transl[(size_t)gb * 3 + r] : 0.f;
       a.joints[((size_t)gb * STRAPS_NUM_SUPERSET_JOINTS + j) * 3 + r] = g[3] + tr;
     }
@@ -191,19 +222,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
   uint64_t* a_full = bars;                 // [TC_NA]
   uint64_t* a_empty = bars + TC_NA;        // [TC_NA]
-  uint64_t* b_full = bars + 2 * TC_NA;
-  uint64_t* t_full = b_full + 1;
-  uint64_t* acc_full = t_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* b_full = bars + 2 * TC_NA;     // Bm + W
+  uint64_t* at_full = b_full + 1;          // [2] transform operand slots
+  uint64_t* at_free = at_full + 2;         // slot 0 may be refilled (row 0's MMAs have completed)
+  uint64_t* vp_full = at_free + 1;         // blend accumulators complete
+  uint64_t* t_full = vp_full + 1;          // T_r complete
+  uint64_t* t_empty = t_full + 1;          // every epilogue thread has read T_r
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, group = blockIdx.y;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < TC_NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    mbar_init(b_full, 1); mbar_init(t_full, 1); mbar_init(acc_full, 1);
+    mbar_init(b_full, 1); mbar_init(&at_full[0], 1); mbar_init(&at_full[1], 1); mbar_init(at_free, 1);
+    mbar_init(vp_full, 1); mbar_init(t_full, 1); mbar_init(t_empty, TC_EPI_THREADS);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<256>(tmem_slot);
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -212,11 +247,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
 
   if (warp == 0) {
     if (elect_one_sync()) {
-      // ================= producer: Bm and the transforms up front, then the 24 A images of this vertex tile =================
-      mbar_arrive_expect_tx(b_full, TC_B_BYTES);
+      // ================= producer: group operands up front, then the 24 A images of this vertex tile, then transform row 2 =================
+      mbar_arrive_expect_tx(b_full, TC_B_BYTES + TC_W_BYTES);
       bulk_g2s(smem + TC_OFF_B, a.bimg + (size_t)group * TC_B_BYTES, TC_B_BYTES, b_full);
-      mbar_arrive_expect_tx(t_full, TC_T_BYTES);
-      bulk_g2s(smem + TC_OFF_T, a.aout + (size_t)group * TC_NB * NJ * 12, TC_T_BYTES, t_full);
+      bulk_g2s(smem + TC_OFF_W, a.wk + (size_t)tile * TC_W_BYTES, TC_W_BYTES, b_full);
+      const unsigned char* at = a.atimg + (size_t)group * TC_AT_GROUP;
+      for (int r = 0; r < 2; ++r) {
+        mbar_arrive_expect_tx(&at_full[r], TC_AT_BYTES);
+        bulk_g2s(smem + TC_OFF_AT + r * TC_AT_BYTES, at + (size_t)r * TC_AT_BYTES, TC_AT_BYTES, &at_full[r]);
+      }
       const unsigned char* src = a.apk + (size_t)tile * TC_STAGES_PER_TILE * TC_A_IMG;
       uint32_t st = 0, ph = 1;
       for (int s = 0; s < TC_STAGES_PER_TILE; ++s) {
@@ -225,10 +264,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
         bulk_g2s(smem + st * TC_A_IMG, src + (size_t)s * TC_A_IMG, TC_A_IMG, &a_full[st]);
         if (++st == TC_NA) { st = 0; ph ^= 1; }
       }
+      mbar_wait(at_free, 0);
+      mbar_arrive_expect_tx(&at_full[0], TC_AT_BYTES);
+      bulk_g2s(smem + TC_OFF_AT, at + (size_t)2 * TC_AT_BYTES, TC_AT_BYTES, &at_full[0]);
     }
   } else if (warp == 1) {
     if (elect_one_sync()) {
-      // ================= MMA issuer: per K chunk and plane, A_hi.[B_hi, B_lo] then A_lo.B_hi into the plane's accumulator =================
+      // ================= MMA issuer =================
+      // (i) blend: per K chunk and plane, A_hi.[B_hi, B_lo] then A_lo.B_hi into the plane's accumulator
       constexpr uint32_t idesc = umma_idesc_f16(TV, TC_NB);
       const uint32_t adesc0 = umma_desc_sw128_lo(smem0), bdesc0 = umma_desc_sw128_lo(smem0 + TC_OFF_B);
       mbar_wait(b_full, 0);
@@ -258,69 +301,102 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
           }
         }
       }
-      umma_commit(acc_full);
+      umma_commit(vp_full);
+      // (ii) transforms, one output row at a time: W_hi.AT_hi + W_hi.AT_lo + W_lo.AT_hi, K = 2 steps of 16 joints (SWIZZLE_64B rows)
+      constexpr uint32_t idesc_t = umma_idesc_f16(TV, TC_TN);
+      const uint32_t w_hi = umma_desc_sw128_lo(smem0 + TC_OFF_W), w_lo = w_hi + (TC_W_IMG >> 4);
+      const uint32_t dt = tmem_base + TC_COL_T;
+      for (int r = 0; r < 3; ++r) {
+        const int slot = r & 1;
+        if (r > 0) { mbar_wait(t_empty, (r - 1) & 1); }
+        mbar_wait(&at_full[slot], r >> 1);
+        tc_fence_after();
+        const uint32_t t_hi = umma_desc_sw128_lo(smem0 + TC_OFF_AT + slot * TC_AT_BYTES), t_lo = t_hi + (TC_AT_IMG >> 4);
+#pragma unroll
+        for (int ks = 0; ks < TC_TK / 16; ++ks) {
+          const uint32_t ko = ks * 2;
+          umma_f16_lohi(dt, w_hi + ko, t_hi + ko, idesc_t, ks != 0, UMMA_DESC_SW64_HI);
+          umma_f16_lohi(dt, w_hi + ko, t_lo + ko, idesc_t, 1, UMMA_DESC_SW64_HI);
+          umma_f16_lohi(dt, w_lo + ko, t_hi + ko, idesc_t, 1, UMMA_DESC_SW64_HI);
+        }
+        umma_commit(t_full);
+        if (r == 0) umma_commit(at_free);
+      }
     }
   }
   __syncwarp();
 
-  // ================= epilogue, all 8 warps: v_posed from TMEM, 4-sparse skinning, stores =================
-  const int quad = warp & 3, half = warp >> 2;
+  // ================= epilogue, warps 2..9: thread = vertex row (TMEM lane) x 32 bodies =================
+  // (the two issue warps stay out of it: the MMA issuer waits for the epilogue's t_empty arrivals between output rows)
+  if (warp >= 2) {
+  const int quad = warp & 3, half = (warp - 2) >> 2;    // a warp reads the TMEM lanes 32 (warp % 4) .. +31
   const int row = quad * 32 + lane;
   const int v = tile * TV + row;                        // < VPAD: the packed arrays are zero padded
-  const int4 ji = *reinterpret_cast<const int4*>(a.widx + v * 4);
-  const float4 jw = *reinterpret_cast<const float4*>(a.wval + v * 4);
-  const int wj[4] = {ji.x, ji.y, ji.z, ji.w};
-  const float ww[4] = {jw.x, jw.y, jw.z, jw.w};
+  const bool vok = v < V;
+  const int body0 = group * TC_NB + half * 32;          // first of this thread's 32 bodies
+  const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  mbar_wait(vp_full, 0);
+  tc_fence_after();
   float ainv[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) ainv[c] = a.ainv[(tile * 3 + c) * TV + row];
-  mbar_wait(t_full, 0);
-  mbar_wait(acc_full, 0);
-  tc_fence_after();
-  uint32_t d0[32], d1[32], d2[32];
-  const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + half * 32;
-  tmem_ld_32x32(tacc, d0);
-  tmem_ld_32x32(tacc + TC_NB, d1);
-  tmem_ld_32x32(tacc + 2 * TC_NB, d2);
-  tmem_ld_wait();
-  const float4* T = reinterpret_cast<const float4*>(smem + TC_OFF_T);
-  const int body0 = half * 32;
-  const bool vok = v < V;
+  if (a.save_vposed) {                                  // training path: v_posed itself, once
 #pragma unroll
-  for (int b = 0; b < 32; ++b) {
-    const int body = body0 + b;
-    const int gb = group * TC_NB + body;
-    if (gb < a.B) {
-      const float vp0 = __uint_as_float(d0[b]) * ainv[0], vp1 = __uint_as_float(d1[b]) * ainv[1], vp2 = __uint_as_float(d2[b]) * ainv[2];
-      float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
+    for (int q = 0; q < 4; ++q) {
+      uint32_t d[3][8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float4* tj = T + ((size_t)body * NJ + wj[e]) * 3;
-        const float4 r0 = tj[0], r1 = tj[1], r2 = tj[2];
-        const float w = ww[e];
-        T0.x = fmaf(w, r0.x, T0.x); T0.y = fmaf(w, r0.y, T0.y); T0.z = fmaf(w, r0.z, T0.z); T0.w = fmaf(w, r0.w, T0.w);
-        T1.x = fmaf(w, r1.x, T1.x); T1.y = fmaf(w, r1.y, T1.y); T1.z = fmaf(w, r1.z, T1.z); T1.w = fmaf(w, r1.w, T1.w);
-        T2.x = fmaf(w, r2.x, T2.x); T2.y = fmaf(w, r2.y, T2.y); T2.z = fmaf(w, r2.z, T2.z); T2.w = fmaf(w, r2.w, T2.w);
-      }
-      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-      if (a.transl) { t0 = __ldg(a.transl + (size_t)gb * 3); t1 = __ldg(a.transl + (size_t)gb * 3 + 1); t2 = __ldg(a.transl + (size_t)gb * 3 + 2); }
-      if (vok) {
-        float* o = a.verts + ((size_t)gb * V + v) * 3;
-        o[0] = T0.x * vp0 + T0.y * vp1 + T0.z * vp2 + T0.w + t0;
-        o[1] = T1.x * vp0 + T1.y * vp1 + T1.z * vp2 + T1.w + t1;
-        o[2] = T2.x * vp0 + T2.y * vp1 + T2.z * vp2 + T2.w + t2;
-        if (a.save_vposed) {
+      for (int c = 0; c < 3; ++c) tmem_ld_32x8(tlane + c * TC_NB + half * 32 + q * 8, d[c]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) {
+        const int gb = body0 + q * 8 + bb;
+        if (gb < a.B && vok) {
           float* sv = a.save_vposed + ((size_t)gb * V + v) * 3;
-          sv[0] = vp0; sv[1] = vp1; sv[2] = vp2;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) sv[c] = __uint_as_float(d[c][bb]) * ainv[c];
         }
       }
     }
+  }
+  // out_r = T_r . [v_posed ; 1]: the v_posed accumulators are re-read from TMEM for every row (24 registers instead of 96 held
+  // across the loop; 10 warps leave 168 registers per thread), with 1 / (all scales) folded into three per-thread constants
+  constexpr float tscale = 1.f / (TC_WSCALE * TC_BSCALE);
+  const float k0 = ainv[0] * tscale, k1 = ainv[1] * tscale, k2 = ainv[2] * tscale;
+#pragma unroll 1
+  for (int r = 0; r < 3; ++r) {
+    mbar_wait(t_full, r & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                       // 8 bodies = 32 TMEM columns of T_r per load
+      uint32_t t[32], d[3][8];
+      tmem_ld_32x32(tlane + TC_COL_T + half * 128 + q * 32, t);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tmem_ld_32x8(tlane + c * TC_NB + half * 32 + q * 8, d[c]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) {
+        const int gb = body0 + q * 8 + bb;
+        if (gb < a.B && vok) {
+          const float tr = a.transl ? __ldg(a.transl + (size_t)gb * 3 + r) : 0.f;
+          float acc = fmaf(__uint_as_float(t[bb * 4 + 3]), tscale, tr);
+          acc = fmaf(__uint_as_float(t[bb * 4 + 0]) * k0, __uint_as_float(d[0][bb]), acc);
+          acc = fmaf(__uint_as_float(t[bb * 4 + 1]) * k1, __uint_as_float(d[1][bb]), acc);
+          acc = fmaf(__uint_as_float(t[bb * 4 + 2]) * k2, __uint_as_float(d[2][bb]), acc);
+          a.verts[((size_t)gb * V + v) * 3 + r] = acc;
+        }
+      }
+    }
+    if (r < 2) {
+      tc_fence_before();
+      mbar_arrive(t_empty);
+    }
+  }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -328,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
 
 using namespace straps;
 
-// ---- host side: pack Apk once, run the two kernels ----
+// ---- host side: pack the constant operands once, run the two kernels ----
 static inline uint16_t f2h_bits(float f) {          // round-to-nearest-even fp32 -> fp16 bits (cuda_fp16.h host path)
   const __half h = __float2half_rn(f);
   uint16_t b;
@@ -343,12 +419,16 @@ static inline float h2f_bits(uint16_t b) {
 
 // Apk[(v, c), k] rows scaled to [2^13, 2^14), split into fp16 hi / lo, laid out as the SWIZZLE_128B images lbs_tc_kernel streams:
 // image (tile, kc, c, h) = 128 rows of 128 bytes, 16-byte unit u of row r at physical unit u ^ (r & 7).
-int straps::smpl_tc_pack(const float* v_template, const float* shapedirs, const float* posedirs, std::vector<unsigned char>& apk,
-                         std::vector<float>& ainv) {
+// Wk[v, j] = skinning weight * 2^14, hi / lo, image (tile, h) = 128 rows of 64 bytes (32 joint slots), SWIZZLE_64B: unit u of row r at
+// physical unit u ^ ((r >> 1) & 3).
+int straps::smpl_tc_pack(const float* v_template, const float* shapedirs, const float* posedirs, const float* lbs_weights,
+                         std::vector<unsigned char>& apk, std::vector<float>& ainv, std::vector<unsigned char>& wk) {
   apk.assign((size_t)NTILES * TC_STAGES_PER_TILE * TC_A_IMG, 0);
   ainv.assign((size_t)NTILES * 3 * TV, 0.f);
+  wk.assign((size_t)NTILES * TC_W_BYTES, 0);
   std::vector<float> rowv(TC_K);
-  for (int v = 0; v < V; ++v)
+  for (int v = 0; v < V; ++v) {
+    const int tile = v / TV, r = v % TV;
     for (int c = 0; c < 3; ++c) {
       float mx = 0.f;
       for (int k = 0; k < TC_K; ++k) {
@@ -362,7 +442,6 @@ int straps::smpl_tc_pack(const float* v_template, const float* shapedirs, const 
       int e = 0;
       if (mx > 0.f) { std::frexp(mx, &e); e = 14 - e; }                        // mx * 2^e in [2^13, 2^14)
       const float sc = std::ldexp(1.f, e);
-      const int tile = v / TV, r = v % TV;
       ainv[((size_t)tile * 3 + c) * TV + r] = 1.f / (sc * TC_BSCALE);
       for (int k = 0; k < TC_K; ++k) {
         const float x = rowv[k] * sc;
@@ -375,6 +454,16 @@ int straps::smpl_tc_pack(const float* v_template, const float* shapedirs, const 
         memcpy(&apk[img + TC_A_IMG + off], &lb, 2);
       }
     }
+    for (int j = 0; j < NJ; ++j) {
+      const float x = lbs_weights[(size_t)v * NJ + j] * TC_WSCALE;
+      const uint16_t hb = f2h_bits(x);
+      const uint16_t lb = f2h_bits(x - h2f_bits(hb));
+      const size_t img = (size_t)tile * TC_W_BYTES;
+      const size_t off = (size_t)r * 64 + (size_t)(((j >> 3) ^ ((r >> 1) & 3)) << 4) + (size_t)(j & 7) * 2;
+      memcpy(&wk[img + off], &hb, 2);
+      memcpy(&wk[img + TC_W_IMG + off], &lb, 2);
+    }
+  }
   return 0;
 }
 
@@ -383,7 +472,7 @@ int straps::smpl_tc_forward(straps_smpl* m, const float* global_orient, int64_t 
                             float* joints, float* save_vposed, float* save_A, cudaStream_t st) {
   const int groups = (batch + TC_NB - 1) / TC_NB;
   const int b_pad = groups * TC_NB;
-  const size_t need = (size_t)groups * TC_B_BYTES + (size_t)b_pad * NJ * 12 * sizeof(float);
+  const size_t need = (size_t)groups * (TC_B_BYTES + TC_AT_GROUP);
   if (need > m->tc_scratch_bytes) {
     // grows with the largest batch seen (first call / warm-up; never inside a CUDA-graph capture of a warmed-up shape)
     STRAPS_CUDA(cudaStreamSynchronize(st));
@@ -391,14 +480,20 @@ int straps::smpl_tc_forward(straps_smpl* m, const float* global_orient, int64_t 
     m->tc_scratch = nullptr;
     m->tc_scratch_bytes = 0;
     STRAPS_CUDA(cudaMalloc(&m->tc_scratch, need));
+    STRAPS_CUDA(cudaMemsetAsync(m->tc_scratch, 0, need, st));        // the unused joint slots of the transform images stay zero
     m->tc_scratch_bytes = need;
   }
   unsigned char* bimg = static_cast<unsigned char*>(m->tc_scratch);
-  float* aout = reinterpret_cast<float*>(bimg + (size_t)groups * TC_B_BYTES);
+  unsigned char* atimg = bimg + (size_t)groups * TC_B_BYTES;
+  if (atimg != m->tc_at_base) {
+    // a smaller batch moves the boundary between the two regions: what was Bm data must not be read as joint slots 24..31
+    STRAPS_CUDA(cudaMemsetAsync(atimg, 0, (size_t)groups * TC_AT_GROUP, st));
+    m->tc_at_base = atimg;
+  }
   ChainArgs ca;
   ca.go = global_orient; ca.bp = body_pose; ca.betas = betas; ca.transl = transl;
   ca.go_stride = go_stride; ca.bp_stride = bp_stride; ca.betas_stride = betas_stride;
-  ca.B = batch; ca.B_pad = b_pad; ca.pose2rot = pose2rot; ca.joints = joints; ca.aout = aout; ca.bimg = bimg; ca.save_A = save_A;
+  ca.B = batch; ca.B_pad = b_pad; ca.pose2rot = pose2rot; ca.joints = joints; ca.bimg = bimg; ca.atimg = atimg; ca.save_A = save_A;
   smpl_chain_kernel<<<b_pad / CH_TB, 128, 0, st>>>(m->d, ca);
   STRAPS_LAUNCH_CHECK();
   static PerDeviceOnce attr_once;
@@ -408,7 +503,7 @@ int straps::smpl_tc_forward(straps_smpl* m, const float* global_orient, int64_t 
     attr_once.done(dev);
   }
   LbsTcArgs la;
-  la.apk = m->tc_apk; la.ainv = m->tc_ainv; la.bimg = bimg; la.aout = aout; la.widx = m->d.widx; la.wval = m->d.wval;
+  la.apk = m->tc_apk; la.ainv = m->tc_ainv; la.wk = m->tc_wk; la.bimg = bimg; la.atimg = atimg;
   la.transl = transl; la.B = batch; la.verts = vertices; la.save_vposed = save_vposed;
   lbs_tc_kernel<<<dim3(NTILES, groups), TC_THREADS, TC_SMEM, st>>>(la);
   STRAPS_LAUNCH_CHECK();

@@ -58,7 +58,10 @@ class GraphedTrainStep(object):
 
     `step_fn(*inputs)` must run the step exactly as the reference's loop body does (train/train_synthetic_otf_rendering.py:186-233):
     `optimiser.zero_grad(); loss, ... = criterion(...); loss.backward(); optimiser.step()` with a
-    straps_b200.parallel.DataParallelAdam `optimiser`, and return the tensors the caller wants to read (e.g. the loss).  The step
+    straps_b200.parallel.DataParallelAdam `optimiser`, and return the tensors the caller wants to read DETACHED (e.g.
+    `loss.detach()`: a returned tensor that still holds its autograd graph keeps the graph's nodes and their streams alive across
+    steps).  Joint selections inside the step use `straps_b200.ops.select_joints` (indexing with a Python list copies the list to the
+    device on every call, which a capture refuses).  The step
     launches ~500 kernels for ~9 ms of GPU work; eager PyTorch spends another ~1.5 ms in launch gaps and autograd bookkeeping,
     which replay removes.  Everything the step touches is graph-safe: the library allocates its workspaces on first use (the
     warm-up steps here), Adam's step count lives on the device, BatchNorm's counters are bumped by a captured foreach kernel.
@@ -78,6 +81,8 @@ class GraphedTrainStep(object):
         self._opt = optimiser
         self._static_in = [t.detach().clone() for t in example_inputs]
         dev = optimiser.bucket.params.device
+        import gc
+        gc.collect()                                 # autograd graphs of earlier eager steps (and their AccumulateGrad nodes) go first
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -88,15 +93,17 @@ class GraphedTrainStep(object):
         self._split = optimiser.world > 1
         self._graph = torch.cuda.CUDAGraph()
         optimiser._deferred = self._split
+        # capture on the warm-up stream: autograd nodes that outlive a step (AccumulateGrad of the criterion's log-variances) were
+        # created there, and a node on ANOTHER stream makes the engine synchronise with it, which invalidates the capture
         try:
-            with torch.cuda.graph(self._graph):
+            with torch.cuda.graph(self._graph, stream=side):
                 self._static_out = step_fn(*self._static_in)
         finally:
             optimiser._deferred = False
         self._graph_b = None
         if self._split:
             self._graph_b = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph_b, pool=self._graph.pool()):
+            with torch.cuda.graph(self._graph_b, pool=self._graph.pool(), stream=side):
                 optimiser.apply_update()
             # the capture ran the forward/backward once without the update: finish that step so the replicas stay in step
             optimiser.exchange()

@@ -169,7 +169,8 @@ def test_proxy_representation_synthesis_bit_exact(assets_root):
 
 
 def _lbs_mode(mode):
-    """STRAPS_LBS is read by the library on every SMPL forward: 'simt' keeps the CUDA-core kernel, unset = tensor cores for B >= 32."""
+    """STRAPS_LBS is read by the library on every SMPL forward: 'simt' = the CUDA-core kernel, 'tc' = the tensor-core kernels at every
+    batch size, unset = tensor cores from the batch size where they win."""
     import os
     if mode is None:
         os.environ.pop('STRAPS_LBS', None)
@@ -177,7 +178,7 @@ def _lbs_mode(mode):
         os.environ['STRAPS_LBS'] = mode
 
 
-@pytest.mark.parametrize('B', [32, 40, 64, 127, 200])
+@pytest.mark.parametrize('B', [1, 7, 32, 40, 64, 127, 200])
 def test_tensor_core_lbs_against_oracle_and_cuda_core_kernel(assets_root, smpl_oracle, B):
     """Batches >= 32 take smpl_tc.cu (blend shapes as a 3-pass fp16-split tcgen05 GEMM).  Held to 1e-5 against the oracle
     (smplx lbs()) -- ten times tighter than north_star -- and compared with the CUDA-core kernel on the same
@@ -191,7 +192,7 @@ def test_tensor_core_lbs_against_oracle_and_cuda_core_kernel(assets_root, smpl_o
     t = torch.from_numpy(transl)[:, None]
     try:
         outs = {}
-        for mode in (None, 'simt'):
+        for mode in ('tc', 'simt'):
             _lbs_mode(mode)
             with torch.no_grad():
                 o = smpl(body_pose=Rg[:, 1:], global_orient=Rg[:, :1], betas=bg, transl=tg, pose2rot=False)
@@ -202,7 +203,7 @@ def test_tensor_core_lbs_against_oracle_and_cuda_core_kernel(assets_root, smpl_o
     with torch.no_grad():
         va, ja = smpl_oracle.forward(betas=torch.from_numpy(betas), body_pose=torch.from_numpy(aa[:, 3:]),
                                      global_orient=torch.from_numpy(aa[:, :3]), pose2rot=True)
-    tc, simt = outs[None], outs['simt']
+    tc, simt = outs['tc'], outs['simt']
     assert rel_err(tc[0].numpy(), (v + t).numpy()) < 1e-5
     assert rel_err(tc[1].numpy(), (j + t).numpy()) < 1e-5
     assert rel_err(tc[2].numpy(), va.numpy()) < 1e-5

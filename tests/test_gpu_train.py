@@ -259,7 +259,7 @@ def test_config3_training_step_gradients(B, mode, assets_root, additional_dir, s
     # the oracle once more with conv weights perturbed by 3e-7: its own fp32 noise floor (B=4 with these seeds is flip-free
     # and is held to the plain 2e-4 bar)
     noise_runs = []
-    for seed in ({4: (), 16: (5, 6, 7, 8, 9, 10), 64: (5, 6, 7)}[B]):
+    for seed in ({4: () if mode == 'fp32_simt' else (5, 6, 7, 8, 9, 10), 16: (5, 6, 7, 8, 9, 10), 64: (5, 6, 7)}[B]):
         sdn = _perturbed(sdg, seed, NOISE_REL_BY_MODE[mode])
         on = O.regress_and_pose(_t(x), sdn, init, smpl_oracle, train=True)
         lvn = {k: v.detach().clone().requires_grad_(True) for k, v in lv.items()}
@@ -296,8 +296,11 @@ def test_config3_training_step_gradients(B, mode, assets_root, additional_dir, s
         for d, (sdn, lvn) in zip(noise, noise_runs):
             d[t + '_log_var'] = lvn[t].grad
     assert len(ref) == 71            # 71 gradient tensors in the bucket
-    # B = 4 with these seeds is flip-free (no ReLU / max-pool decision differs from the oracle's): all 71 tensors are held to the
-    # contract's plain 1e-4 in both convolution modes; the larger batches use the oracle's own noise floor
+    # B = 4 in fp32 mode is flip-free with these seeds (no ReLU / max-pool decision differs from the oracle's): all 71 tensors are held
+    # to the contract's plain 1e-4.  Flip-freeness is luck, not a property: ~1e7 pre-activations, a forward
+    # error of 1e-6 -- the tensor-core mode (different rounding) did flip one deep decision on B200 (5.9e-3 on every upstream weight), so
+    # it is judged like the larger batches, against the oracle's own noise floor; its ARITHMETIC is held to 1e-4 on all encoder tensors
+    # by test_tensor_core_backward_matches_fp32_backward_on_the_same_activations (same masks by construction).
     _check_grads(got, ref, noise, 'config3 B=%d %s' % (B, mode), gtol=RTOL if B == 4 else GTOL)
 
 

@@ -4,8 +4,8 @@
   the step count on the device lands where torch.optim.Adam lands on an identical replica;
 * gradient accumulation over two backward passes still accumulates (the slot shortcut only applies to a fresh gradient);
 * GraphedTrainStep (the whole step captured as a CUDA graph and replayed) follows the eager loop.
-Tolerance: parameters after a few steps within 1e-5 of their magnitude (the weight-gradient kernels add partial tiles with fp32
-atomics, so two runs of the SAME code differ in the last bits; Adam's ratio m / sqrt(v) is then compared in aggregate)."""
+Tolerance: updates compared in aggregate (see _updates_agree: Adam's ratio m / sqrt(v) amplifies rounding noise of near-zero gradients
+to a full +-lr step, and the weight-gradient kernels add partial tiles with fp32 atomics, so two runs of the SAME code differ)."""
 import numpy as np
 import pytest
 import torch
@@ -67,9 +67,14 @@ def _flat(reg, crit):
 
 
 def _updates_agree(a, b, start, steps):
-    """Parameters agree to 1e-5 of their magnitude and the mean update error is a small fraction of steps * lr."""
-    assert rel_err(a.numpy(), b.numpy()) < 1e-5
-    assert float(((a - start) - (b - start)).abs().mean()) < 0.02 * steps * LR
+    """The mean update error is a small fraction of steps * lr and all but a sliver of the elements land within 0.1 lr of each other.
+    (No max-norm bar: Adam's first updates are lr * sign-like, m / sqrt(v) = +-1, so an element whose gradient is rounding noise -- the
+    weight-gradient kernels add partial tiles with fp32 atomics -- legitimately moves by +lr in one run and -lr in the other:
+    measured on B200 9e-5 relative = 2 lr on one element between two runs of the same code.)"""
+    d = ((a - start) - (b - start)).abs()
+    assert float(d.mean()) < 0.02 * steps * LR
+    assert float((d > 0.1 * LR).float().mean()) < 5e-3, float((d > 0.1 * LR).float().mean())
+    assert float(d.max()) <= 2.0 * steps * LR * 1.001
 
 
 def test_flat_bucket_adam_matches_torch_adam(assets_root):
@@ -125,7 +130,7 @@ def test_graphed_training_step_follows_the_eager_loop(assets_root):
             loss = _loss(reg, crit, smpl, x, labels)
             loss.backward()
             opt.step()
-            return loss
+            return loss.detach()
         return step
     step_a, step_b = make_step(reg_a, crit_a, opt_a), make_step(reg_b, crit_b, opt_b)
     gstep = GraphedTrainStep(step_a, opt_a, warmup=2)          # 2 real warm-up steps + 1 captured (not executed)

@@ -27,12 +27,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batches', type=int, nargs='+', default=[1, 8, 64, 256, 1024, 4096])
     ap.add_argument('--iters', type=int, default=50)
+    ap.add_argument('--modes', nargs='+', default=['default'], help="STRAPS_LBS values to time: default, tc (tensor cores at every batch), simt")
     args = ap.parse_args()
     peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(REPO, 'MEASURED_PEAKS.json')) else {}
     hbm = peaks.get('hbm_gbs', 6650.0)
     dev = 'cuda:0'
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # 256 MB > 126 MB L2
-    for B in args.batches:
+    for B, mode in [(b, m) for b in args.batches for m in args.modes]:
+        if mode == 'default':
+            os.environ.pop('STRAPS_LBS', None)
+        else:
+            os.environ['STRAPS_LBS'] = mode
         smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(dev)
         rng = np.random.RandomState(B)
         betas = torch.from_numpy(rng.normal(0, 1, (B, 10)).astype(np.float32)).to(dev)
@@ -93,7 +98,7 @@ def main():
             graph['frac_graph_cold'] = graph['achieved_gbs_graph_cold'] / hbm
         except Exception as e:                       # capture is an extra: the eager figures stand on their own
             graph = {'graph_error': str(e)[:200]}
-        print(json.dumps({'workload': 'SMPL LBS forward (lbs_kernel + joints_kernel)', 'batch': B,
+        print(json.dumps({'workload': 'SMPL LBS forward (LBS kernels + joints_kernel)', 'lbs_mode': mode, 'batch': B,
                           'ms_cold_l2': cold_ms, 'ms_back_to_back': warm_ms, 'bodies_per_s': B / (warm_ms * 1e-3),
                           'algorithmic_bytes': bytes_, 'achieved_gbs_cold': bytes_ / (cold_ms * 1e-3) / 1e9,
                           'achieved_gbs_back_to_back': bytes_ / (warm_ms * 1e-3) / 1e9, 'peak_gbs': hbm,
