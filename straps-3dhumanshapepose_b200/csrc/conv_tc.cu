@@ -1549,6 +1549,33 @@ __global__ void unpack_dw_tc_kernel(const float* __restrict__ dw, const unsigned
   out[i] = dw[(size_t)n * k_eff + k] * ldexpf(1.f, -e);
 }
 
+// the same for every convolution of a backward pass in one launch (20 launches of 3-10 us before)
+struct DwUnpackTable {
+  const float* src[NCONV];
+  float* dst[NCONV];            // null: skipped
+  int cout[NCONV], cin[NCONV], ks[NCONV], k_eff[NCONV];
+  int blk_start[NCONV + 1];
+  const unsigned* maxbits;      // [NCONV] bits of max |dY| per convolution
+};
+__global__ void __launch_bounds__(256) unpack_dw_all_kernel(const __grid_constant__ DwUnpackTable t) {
+  int l = 0;
+#pragma unroll 1
+  while (l + 1 < NCONV && (int)blockIdx.x >= t.blk_start[l + 1]) ++l;
+  const size_t i = (size_t)((int)blockIdx.x - t.blk_start[l]) * 256 + threadIdx.x;
+  const int ks = t.ks[l], cin = t.cin[l];
+  if (i >= (size_t)t.cout[l] * cin * ks * ks) return;
+  int e = 0;
+  const float mx = __uint_as_float(t.maxbits[l]);
+  if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); e = max(-100, min(100, 14 - e)); }
+  const int kw = (int)(i % ks);
+  size_t q = i / ks;
+  const int kh = (int)(q % ks); q /= ks;
+  const int c = (int)(q % cin);
+  const int n = (int)(q / cin);
+  const int k = (l == 0) ? kh * C1_KROW + kw * XP_C + c : (kh * ks + kw) * cin + c;
+  t.dst[l][i] = t.src[l][(size_t)n * t.k_eff[l] + k] * ldexpf(1.f, -e);
+}
+
 // ------------------------------------------------------------------------------------------------
 // training path on the tensor cores (called from train.cu)
 //
@@ -1574,8 +1601,10 @@ struct TcTrain {
   unsigned* dy_max;                            // bits of max |dY| (atomicMax target of bn_bwd_apply_kernel)
   __half *dy_hi, *dy_lo;                       // split (scaled, optionally zero-upsampled) dY of the current layer
   size_t dy_plane;                             // elements per plane
-  float* dw_packed;                            // [cout][k_eff] fp32 accumulation target of the weight gradient (largest conv)
-  size_t dw_elems;
+  float* dw_packed;                            // per conv [cout][k_eff] fp32 accumulation targets of the weight gradients (dw_off), zeroed
+  size_t dw_elems;                             // once per backward; unpacked to OIHW by ONE launch at its end (tc_train_unpack_all)
+  size_t dw_off[NCONV];
+  float* dw_dst[NCONV];                        // where this backward's weight gradient of conv i goes (null: not computed on the tensor cores)
   std::map<int, std::vector<TcLayerMaps>> fwd_maps, dg_maps;
   std::map<int, std::vector<TcLayerMaps>> wg_maps;   // a_* = X with 64-pixel boxes, w_* = dY [pixels][cout] boxes {64, 64}
 };
@@ -1655,6 +1684,109 @@ __global__ void split_scaled_kernel(const float* __restrict__ src, const unsigne
   *reinterpret_cast<uint2*>(lo + o) = make_uint2(pack_f16(l[0], l[1]), pack_f16(l[2], l[3]));
 }
 
+// ---- all 20 convolutions' weights prepared in TWO launches per training step (round 1: w_rowscale + pack_w_tc per layer at the
+// forward, w_colscale + pack_w_dgrad_tc per layer at the backward = 78 launches of 3-7 us for 11 M weights) ----
+struct WPrepLayer {
+  const float* w;               // OIHW fp32 (the parameter itself)
+  __half* f_hi; __half* f_lo;   // forward operand [cout][k_eff]
+  __half* d_hi; __half* d_lo;   // data-gradient operand [cin][(kh', kw', co)], null for conv1
+  int cout, cin, ks, k_eff;
+  int ch_off, wd_off;           // offsets into the forward row-scale / data-gradient row-scale arrays
+};
+struct WPrepTable {
+  WPrepLayer L[NCONV];
+  int row_start[NCONV + 1];     // scale kernel: blocks [row_start[i], row_start[i+1]) = output channels of conv i ...
+  int col_start[NCONV + 1];     // ... followed by rows_total + [col_start[i], col_start[i+1]) = input channels of conv i (i >= 1)
+  int fblk_start[NCONV + 1];    // pack kernel: blocks of 256 forward elements, then blocks of 256 data-gradient elements
+  int dblk_start[NCONV + 1];
+  float* wf_scale; float* wf_unscale; float* wd_scale; float* wd_unscale;
+};
+
+__device__ __forceinline__ int wprep_find(const int* start, int b) {
+  int i = 0;
+#pragma unroll 1
+  while (i + 1 < NCONV && b >= start[i + 1]) ++i;
+  return i;
+}
+__device__ __forceinline__ void wprep_pow2(float mx, float* pscale, float* unscale) {
+  int e = 0;
+  if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); e = max(-60, min(60, 14 - e)); }     // mx * 2^e in [2^13, 2^14)
+  *pscale = ldexpf(1.f, e);
+  *unscale = ldexpf(1.f, -e);
+}
+
+__global__ void __launch_bounds__(256) w_scales_all_kernel(const __grid_constant__ WPrepTable t) {
+  __shared__ float red[256];
+  const int rows_total = t.row_start[NCONV];
+  int b = blockIdx.x;
+  float m = 0.f;
+  const bool fwd = b < rows_total;
+  int i, n;
+  if (fwd) {
+    i = wprep_find(t.row_start, b);
+    n = b - t.row_start[i];
+    const WPrepLayer& L = t.L[i];
+    const int row_len = L.cin * L.ks * L.ks;
+    for (int k = threadIdx.x; k < row_len; k += 256) m = fmaxf(m, fabsf(L.w[(size_t)n * row_len + k]));
+  } else {
+    b -= rows_total;
+    i = wprep_find(t.col_start, b);
+    n = b - t.col_start[i];
+    const WPrepLayer& L = t.L[i];
+    const int kk = L.ks * L.ks;
+    for (int k = threadIdx.x; k < L.cout * kk; k += 256) m = fmaxf(m, fabsf(L.w[((size_t)(k / kk) * L.cin + n) * kk + (k % kk)]));
+  }
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (fwd) wprep_pow2(red[0], t.wf_scale + t.L[i].ch_off + n, t.wf_unscale + t.L[i].ch_off + n);
+    else wprep_pow2(red[0], t.wd_scale + t.L[i].wd_off + n, t.wd_unscale + t.L[i].wd_off + n);
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_w_all_kernel(const __grid_constant__ WPrepTable t) {
+  const int fblk_total = t.fblk_start[NCONV];
+  int b = blockIdx.x;
+  if (b < fblk_total) {
+    const int i = wprep_find(t.fblk_start, b);
+    const WPrepLayer& L = t.L[i];
+    const size_t e = (size_t)(b - t.fblk_start[i]) * 256 + threadIdx.x;
+    if (e >= (size_t)L.cout * L.k_eff) return;
+    const int n = (int)(e / L.k_eff), k = (int)(e % L.k_eff);
+    float v = 0.f;
+    if (i == 0) {
+      const int kh = k / C1_KROW, r = k % C1_KROW, kw = r / XP_C, c = r % XP_C;
+      if (kw < L.ks && c < L.cin) v = L.w[(((size_t)n * L.cin + c) * L.ks + kh) * L.ks + kw];
+    } else {
+      const int tap = k / L.cin, c = k % L.cin, kh = tap / L.ks, kw = tap % L.ks;
+      v = L.w[(((size_t)n * L.cin + c) * L.ks + kh) * L.ks + kw];
+    }
+    v *= t.wf_scale[L.ch_off + n];
+    __half h, l;
+    split_f16(v, h, l);
+    L.f_hi[e] = h;
+    L.f_lo[e] = l;
+  } else {
+    b -= fblk_total;
+    const int i = wprep_find(t.dblk_start, b);
+    const WPrepLayer& L = t.L[i];
+    const int k_eff = L.ks * L.ks * L.cout;
+    const size_t e = (size_t)(b - t.dblk_start[i]) * 256 + threadIdx.x;
+    if (e >= (size_t)L.cin * k_eff) return;
+    const int ci = (int)(e / k_eff), k = (int)(e % k_eff);
+    const int tap = k / L.cout, co = k % L.cout, kh = L.ks - 1 - tap / L.ks, kw = L.ks - 1 - tap % L.ks;
+    const float v = L.w[(((size_t)co * L.cin + ci) * L.ks + kh) * L.ks + kw] * t.wd_scale[L.wd_off + ci];
+    __half h, l;
+    split_f16(v, h, l);
+    L.d_hi[e] = h;
+    L.d_lo[e] = l;
+  }
+}
+
 static bool buf_is_conv_input(const straps_regressor* r, int buf) {
   for (int i = 1; i < NCONV; ++i)
     if (r->conv[i].in_buf == buf) return true;
@@ -1674,7 +1806,7 @@ int tc_train_begin(straps_regressor* r, int B, cudaStream_t st) {
     std::vector<size_t> off_p(nb, (size_t)-1);
     for (size_t b = 0; b < nb; ++b)
       if ((int)b != r->buf_xin && buf_is_conv_input(r, (int)b)) off_p[b] = take(2 * (size_t)r->max_batch * r->bufs[b].h * r->bufs[b].w * r->bufs[b].c);
-    size_t off_wf[NCONV], off_wd[NCONV], nco = 0, nci = 0, dy_el = 0, dw_el = 0;
+    size_t off_wf[NCONV], off_wd[NCONV], dw_off_tmp[NCONV], nco = 0, nci = 0, dy_el = 0, dw_el = 0;
     for (int i = 0; i < NCONV; ++i) {
       const ConvSpec& c = r->conv[i];
       off_wf[i] = take(2 * (size_t)c.cout * c.k_eff);
@@ -1683,7 +1815,8 @@ int tc_train_begin(straps_regressor* r, int B, cudaStream_t st) {
       nco += c.cout; nci += (i == 0) ? 0 : c.cin;
       dy_el = std::max(dy_el, (size_t)r->max_batch * c.hout * c.wout * c.cout);
       if (i > 0) dy_el = std::max(dy_el, (size_t)r->max_batch * c.hin * c.win * c.cout);   // (upsampled) dY of this layer
-      dw_el = std::max(dw_el, (size_t)c.cout * c.k_eff);
+      dw_off_tmp[i] = dw_el;
+      dw_el += (size_t)c.cout * c.k_eff;
     }
     tt->dy_plane = dy_el;
     const size_t off_dy = take(2 * dy_el);
@@ -1713,22 +1846,35 @@ int tc_train_begin(straps_regressor* r, int B, cudaStream_t st) {
     tt->dg_unscale = f; f += 512; tt->ones = f; f += 512; tt->zeros = f; f += 512;
     tt->dy_max = reinterpret_cast<unsigned*>(f); f += 64;
     tt->dw_packed = f; tt->dw_elems = dw_el;
+    for (int i = 0; i < NCONV; ++i) { tt->dw_off[i] = dw_off_tmp[i]; tt->dw_dst[i] = nullptr; }
     std::vector<float> one(512, 1.f);
     STRAPS_CUDA(cudaMemcpy(tt->ones, one.data(), 512 * sizeof(float), cudaMemcpyHostToDevice));
     STRAPS_CUDA(cudaMemset(tt->zeros, 0, 512 * sizeof(float)));
-    STRAPS_CUDA(cudaMemset(tt->dy_max, 0, sizeof(unsigned)));
+    STRAPS_CUDA(cudaMemset(tt->dy_max, 0, 64 * sizeof(unsigned)));
     t->train = tt;
   }
   TcTrain* tt = t->train;
-  // forward weights of this step (the optimiser has changed them): BN scale not folded
-  for (int i = 0; i < NCONV; ++i) {
-    const ConvSpec& c = r->conv[i];
-    const size_t total = (size_t)c.cout * c.k_eff;
-    w_rowscale_kernel<<<c.cout, 256, 0, st>>>(c.w_oihw, tt->ones, c.cin * c.ksize * c.ksize, tt->wf_scale + t->ch_off[i],
-                                             tt->wf_unscale + t->ch_off[i]);
+  // weights of this step (the optimiser has changed them; BN scale not folded): forward AND data-gradient operands of all 20
+  // convolutions in two launches
+  {
+    WPrepTable wt;
+    int rows = 0, cols = 0, fb = 0, db = 0;
+    for (int i = 0; i < NCONV; ++i) {
+      const ConvSpec& c = r->conv[i];
+      WPrepLayer& L = wt.L[i];
+      L.w = c.w_oihw; L.f_hi = tt->wf_hi[i]; L.f_lo = tt->wf_lo[i]; L.d_hi = tt->wd_hi[i]; L.d_lo = tt->wd_lo[i];
+      L.cout = c.cout; L.cin = c.cin; L.ks = c.ksize; L.k_eff = c.k_eff;
+      L.ch_off = (int)t->ch_off[i]; L.wd_off = (i == 0) ? 0 : (int)tt->wd_off[i];
+      wt.row_start[i] = rows; rows += c.cout;
+      wt.col_start[i] = cols; cols += (i == 0) ? 0 : c.cin;
+      wt.fblk_start[i] = fb; fb += (int)(((size_t)c.cout * c.k_eff + 255) / 256);
+      wt.dblk_start[i] = db; db += (i == 0) ? 0 : (int)(((size_t)c.cin * c.ksize * c.ksize * c.cout + 255) / 256);
+    }
+    wt.row_start[NCONV] = rows; wt.col_start[NCONV] = cols; wt.fblk_start[NCONV] = fb; wt.dblk_start[NCONV] = db;
+    wt.wf_scale = tt->wf_scale; wt.wf_unscale = tt->wf_unscale; wt.wd_scale = tt->wd_scale; wt.wd_unscale = tt->wd_unscale;
+    w_scales_all_kernel<<<rows + cols, 256, 0, st>>>(wt);
     STRAPS_LAUNCH_CHECK();
-    pack_w_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c.w_oihw, tt->ones, tt->wf_scale + t->ch_off[i], c.cout, c.cin, c.ksize,
-                                                                     i == 0, c.k_eff, tt->wf_hi[i], tt->wf_lo[i]);
+    pack_w_all_kernel<<<fb + db, 256, 0, st>>>(wt);
     STRAPS_LAUNCH_CHECK();
   }
   if (tt->fwd_maps.find(B) == tt->fwd_maps.end()) {
@@ -1839,25 +1985,44 @@ int tc_train_conv_fwd(straps_regressor* r, int ci, int B, float* raw, cudaStream
 }
 
 int tc_train_pack_dgrad(straps_regressor* r, cudaStream_t st) {
+  // start of a backward pass.  The data-gradient operands were packed with the forward ones (pack_w_all_kernel in tc_train_begin:
+  // same weights); what is left is clearing the per-convolution max |dY| words and weight-gradient accumulators -- two memsets.
   TcState* t = static_cast<TcState*>(r->tc);
+  STRAPS_CHECK(t && t->train, "tc_train_pack_dgrad: no tensor-core training forward before this backward");
   TcTrain* tt = t->train;
-  STRAPS_CHECK(tt, "tc_train_pack_dgrad: no tensor-core training forward before this backward");
-  for (int i = 1; i < NCONV; ++i) {
-    const ConvSpec& c = r->conv[i];
-    const int kk = c.ksize * c.ksize;
-    w_colscale_kernel<<<c.cin, 256, 0, st>>>(c.w_oihw, c.cout, c.cin, kk, tt->wd_scale + tt->wd_off[i], tt->wd_unscale + tt->wd_off[i]);
-    STRAPS_LAUNCH_CHECK();
-    const size_t total = (size_t)c.cin * kk * c.cout;
-    pack_w_dgrad_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c.w_oihw, tt->wd_scale + tt->wd_off[i], c.cout, c.cin, c.ksize,
-                                                                           tt->wd_hi[i], tt->wd_lo[i]);
-    STRAPS_LAUNCH_CHECK();
-  }
+  STRAPS_CUDA(cudaMemsetAsync(tt->dy_max, 0, 64 * sizeof(unsigned), st));
+  STRAPS_CUDA(cudaMemsetAsync(tt->dw_packed, 0, tt->dw_elems * sizeof(float), st));
+  for (int i = 0; i < NCONV; ++i) tt->dw_dst[i] = nullptr;
   return 0;
 }
 
-unsigned* tc_train_dy_max(straps_regressor* r) {
+unsigned* tc_train_dy_max(straps_regressor* r, int ci) {
   TcState* t = static_cast<TcState*>(r->tc);
-  return (t && t->train) ? t->train->dy_max : nullptr;
+  return (t && t->train) ? t->train->dy_max + ci : nullptr;
+}
+
+// end of a backward pass: every weight gradient the tensor cores accumulated, [cout][k_eff] scaled -> OIHW, one launch
+int tc_train_unpack_all(straps_regressor* r, cudaStream_t st) {
+  TcState* t = static_cast<TcState*>(r->tc);
+  TcTrain* tt = t ? t->train : nullptr;
+  if (!tt) return 0;
+  DwUnpackTable u;
+  int blocks = 0;
+  for (int i = 0; i < NCONV; ++i) {
+    const ConvSpec& c = r->conv[i];
+    u.src[i] = tt->dw_packed + tt->dw_off[i];
+    u.dst[i] = tt->dw_dst[i];
+    u.cout[i] = c.cout; u.cin[i] = c.cin; u.ks[i] = c.ksize; u.k_eff[i] = c.k_eff;
+    u.blk_start[i] = blocks;
+    if (tt->dw_dst[i]) blocks += (int)(((size_t)c.cout * c.cin * c.ksize * c.ksize + 255) / 256);
+    tt->dw_dst[i] = nullptr;
+  }
+  u.blk_start[NCONV] = blocks;
+  u.maxbits = tt->dy_max;
+  if (!blocks) return 0;
+  unpack_dw_all_kernel<<<blocks, 256, 0, st>>>(u);
+  STRAPS_LAUNCH_CHECK();
+  return 0;
 }
 
 // dy: fp32 NHWC [B,hout,wout,cout] whose max |.| bits are in *dy_max  ->  scaled split planes (plain, or zero-upsampled x2 for the
@@ -1873,7 +2038,7 @@ int tc_train_split_dy(straps_regressor* r, int ci, int B, const float* dy, int u
     STRAPS_CUDA(cudaMemsetAsync(tt->dy_lo, 0, n * sizeof(__half), st));
   }
   const long long n4 = (long long)B * c.hout * c.wout * c.cout / 4;
-  split_scaled_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dy, tt->dy_max, n4, c.cout, c.hout, c.wout, up, tt->dy_hi, tt->dy_lo,
+  split_scaled_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dy, tt->dy_max + ci, n4, c.cout, c.hout, c.wout, up, tt->dy_hi, tt->dy_lo,
                                                                   ci > 0 ? tt->wd_unscale + tt->wd_off[ci] : nullptr, ci > 0 ? c.cin : 0,
                                                                   ci > 0 ? tt->dg_unscale : nullptr);
   STRAPS_LAUNCH_CHECK();
@@ -1932,13 +2097,10 @@ int tc_train_conv_wgrad(straps_regressor* r, int ci, int B, float* dw_oihw, cuda
   p.cchunks = c.cin / 64; p.kw_count = c.ksize; p.stride = c.stride; p.pad = c.pad;
   p.hw_out = c.hout * c.wout; p.wout = c.wout;
   p.k_eff = c.k_eff;
-  p.dw = tt->dw_packed;
-  STRAPS_CUDA(cudaMemsetAsync(tt->dw_packed, 0, (size_t)c.cout * c.k_eff * sizeof(float), st));
+  p.dw = tt->dw_packed + tt->dw_off[ci];       // zeroed at the start of the backward pass (tc_train_pack_dgrad)
   const TcLayerMaps& m = tt->wg_maps.at(B)[ci];
   if (bn == 64 ? launch_wgrad_tc<64>(m, p, t->num_sms, st) : launch_wgrad_tc<128>(m, p, t->num_sms, st)) return 1;
-  const size_t total = (size_t)c.cout * c.cin * c.ksize * c.ksize;
-  unpack_dw_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tt->dw_packed, tt->dy_max, c.cout, c.cin, c.ksize, ci == 0, c.k_eff, dw_oihw);
-  STRAPS_LAUNCH_CHECK();
+  tt->dw_dst[ci] = dw_oihw;                    // unpacked by tc_train_unpack_all at the end of the pass
   return 0;
 }
 

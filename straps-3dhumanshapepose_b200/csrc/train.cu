@@ -551,8 +551,7 @@ static int bn_backward(straps_regressor* r, TrainState* t, int ci, int B, const 
   const long long npix = (long long)B * c.hout * c.wout;
   const int chunks = (int)std::max<long long>(1, std::min<long long>(1184, npix / (16LL * (1024 / c.cout))));
   STRAPS_CUDA(cudaMemsetAsync(t->fstat, 0, 1024 * sizeof(float), st));
-  unsigned* maxbits = (t->mode == STRAPS_CONV_F16X3_TC) ? tc_train_dy_max(r) : nullptr;
-  if (maxbits) STRAPS_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(unsigned), st));
+  unsigned* maxbits = (t->mode == STRAPS_CONV_F16X3_TC) ? tc_train_dy_max(r, ci) : nullptr;    // zeroed at the start of the pass
   bn_bwd_reduce_kernel<<<chunks, 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], npix, c.cout, t->fstat);
   STRAPS_LAUNCH_CHECK();
   const long long n4 = npix * c.cout / 4;
@@ -721,6 +720,7 @@ extern "C" int straps_encoder_backward(straps_regressor_t* r, const float* dfeat
     if (bn_backward(r, t, 0, batch, t->gbuf[r->buf_stem], act_ptr(r, r->buf_stem), nullptr, d_bn[0], d_bn[1], st)) return 1;
     if (conv_wgrad(r, t, 0, batch, d_conv_w[0], st)) return 1;
   }
+  if (t->mode == STRAPS_CONV_F16X3_TC && straps::tc_train_unpack_all(r, st)) return 1;
   return 0;
 }
 
