@@ -54,9 +54,11 @@ constexpr int TC_OFF_B = TC_NA * TC_A_IMG;
 constexpr int TC_OFF_W = TC_OFF_B + TC_B_BYTES;
 constexpr int TC_OFF_AT = TC_OFF_W + TC_W_BYTES;            // two slots: rows 0 and 1 up front, row 2 re-uses slot 0
 constexpr int TC_OFF_BAR = TC_OFF_AT + 2 * TC_AT_BYTES;
-constexpr int TC_SMEM = TC_OFF_BAR + 256 + 1024;
+constexpr int TC_OFF_TR = TC_OFF_BAR + 256;                 // transl of the group's 64 bodies
+constexpr int TC_SMEM = TC_OFF_TR + TC_NB * 3 * 4 + 1024;
 constexpr int TC_THREADS = 320;                             // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
 constexpr int TC_EPI_THREADS = 256;
+static_assert(TC_NB * TV * 3 * 4 <= TC_OFF_W, "output staging must fit below the transform operands");
 constexpr int TC_COL_T = 3 * TC_NB;                         // TMEM: columns [0, 192) v_posed planes, [192, 448) T_r
 static_assert(TC_SMEM <= 232448, "lbs_tc_kernel shared memory");
 static_assert(TC_KREAL <= TC_K && TC_KSTEPS <= TC_CHUNKS * 4, "K padding");
@@ -257,6 +259,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
         bulk_g2s(smem + TC_OFF_AT + r * TC_AT_BYTES, at + (size_t)r * TC_AT_BYTES, TC_AT_BYTES, &at_full[r]);
       }
       const unsigned char* src = a.apk + (size_t)tile * TC_STAGES_PER_TILE * TC_A_IMG;
+      // the whole 384 KB of this tile towards L2 at once: after the encoder's activations have gone through L2 the constants are in
+      // HBM again, and five 16 KB stages in flight would fetch them in ~5 dependent round trips
+      for (int s = 0; s < TC_STAGES_PER_TILE; s += 4) bulk_prefetch_l2(src + (size_t)s * TC_A_IMG, 4 * TC_A_IMG);
       uint32_t st = 0, ph = 1;
       for (int s = 0; s < TC_STAGES_PER_TILE; ++s) {
         mbar_wait(&a_empty[st], ph);
@@ -335,6 +340,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
   const bool vok = v < V;
   const int body0 = group * TC_NB + half * 32;          // first of this thread's 32 bodies
   const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  // transl of the group's bodies once, into shared memory: a per-body __ldg inside the row loop (the first version) was a dependent
+  // L2 round trip before every output -- 96 of them per thread, 25 k of the CTA's 49 k cycles (profiles/r02_lbs_tc_ncu.txt)
+  float* s_tr = reinterpret_cast<float*>(smem + TC_OFF_TR);
+  for (int i = threadIdx.x - 64; i < TC_NB * 3; i += TC_EPI_THREADS) {
+    const int gb = group * TC_NB + i / 3;
+    s_tr[i] = (a.transl && gb < a.B) ? a.transl[(size_t)gb * 3 + i % 3] : 0.f;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
   mbar_wait(vp_full, 0);
   tc_fence_after();
   float ainv[3];
@@ -360,6 +373,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
   }
   // out_r = T_r . [v_posed ; 1]: the v_posed accumulators are re-read from TMEM for every row (24 registers instead of 96 held
   // across the loop; 10 warps leave 168 registers per thread), with 1 / (all scales) folded into three per-thread constants
+  // output staging [64 bodies][128 vertices x 3] fp32 = 96 KB over the A ring and Bm: both are dead once vp_full has completed
+  float* sout = reinterpret_cast<float*>(smem);
   constexpr float tscale = 1.f / (TC_WSCALE * TC_BSCALE);
   const float k0 = ainv[0] * tscale, k1 = ainv[1] * tscale, k2 = ainv[2] * tscale;
 #pragma unroll 1
@@ -377,18 +392,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
       for (int bb = 0; bb < 8; ++bb) {
         const int gb = body0 + q * 8 + bb;
         if (gb < a.B && vok) {
-          const float tr = a.transl ? __ldg(a.transl + (size_t)gb * 3 + r) : 0.f;
+          const float tr = s_tr[(q * 8 + bb + half * 32) * 3 + r];
           float acc = fmaf(__uint_as_float(t[bb * 4 + 3]), tscale, tr);
           acc = fmaf(__uint_as_float(t[bb * 4 + 0]) * k0, __uint_as_float(d[0][bb]), acc);
           acc = fmaf(__uint_as_float(t[bb * 4 + 1]) * k1, __uint_as_float(d[1][bb]), acc);
           acc = fmaf(__uint_as_float(t[bb * 4 + 2]) * k2, __uint_as_float(d[2][bb]), acc);
-          a.verts[((size_t)gb * V + v) * 3 + r] = acc;
+          sout[(q * 8 + bb + half * 32) * (TV * 3) + row * 3 + r] = acc;        // lanes 3 words apart: conflict free
         }
       }
     }
     if (r < 2) {
       tc_fence_before();
       mbar_arrive(t_empty);
+    }
+  }
+  // the tile's vertices of one body are 1536 contiguous bytes of the output: written from the staging buffer with full-width
+  // stores.  (The first version stored each coordinate from its thread -- 4 bytes every 12 -- i.e. 12 partially written sectors
+  // per warp instruction, 144 sector writes per body and tile instead of 48: B = 4096 took 582 us.)
+  asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+  {
+    const int n2 = (min(TV, V - tile * TV) * 3) / 2;            // float2 per body (384 or 318 floats: both even)
+    for (int b = warp - 2; b < TC_NB; b += TC_EPI_THREADS / 32) {
+      const int gb = group * TC_NB + b;
+      if (gb >= a.B) break;
+      const float2* src = reinterpret_cast<const float2*>(sout + b * (TV * 3));
+      float2* dst = reinterpret_cast<float2*>(a.verts + ((size_t)gb * V + (size_t)tile * TV) * 3);      // 8-byte aligned (82,680 B per body)
+      for (int i = lane; i < n2; i += 32) dst[i] = src[i];
     }
   }
   }

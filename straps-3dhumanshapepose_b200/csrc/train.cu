@@ -349,19 +349,29 @@ __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int cout, int c
 // ------------------------------------------------------------------------------------------------
 // small GEMM for the IEF backward:  C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C,  row-major with leading dims
 // ------------------------------------------------------------------------------------------------
+// C (+)= op(A) op(B), fp32, 32x32 tiles.  gridDim.z > 1 splits K: every slice adds its partial tile with atomics, so C must hold the
+// value to accumulate onto (zeros for a plain product).  The tile loads walk the CONTIGUOUS index of each operand with consecutive
+// threads whatever the transposition (round 1 read transposed operands with a stride of lda / ldb floats between lanes).
 __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, int lda, int ta, const float* __restrict__ Bm, int ldb, int tb,
-                                                   float* __restrict__ C, int ldc, int M, int N, int K, float beta) {
+                                                   float* __restrict__ C, int ldc, int M, int N, int K, float beta, int k_per) {
   __shared__ float As[32][33], Bs[32][33];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int kbeg = blockIdx.z * k_per, kend = min(K, kbeg + k_per);
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < K; k0 += 32) {
+  for (int k0 = kbeg; k0 < kend; k0 += 32) {
     for (int i = threadIdx.x; i < 1024; i += 256) {
-      const int r = i >> 5, c = i & 31;
-      const int m = m0 + r, k = k0 + c;      // As[r][c] = op(A)[m][k]
-      As[r][c] = (m < M && k < K) ? (ta ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
-      const int kk = k0 + r, n = n0 + c;     // Bs[r][c] = op(B)[kk][n]
-      Bs[r][c] = (kk < K && n < N) ? (tb ? Bm[(size_t)n * ldb + kk] : Bm[(size_t)kk * ldb + n]) : 0.f;
+      const int lo = i & 31, hi = i >> 5;
+      {                                        // As[r][c] = op(A)[m0 + r][k0 + c]
+        const int r = ta ? lo : hi, c = ta ? hi : lo;
+        const int m = m0 + r, k = k0 + c;
+        As[r][c] = (m < M && k < kend) ? (ta ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
+      }
+      {                                        // Bs[r][c] = op(B)[k0 + r][n0 + c]
+        const int r = tb ? lo : hi, c = tb ? hi : lo;
+        const int kk = k0 + r, n = n0 + c;
+        Bs[r][c] = (kk < kend && n < N) ? (tb ? Bm[(size_t)n * ldb + kk] : Bm[(size_t)kk * ldb + n]) : 0.f;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -377,7 +387,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int m = m0 + ty * 2 + i, n = n0 + tx * 2 + j;
-      if (m < M && n < N) C[(size_t)m * ldc + n] = acc[i][j] + (beta != 0.f ? beta * C[(size_t)m * ldc + n] : 0.f);
+      if (m < M && n < N) {
+        if (gridDim.z > 1) atomicAdd(&C[(size_t)m * ldc + n], acc[i][j]);
+        else C[(size_t)m * ldc + n] = acc[i][j] + (beta != 0.f ? beta * C[(size_t)m * ldc + n] : 0.f);
+      }
     }
 }
 // y[b][n] *= (h[b][n] > 0)
@@ -438,14 +451,21 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 
 static int gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C, int ldc, int M, int N, int K, float beta,
                 cudaStream_t st) {
-  gemm_kernel<<<dim3(ceil_div(N, 32), ceil_div(M, 32)), 256, 0, st>>>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta);
+  // few tiles and a long K (the data gradients of the IEF layers: M = batch): split K over enough CTAs to fill the machine
+  const int tiles = ceil_div(N, 32) * ceil_div(M, 32);
+  int splits = 1;
+  if (tiles < 120 && K >= 128 && (beta == 0.f || beta == 1.f)) splits = std::min(ceil_div(K, 32), std::max(1, 296 / tiles));
+  const int k_per = ceil_div(ceil_div(K, splits), 32) * 32;
+  splits = ceil_div(K, k_per);
+  if (splits > 1 && beta == 0.f) {
+    STRAPS_CHECK(ldc == N, "gemm: split-K needs a dense C to clear");
+    STRAPS_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st));
+  }
+  gemm_kernel<<<dim3(ceil_div(N, 32), ceil_div(M, 32), splits), 256, 0, st>>>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, k_per);
   STRAPS_LAUNCH_CHECK();
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// training workspace
-// ------------------------------------------------------------------------------------------------
 static int train_ensure(straps_regressor* r) {
   if (r->train) return 0;
   TrainState* t = new TrainState();
