@@ -2001,6 +2001,19 @@ unsigned* tc_train_dy_max(straps_regressor* r, int ci) {
   return (t && t->train) ? t->train->dy_max + ci : nullptr;
 }
 
+// where bn_backward's apply pass writes the scaled split planes of dX (= dY of conv ci), and what its scale kernel needs to publish the
+// data gradient's epilogue unscales (row unscales of the packed weights x 2^-e)
+void tc_train_dy_planes(straps_regressor* r, int ci, __half** hi, __half** lo) {
+  TcTrain* tt = static_cast<TcState*>(r->tc)->train;
+  (void)ci;
+  *hi = tt->dy_hi; *lo = tt->dy_lo;
+}
+void tc_train_dgrad_scales(straps_regressor* r, int ci, const float** w_unscale, int* n, float** out_unscale) {
+  TcTrain* tt = static_cast<TcState*>(r->tc)->train;
+  if (ci > 0) { *w_unscale = tt->wd_unscale + tt->wd_off[ci]; *n = r->conv[ci].cin; *out_unscale = tt->dg_unscale; }
+  else { *w_unscale = nullptr; *n = 0; *out_unscale = nullptr; }
+}
+
 // end of a backward pass: every weight gradient the tensor cores accumulated, [cout][k_eff] scaled -> OIHW, one launch
 int tc_train_unpack_all(straps_regressor* r, cudaStream_t st) {
   TcState* t = static_cast<TcState*>(r->tc);

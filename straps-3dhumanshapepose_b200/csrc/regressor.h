@@ -132,6 +132,8 @@ int tc_train_pack_dgrad(straps_regressor* r, cudaStream_t st);
 int tc_train_split_dy(straps_regressor* r, int ci, int batch, const float* dy, int upsample, cudaStream_t st);   // scaled split of dY
 int tc_train_conv_wgrad(straps_regressor* r, int ci, int batch, float* dw_oihw, cudaStream_t st);                // needs the plain split
 unsigned* tc_train_dy_max(straps_regressor* r, int ci);                                    // device word of conv ci: bits of max |dY| (atomicMax target)
+void tc_train_dy_planes(straps_regressor* r, int ci, __half** hi, __half** lo);              // split planes bn_backward writes dX into
+void tc_train_dgrad_scales(straps_regressor* r, int ci, const float** w_unscale, int* n, float** out_unscale);
 int tc_train_unpack_all(straps_regressor* r, cudaStream_t st);                             // end of a backward pass: all weight gradients -> OIHW
 int tc_train_conv_dgrad(straps_regressor* r, int ci, int batch, const float* add, float* gin, cudaStream_t st);  // needs the split
 inline float* act_ptr(const straps_regressor* r, int buf) { return reinterpret_cast<float*>(r->ws + r->bufs[buf].offset); }

@@ -31,13 +31,14 @@ struct TrainState {
   float* mean[NCONV];
   float* invstd[NCONV];
   double* dstat;               // [2][512] fp64 accumulators
-  float* fstat;                // [2][512] fp32 reductions (dbeta, dgamma)
+  float* fstat;                // [2][512] fp32 reductions (dbeta, dgamma) + [2][512] per-channel maxima (bits)
   float* ones; float* zeros;   // [512]
   float* w_dgrad[NCONV];       // [(kh,kw,co)][ci]
   float* dw_packed;            // [(kh,kw,ci_pad)][cout] scratch for the weight gradient (largest conv)
   int last_batch;
   int mode;                    // STRAPS_CONV_* of the last training forward (the backward follows it)
   int xin_valid;               // the fp32 NHWC copy of the input (CUDA-core conv1 weight gradient) matches the last forward
+  bool draw_valid;             // the last bn_backward wrote the fp32 gradient `draw` (else only its split planes exist)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -133,12 +134,13 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ gout, const float* __restrict__ act,
                                                             const float* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, long long npix, int C,
-                                                            float* __restrict__ acc) {
+                                                            float* __restrict__ acc, unsigned* __restrict__ cmax) {
   __shared__ float red[2][256][4];
   const int tq = C >> 2, lanes = 256 / tq;
   const int q = threadIdx.x % tq, pl = threadIdx.x / tq;
   const float4 mu = *reinterpret_cast<const float4*>(mean + 4 * q), is = *reinterpret_cast<const float4*>(invstd + 4 * q);
   float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+  float mdy[4] = {0, 0, 0, 0}, mxc[4] = {0, 0, 0, 0};       // max |dy| and max |x - mean| (bound of max |dx|: bn_bwd_scale_kernel)
   const long long stride = (long long)gridDim.x * lanes;
   for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += 4 * stride) {
     float4 dy[4], xv[4], av[4];
@@ -158,6 +160,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
       s0[0] += d0; s0[1] += d1; s0[2] += d2; s0[3] += d3;
       s1[0] += d0 * (xv[u].x - mu.x) * is.x; s1[1] += d1 * (xv[u].y - mu.y) * is.y;
       s1[2] += d2 * (xv[u].z - mu.z) * is.z; s1[3] += d3 * (xv[u].w - mu.w) * is.w;
+      mdy[0] = fmaxf(mdy[0], fabsf(d0)); mdy[1] = fmaxf(mdy[1], fabsf(d1)); mdy[2] = fmaxf(mdy[2], fabsf(d2)); mdy[3] = fmaxf(mdy[3], fabsf(d3));
+      mxc[0] = fmaxf(mxc[0], fabsf(xv[u].x - mu.x)); mxc[1] = fmaxf(mxc[1], fabsf(xv[u].y - mu.y));
+      mxc[2] = fmaxf(mxc[2], fabsf(xv[u].z - mu.z)); mxc[3] = fmaxf(mxc[3], fabsf(xv[u].w - mu.w));
     }
   }
 #pragma unroll
@@ -169,18 +174,79 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     atomicAdd(&acc[c], t0);
     atomicAdd(&acc[C + c], t1);
   }
+  if (cmax) {                                  // non-negative floats order like their bit patterns
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { red[0][threadIdx.x][k] = mdy[k]; red[1][threadIdx.x][k] = mxc[k]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int l = 0; l < lanes; ++l) { t0 = fmaxf(t0, red[0][l * tq + (c >> 2)][c & 3]); t1 = fmaxf(t1, red[1][l * tq + (c >> 2)][c & 3]); }
+      atomicMax(&cmax[c], __float_as_uint(t0));
+      atomicMax(&cmax[C + c], __float_as_uint(t1));
+    }
+  }
 }
-// dx = gamma * invstd * (dy - sum_dy/N - xhat * sum_dy_xhat/N);   optionally also writes the masked dy and the max |dx|.
+
+// One block between the two passes: dbeta / dgamma to the caller's tensors, and -- tensor-core mode -- an upper bound of max |dx| from
+// the per-channel sums and maxima, |dx| <= |gamma| invstd (max|dy| + |sum dy| / N + max|x - mean| invstd |sum dy xhat| / N).  Its bits go
+// to *maxbits: the power of two that puts it into [2^13, 2^14) scales dX before the fp16 split (done by bn_bwd_apply_kernel itself
+// instead of a separate pass over the tensor), is undone by the weight-gradient unpack, and -- folded into the data gradient's row
+// unscales here -- by the data-gradient epilogue.  The bound is at most a few times the true maximum: two or three of fp16's thirty
+// binades.
+__global__ void __launch_bounds__(512) bn_bwd_scale_kernel(const float* __restrict__ acc, const unsigned* __restrict__ cmax,
+                                                           const float* __restrict__ gamma, const float* __restrict__ invstd, int C, float inv_n,
+                                                           float* __restrict__ dbeta, float* __restrict__ dgamma, unsigned* __restrict__ maxbits,
+                                                           const float* __restrict__ w_unscale, int n_unscale, float* __restrict__ out_unscale) {
+  __shared__ float red[16];
+  __shared__ int s_e;
+  const int c = threadIdx.x;
+  float bound = 0.f;
+  if (c < C) {
+    const float s0 = acc[c], s1 = acc[C + c];
+    dbeta[c] = s0;
+    dgamma[c] = s1;
+    if (maxbits) {
+      const float is = invstd[c];
+      bound = fabsf(gamma[c]) * is * (__uint_as_float(cmax[c]) + fabsf(s0) * inv_n + __uint_as_float(cmax[C + c]) * is * fabsf(s1) * inv_n);
+    }
+  }
+  if (!maxbits) return;
+  for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bound;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int k = 1; k < 16; ++k) m = fmaxf(m, red[k]);
+    *maxbits = __float_as_uint(m);
+    int e = 0;
+    if (m > 0.f && isfinite(m)) { frexpf(m, &e); e = max(-100, min(100, 14 - e)); }
+    s_e = e;
+  }
+  __syncthreads();
+  if (out_unscale) {
+    const float inv = ldexpf(1.f, -s_e);
+    for (int k = threadIdx.x; k < n_unscale; k += 512) out_unscale[k] = w_unscale[k] * inv;
+  }
+}
+// dx = gamma * invstd * (dy - sum_dy/N - xhat * sum_dy_xhat/N) as fp32 (dx != null) and / or as scaled fp16 split planes (p_hi != null);
+// optionally also writes the masked dy.
 // 4 float4 per thread; n4 = npix * C / 4
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ gout, const float* __restrict__ act,
                                                            const float* __restrict__ x, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ acc, long long npix, int C, float* __restrict__ dx,
-                                                           float* __restrict__ masked_out, unsigned* __restrict__ maxbits) {
-  __shared__ unsigned smax[8];
+                                                           float* __restrict__ masked_out, const unsigned* __restrict__ maxbits,
+                                                           __half* __restrict__ p_hi, __half* __restrict__ p_lo) {
   const long long n4 = npix * C / 4;
   const float inv_n = 1.f / (float)npix;
-  float m = 0.f;
+  float sc = 1.f;
+  if (p_hi) {                                  // scaled fp16 split planes of dX for the tensor-core gradients (bound: bn_bwd_scale_kernel)
+    int e = 0;
+    const float mx = __uint_as_float(*maxbits);
+    if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); e = max(-100, min(100, 14 - e)); }
+    sc = ldexpf(1.f, e);
+  }
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const long long i = ((long long)blockIdx.x * 4 + it) * 256 + threadIdx.x;
@@ -204,18 +270,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     r.y = ga.y * is.y * (dy.y - s0.y * inv_n - ((xv.y - mu.y) * is.y) * s1.y * inv_n);
     r.z = ga.z * is.z * (dy.z - s0.z * inv_n - ((xv.z - mu.z) * is.z) * s1.z * inv_n);
     r.w = ga.w * is.w * (dy.w - s0.w * inv_n - ((xv.w - mu.w) * is.w) * s1.w * inv_n);
-    reinterpret_cast<float4*>(dx)[i] = r;
-    m = fmaxf(fmaxf(m, fmaxf(fabsf(r.x), fabsf(r.y))), fmaxf(fabsf(r.z), fabsf(r.w)));
-  }
-  if (maxbits) {   // max |dx| for the power-of-two scale of the tensor-core gradients (non-negative floats order like their bits)
-    const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = w;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned t = smax[0];
-#pragma unroll
-      for (int k = 1; k < 8; ++k) t = max(t, smax[k]);
-      if (t) atomicMax(maxbits, t);
+    if (dx) reinterpret_cast<float4*>(dx)[i] = r;
+    if (p_hi) {
+      __half h[4], l[4];
+      split_f16(r.x * sc, h[0], l[0]); split_f16(r.y * sc, h[1], l[1]); split_f16(r.z * sc, h[2], l[2]); split_f16(r.w * sc, h[3], l[3]);
+      reinterpret_cast<uint2*>(p_hi)[i] = make_uint2(pack_f16(h[0], h[1]), pack_f16(h[2], h[3]));
+      reinterpret_cast<uint2*>(p_lo)[i] = make_uint2(pack_f16(l[0], l[1]), pack_f16(l[2], l[3]));
     }
   }
 }
@@ -493,7 +553,7 @@ static int train_ensure(straps_regressor* r) {
   const size_t off_gmask = take((size_t)r->max_batch * 64 * 64 * 64);
   const size_t off_draw = take(max_act);
   const size_t off_dw = take(max_w);
-  const size_t off_fstat = take(1024), off_ones = take(512), off_zeros = take(512);
+  const size_t off_fstat = take(2048), off_ones = take(512), off_zeros = take(512);
   const size_t off_dstat = take(2048);   // 1024 doubles
   t->pool_bytes = fl * sizeof(float);
   if (cudaMalloc(&t->pool, t->pool_bytes) != cudaSuccess) {
@@ -519,7 +579,7 @@ static int train_ensure(straps_regressor* r) {
 
 const float* train_last_draw(const straps_regressor* r) {
   const TrainState* t = static_cast<const TrainState*>(r->train);
-  return t ? t->draw : nullptr;
+  return (t && t->draw_valid) ? t->draw : nullptr;      // null when the last gradient exists as split planes only
 }
 
 void train_destroy(straps_regressor* r) {
@@ -565,34 +625,53 @@ static int bn_forward(straps_regressor* r, TrainState* t, int ci, int B, const f
 
 // gout: gradient wrt the BN output (after the optional ReLU whose output is `act`); writes d(raw conv out) into t->draw,
 // dgamma/dbeta into the caller's tensors, and (optionally) the ReLU-masked gout into masked_out.
-static int bn_backward(straps_regressor* r, TrainState* t, int ci, int B, const float* gout, const float* act, float* masked_out,
-                       float* dgamma, float* dbeta, cudaStream_t st) {
-  const ConvSpec& c = r->conv[ci];
-  const long long npix = (long long)B * c.hout * c.wout;
-  const int chunks = (int)std::max<long long>(1, std::min<long long>(1184, npix / (16LL * (1024 / c.cout))));
-  STRAPS_CUDA(cudaMemsetAsync(t->fstat, 0, 1024 * sizeof(float), st));
-  unsigned* maxbits = (t->mode == STRAPS_CONV_F16X3_TC) ? tc_train_dy_max(r, ci) : nullptr;    // zeroed at the start of the pass
-  bn_bwd_reduce_kernel<<<chunks, 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], npix, c.cout, t->fstat);
-  STRAPS_LAUNCH_CHECK();
-  const long long n4 = npix * c.cout / 4;
-  bn_bwd_apply_kernel<<<(unsigned)((n4 + 1023) / 1024), 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], c.gamma, t->fstat, npix,
-                                                                 c.cout, t->draw, masked_out, maxbits);
-  STRAPS_LAUNCH_CHECK();
-  STRAPS_CUDA(cudaMemcpyAsync(dbeta, t->fstat, c.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  STRAPS_CUDA(cudaMemcpyAsync(dgamma, t->fstat + c.cout, c.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  return 0;
-}
-
 static bool wgrad_on_tc() {
   const char* e = getenv("STRAPS_WGRAD");      // "simt" keeps the fp32 CUDA-core weight gradient in tensor-core mode (debugging)
   return !(e && e[0] == 's');
 }
 
+static int bn_backward(straps_regressor* r, TrainState* t, int ci, int B, const float* gout, const float* act, float* masked_out,
+                       float* dgamma, float* dbeta, cudaStream_t st) {
+  const ConvSpec& c = r->conv[ci];
+  const long long npix = (long long)B * c.hout * c.wout;
+  const int chunks = (int)std::max<long long>(1, std::min<long long>(1184, npix / (16LL * (1024 / c.cout))));
+  STRAPS_CUDA(cudaMemsetAsync(t->fstat, 0, 2048 * sizeof(float), st));      // sums [2][512] and maxima [2][512]
+  const bool tc = t->mode == STRAPS_CONV_F16X3_TC;
+  // tensor-core gradients read dX as scaled fp16 split planes: written here by the apply pass (no separate split pass over the tensor).
+  // The fp32 tensor is still written where something reads it: the zero-upsampled split of a stride-2 data gradient, the CUDA-core
+  // weight gradient, the fp32 mode.
+  const bool planes = tc && wgrad_on_tc();
+  const bool need_f32 = !planes || c.stride == 2;
+  unsigned* maxbits = tc ? tc_train_dy_max(r, ci) : nullptr;
+  unsigned* cmax = reinterpret_cast<unsigned*>(t->fstat + 1024);
+  bn_bwd_reduce_kernel<<<chunks, 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], npix, c.cout, t->fstat, tc ? cmax : nullptr);
+  STRAPS_LAUNCH_CHECK();
+  const float* w_unscale = nullptr;
+  float* out_unscale = nullptr;
+  int n_unscale = 0;
+  __half *p_hi = nullptr, *p_lo = nullptr;
+  if (tc) {
+    tc_train_dgrad_scales(r, ci, &w_unscale, &n_unscale, &out_unscale);
+    if (planes) tc_train_dy_planes(r, ci, &p_hi, &p_lo);
+  }
+  bn_bwd_scale_kernel<<<1, 512, 0, st>>>(t->fstat, cmax, c.gamma, t->invstd[ci], c.cout, 1.f / (float)npix, dbeta, dgamma, maxbits, w_unscale,
+                                        n_unscale, out_unscale);
+  STRAPS_LAUNCH_CHECK();
+  const long long n4 = npix * c.cout / 4;
+  bn_bwd_apply_kernel<<<(unsigned)((n4 + 1023) / 1024), 256, 0, st>>>(gout, act, t->raw[ci], t->mean[ci], t->invstd[ci], c.gamma, t->fstat, npix,
+                                                                 c.cout, need_f32 ? t->draw : nullptr, masked_out, maxbits, p_hi, p_lo);
+  STRAPS_LAUNCH_CHECK();
+  t->draw_valid = need_f32;
+  return 0;
+}
+
+
 static int conv_wgrad(straps_regressor* r, TrainState* t, int ci, int B, float* dw_oihw, cudaStream_t st) {
   if (t->mode == STRAPS_CONV_F16X3_TC) {
-    // the plain split of dY serves the weight gradient and (stride-1 convs) the data gradient that follows
-    if (tc_train_split_dy(r, ci, B, t->draw, 0, st)) return 1;
+    // the plain split planes of dY (written by bn_backward's apply pass) serve the weight gradient and, for stride-1 convs, the data
+    // gradient that follows; with the CUDA-core weight gradient they are made here from the fp32 tensor
     if (wgrad_on_tc()) return tc_train_conv_wgrad(r, ci, B, dw_oihw, st);
+    if (tc_train_split_dy(r, ci, B, t->draw, 0, st)) return 1;
   }
   const ConvSpec& c = r->conv[ci];
   const size_t nw = (size_t)c.ksize * c.ksize * c.cin_pad * c.cout;
