@@ -27,6 +27,8 @@
 #include <cuda_fp16.h>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+#include <algorithm>
 
 namespace straps {
 
@@ -111,6 +113,7 @@ struct ChainArgs {
   float* joints;                // [B][90][3]: rows 0..23 written here
   unsigned char* bimg;
   unsigned char* atimg;
+  int at_layout;                // 0: [r][hi|lo][256 rows] (lbs_tc_kernel)   1: [half][r][hi|lo][128 rows] (lbs_tc3_kernel)
   float* save_A;                // training: the transforms as fp32 [B][24][12] in the caller's tensor, or null
 };
 
@@ -139,12 +142,34 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
       tc_rodrigues(r, &sR[b][j][0]);
     }
   } else {
-    for (int i = tid; i < CH_TB * NJ * 9; i += 128) {
-      int b = i / (NJ * 9), r = i % (NJ * 9), j = r / 9, e = r % 9;
+    // fully unrolled so that all of a thread's loads are in flight together: as a rolled loop every iteration waited for its own
+    // L2 / HBM round trip (14 of them in a row -- most of this kernel's 20 us at any batch size)
+    constexpr int NIT = (CH_TB * NJ * 9 + 127) / 128;
+    float val[NIT];
+#pragma unroll
+    for (int u = 0; u < NIT; ++u) {
+      const int i = tid + u * 128;
+      const int b = i / (NJ * 9), r = i % (NJ * 9), j = r / 9, e = r % 9;
       float v = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
-      if (b < nb) v = (j == 0) ? a.go[(size_t)(b0 + b) * a.go_stride + e] : a.bp[(size_t)(b0 + b) * a.bp_stride + (j - 1) * 9 + e];
-      sR[b][j][e] = v;
+      if (i < CH_TB * NJ * 9 && b < nb)
+        v = (j == 0) ? a.go[(size_t)(b0 + b) * a.go_stride + e] : a.bp[(size_t)(b0 + b) * a.bp_stride + (j - 1) * 9 + e];
+      val[u] = v;
     }
+#pragma unroll
+    for (int u = 0; u < NIT; ++u) {
+      const int i = tid + u * 128;
+      if (i < CH_TB * NJ * 9) (&sR[0][0][0])[i] = val[u];
+    }
+  }
+  // rest-joint regressors of this thread's outputs, fetched before the barrier for the same reason
+  constexpr int NJT = (CH_TB * NJ * 3 + 127) / 128;
+  float jsv[NJT][STRAPS_NUM_BETAS], jtv[NJT];
+#pragma unroll
+  for (int u = 0; u < NJT; ++u) {
+    const int i = tid + u * 128, jc = (i % (NJ * 3));
+#pragma unroll
+    for (int l = 0; l < STRAPS_NUM_BETAS; ++l) jsv[u][l] = m.js[jc * STRAPS_NUM_BETAS + l];
+    jtv[u] = m.jt[jc];
   }
   __syncthreads();
   // Bm = [R_j - I (j = 1..23) | betas | 1 | 0...] * 2^10, fp16 hi / lo, in the SWIZZLE_128B image of its body group
@@ -162,12 +187,16 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
     const size_t off = ((size_t)(g * TC_CHUNKS + kc) * 2) * TC_B_IMG + (size_t)r * 128 + (size_t)((u ^ (r & 7)) << 4) + (size_t)e * 2;
     tc_split_store(a.bimg, TC_B_IMG, off, v * TC_BSCALE);
   }
-  for (int i = tid; i < CH_TB * NJ * 3; i += 128) {
-    int b = i / (NJ * 3), jc = i % (NJ * 3);
-    float acc = 0.f;
 #pragma unroll
-    for (int l = 0; l < STRAPS_NUM_BETAS; ++l) acc = fmaf(m.js[jc * STRAPS_NUM_BETAS + l], sbeta[b][l], acc);
-    sJ[b][jc / 3][jc % 3] = m.jt[jc] + acc;
+  for (int u = 0; u < NJT; ++u) {
+    const int i = tid + u * 128;
+    if (i < CH_TB * NJ * 3) {
+      const int b = i / (NJ * 3), jc = i % (NJ * 3);
+      float acc = 0.f;
+#pragma unroll
+      for (int l = 0; l < STRAPS_NUM_BETAS; ++l) acc = fmaf(jsv[u][l], sbeta[b][l], acc);
+      sJ[b][jc / 3][jc % 3] = jtv[u] + acc;
+    }
   }
   __syncthreads();
   for (int lvl = 0; lvl < m.nlevels; ++lvl) {
@@ -203,12 +232,15 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
     const bool live = b < nb;
     const float row[4] = {live ? g[0] : 0.f, live ? g[1] : 0.f, live ? g[2] : 0.f, live ? t : 0.f};
     const int grp = gb / TC_NB, bl = gb % TC_NB;
-    unsigned char* img = a.atimg + (size_t)grp * TC_AT_GROUP + (size_t)r * TC_AT_BYTES;
+    // layout 0: one image pair per output row r, 256 rows; layout 1: one pair per (half of the group, r), 128 rows
+    unsigned char* img = a.atimg + (size_t)grp * TC_AT_GROUP +
+                         (a.at_layout ? (size_t)((bl >> 5) * 3 + r) * (TC_AT_BYTES / 2) : (size_t)r * TC_AT_BYTES);
+    const size_t lo_dist = a.at_layout ? TC_AT_IMG / 2 : TC_AT_IMG;
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
-      const int n = bl * 4 + c4;
+      const int n = (a.at_layout ? (bl & 31) : bl) * 4 + c4;
       const size_t off = (size_t)n * 64 + (size_t)(((j >> 3) ^ ((n >> 1) & 3)) << 4) + (size_t)(j & 7) * 2;
-      tc_split_store(img, TC_AT_IMG, off, row[c4] * TC_BSCALE);
+      tc_split_store(img, lo_dist, off, row[c4] * TC_BSCALE);
     }
     if (live) {
       if (a.save_A) *reinterpret_cast<float4*>(a.save_A + ((size_t)gb * NJ + j) * 12 + r * 4) = make_float4(row[0], row[1], row[2], row[3]);
@@ -429,6 +461,285 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// lbs_tc3_kernel: the same two GEMMs as lbs_tc_kernel, persistent and software pipelined.
+//
+// What ncu showed for lbs_tc_kernel (one CTA per work item, profiles/r02_lbs_tc_ncu.txt): the tensor pipe was busy 23 % of the time;
+// an item (128 vertices x 64 bodies) took 16 us of which 8.6 us was the blend phase WAITING FOR ITS OPERANDS -- 464 KB through 80 KB
+// of ring = one L2 round trip (~1.5 us under load) per 80 KB, 54 GB/s per SM -- and the stream stood still during the transform
+// phases, the epilogue, the copy-out and the next CTA's start-up.  Here:
+//   * a CTA walks a contiguous range of items; the producer runs ahead across item boundaries, so the stream never stops;
+//   * every operand is streamed (Bm per K chunk, the transform operand per phase): the A ring gets 128 KB instead of 80;
+//   * v_posed accumulators are double buffered in TMEM (2 x 192 columns + 128 for T = 512), and because tcgen05.mma executes in
+//     issue order the issuer INTERLEAVES: six chunks of the next item's blend GEMM alternate with the six transform phases
+//     (half of the group x output row) of the current item, so the epilogue of phase p runs under blend chunk p + 1.
+// Producer and issuer follow the same operand order, so a full ring can only wait on work that has already been issued.
+constexpr int T3_NA = 8;                                    // A ring slots of 16 KB
+constexpr int T3_BM_SLOT = 2 * TC_B_IMG;                    // Bm of one K chunk, hi + lo: 16 KB
+constexpr int T3_AT_SLOT = TC_AT_BYTES / 2;                 // transform operand of one phase (32 bodies x 4 columns, hi + lo): 16 KB
+constexpr int T3_OFF_BM = T3_NA * TC_A_IMG;                 // 2 slots
+constexpr int T3_OFF_W = T3_OFF_BM + 2 * T3_BM_SLOT;        // 2 slots
+constexpr int T3_OFF_AT = T3_OFF_W + 2 * TC_W_BYTES;        // 2 slots
+constexpr int T3_OFF_BAR = T3_OFF_AT + 2 * T3_AT_SLOT;
+constexpr int T3_OFF_TR = T3_OFF_BAR + 512;
+constexpr int T3_SMEM = T3_OFF_TR + TC_NB * 3 * 4 + 1024;
+constexpr int T3_TN = 128;                                  // transform GEMM N per phase
+constexpr int T3_COL_T = 2 * 3 * TC_NB;                     // TMEM: [0,192) v_posed buffer 0, [192,384) buffer 1, [384,512) T
+static_assert(T3_SMEM <= 232448 && T3_COL_T + T3_TN <= 512, "lbs_tc3_kernel resources");
+
+struct LbsTc3Args {
+  LbsTcArgs k;
+  int n_items;                  // groups * NTILES, item = group * NTILES + tile
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc3_kernel(const LbsTc3Args args) {
+  const LbsTcArgs& a = args.k;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T3_OFF_BAR);
+  uint64_t* a_full = bars;                    // [T3_NA]
+  uint64_t* a_empty = a_full + T3_NA;         // [T3_NA]
+  uint64_t* bm_full = a_empty + T3_NA;        // [2]
+  uint64_t* bm_empty = bm_full + 2;           // [2]
+  uint64_t* wk_full = bm_empty + 2;           // [2]
+  uint64_t* wk_empty = wk_full + 2;           // [2]
+  uint64_t* at_full = wk_empty + 2;           // [2]
+  uint64_t* at_empty = at_full + 2;           // [2]
+  uint64_t* vp_full = at_empty + 2;           // [2]
+  uint64_t* vp_empty = vp_full + 2;           // [2]
+  uint64_t* t_full = vp_empty + 2;
+  uint64_t* t_empty = t_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i_beg = (int)((long long)blockIdx.x * args.n_items / gridDim.x);
+  const int i_end = (int)((long long)(blockIdx.x + 1) * args.n_items / gridDim.x);
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < T3_NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bm_full[i], 1); mbar_init(&bm_empty[i], 1); mbar_init(&wk_full[i], 1); mbar_init(&wk_empty[i], 1);
+      mbar_init(&at_full[i], 1); mbar_init(&at_empty[i], 1); mbar_init(&vp_full[i], 1); mbar_init(&vp_empty[i], TC_EPI_THREADS);
+    }
+    mbar_init(t_full, 1); mbar_init(t_empty, TC_EPI_THREADS);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem0 = smem_u32(smem);
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // ================= producer =================
+      uint32_t na = 0, nbm = 0, nwk = 0, nat = 0;            // loads issued so far into each ring
+      auto blend_stage = [&](int item, int s) {
+        const int group = item / NTILES, tile = item % NTILES;
+        if (s % 6 == 0) {                                    // Bm of K chunk s / 6 goes first
+          const uint32_t sl = nbm & 1;
+          mbar_wait(&bm_empty[sl], ((nbm >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&bm_full[sl], T3_BM_SLOT);
+          bulk_g2s(smem + T3_OFF_BM + sl * T3_BM_SLOT, a.bimg + ((size_t)group * TC_CHUNKS + s / 6) * T3_BM_SLOT, T3_BM_SLOT, &bm_full[sl]);
+          ++nbm;
+        }
+        const uint32_t sl = na % T3_NA;
+        mbar_wait(&a_empty[sl], ((na / T3_NA) & 1) ^ 1);
+        mbar_arrive_expect_tx(&a_full[sl], TC_A_IMG);
+        bulk_g2s(smem + sl * TC_A_IMG, a.apk + ((size_t)tile * TC_STAGES_PER_TILE + s) * TC_A_IMG, TC_A_IMG, &a_full[sl]);
+        ++na;
+      };
+      if (i_beg < i_end)
+        for (int s = 0; s < TC_STAGES_PER_TILE; ++s) blend_stage(i_beg, s);
+      for (int item = i_beg; item < i_end; ++item) {
+        const int group = item / NTILES, tile = item % NTILES;
+        {
+          const uint32_t sl = nwk & 1;
+          mbar_wait(&wk_empty[sl], ((nwk >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&wk_full[sl], TC_W_BYTES);
+          bulk_g2s(smem + T3_OFF_W + sl * TC_W_BYTES, a.wk + (size_t)tile * TC_W_BYTES, TC_W_BYTES, &wk_full[sl]);
+          ++nwk;
+        }
+        for (int p = 0; p < 6; ++p) {
+          if (item + 1 < i_end)
+            for (int s = 4 * p; s < 4 * p + 4; ++s) blend_stage(item + 1, s);
+          const uint32_t sl = nat & 1;
+          mbar_wait(&at_empty[sl], ((nat >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&at_full[sl], T3_AT_SLOT);
+          bulk_g2s(smem + T3_OFF_AT + sl * T3_AT_SLOT, a.atimg + (size_t)group * TC_AT_GROUP + (size_t)p * T3_AT_SLOT, T3_AT_SLOT, &at_full[sl]);
+          ++nat;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc = umma_idesc_f16(TV, TC_NB);
+      constexpr uint32_t idesc_t = umma_idesc_f16(TV, T3_TN);
+      const uint32_t adesc0 = umma_desc_sw128_lo(smem0), bmdesc0 = umma_desc_sw128_lo(smem0 + T3_OFF_BM);
+      const uint32_t wdesc0 = umma_desc_sw128_lo(smem0 + T3_OFF_W), atdesc0 = umma_desc_sw128_lo(smem0 + T3_OFF_AT);
+      uint32_t na = 0, nbm = 0, nwk = 0, nat = 0, nt = 0;     // operands consumed so far / transform phases issued so far
+      // one stage of the blend GEMM of the item whose accumulators are v_posed buffer `buf`
+      auto blend_stage = [&](int s, uint32_t buf) {
+        const int kc = s / 6, c = (s % 6) >> 1, h = s & 1;
+        const uint32_t bsl = (nbm - (s % 6 == 0 ? 0 : 1)) & 1;      // the chunk's Bm slot: counted when its first stage is issued
+        if (s % 6 == 0) {
+          mbar_wait(&bm_full[nbm & 1], (nbm >> 1) & 1);
+          ++nbm;
+        }
+        const uint32_t b_hi = bmdesc0 + bsl * (T3_BM_SLOT >> 4), b_lo = b_hi + (TC_B_IMG >> 4);
+        const uint32_t sl = na % T3_NA;
+        mbar_wait(&a_full[sl], (na / T3_NA) & 1);
+        tc_fence_after();
+        const uint32_t ad = adesc0 + sl * (TC_A_IMG >> 4);
+        const uint32_t d = tmem_base + buf * (3 * TC_NB) + c * TC_NB;
+        const int nks = min(4, TC_KSTEPS - 4 * kc);
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint32_t ko = ks * 2;
+          if (h == 0) {
+            umma_f16_lohi(d, ad + ko, b_hi + ko, idesc, (kc | ks) != 0);
+            umma_f16_lohi(d, ad + ko, b_lo + ko, idesc, 1);
+          } else {
+            umma_f16_lohi(d, ad + ko, b_hi + ko, idesc, 1);
+          }
+        }
+        umma_commit(&a_empty[sl]);
+        ++na;
+        if (s % 6 == 5) umma_commit(&bm_empty[bsl]);
+      };
+      uint32_t nvp = 0;                                        // blend GEMMs started so far: buffer = nvp & 1
+      if (i_beg < i_end) {
+        // (buffer 0 is free at the start)
+        for (int s = 0; s < TC_STAGES_PER_TILE; ++s) blend_stage(s, 0);
+        umma_commit(&vp_full[0]);
+        nvp = 1;
+      }
+      for (int item = i_beg; item < i_end; ++item) {
+        const uint32_t wsl = nwk & 1;
+        mbar_wait(&wk_full[wsl], (nwk >> 1) & 1);
+        ++nwk;
+        const uint32_t w_hi = wdesc0 + wsl * (TC_W_BYTES >> 4), w_lo = w_hi + (TC_W_IMG >> 4);
+        const bool more = item + 1 < i_end;
+        const uint32_t nbuf = nvp & 1;
+        for (int p = 0; p < 6; ++p) {
+          if (more) {
+            if (p == 0 && nvp >= 2) {                          // the epilogue of two items ago has released this buffer
+              mbar_wait(&vp_empty[nbuf], ((nvp >> 1) - 1) & 1);
+              tc_fence_after();
+            }
+            for (int s = 4 * p; s < 4 * p + 4; ++s) blend_stage(s, nbuf);
+            if (p == 5) umma_commit(&vp_full[nbuf]);
+          }
+          if (nt > 0) {
+            mbar_wait(t_empty, (nt - 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t asl = nat & 1;
+          mbar_wait(&at_full[asl], (nat >> 1) & 1);
+          tc_fence_after();
+          const uint32_t t_hi = atdesc0 + asl * (T3_AT_SLOT >> 4), t_lo = t_hi + (T3_AT_SLOT >> 5);
+          const uint32_t dt = tmem_base + T3_COL_T;
+#pragma unroll
+          for (int ks = 0; ks < TC_TK / 16; ++ks) {
+            const uint32_t ko = ks * 2;
+            umma_f16_lohi(dt, w_hi + ko, t_hi + ko, idesc_t, ks != 0, UMMA_DESC_SW64_HI);
+            umma_f16_lohi(dt, w_hi + ko, t_lo + ko, idesc_t, 1, UMMA_DESC_SW64_HI);
+            umma_f16_lohi(dt, w_lo + ko, t_hi + ko, idesc_t, 1, UMMA_DESC_SW64_HI);
+          }
+          umma_commit(t_full);
+          umma_commit(&at_empty[asl]);
+          ++nat; ++nt;
+        }
+        umma_commit(&wk_empty[wsl]);
+        if (more) ++nvp;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ================= epilogue, warps 2..9: thread = vertex row (TMEM lane) x 16 bodies per phase =================
+  if (warp >= 2) {
+    const int quad = warp & 3, hh = (warp - 2) >> 2;    // a warp reads the TMEM lanes 32 (warp % 4) .. +31; hh = which 16 of a phase's 32 bodies
+    const int row = quad * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float* s_tr = reinterpret_cast<float*>(smem + T3_OFF_TR);
+    constexpr float tscale = 1.f / (TC_WSCALE * TC_BSCALE);
+    uint32_t nt = 0, it = 0;
+    for (int item = i_beg; item < i_end; ++item, ++it) {
+      const int group = item / NTILES, tile = item % NTILES;
+      const int v = tile * TV + row;
+      const bool vok = v < V;
+      // transl of the group's bodies (everybody is past the previous item's reads of it after the first barrier)
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+      for (int i = threadIdx.x - 64; i < TC_NB * 3; i += TC_EPI_THREADS) {
+        const int gb = group * TC_NB + i / 3;
+        s_tr[i] = (a.transl && gb < a.B) ? a.transl[(size_t)gb * 3 + i % 3] : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+      float ainv[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ainv[c] = a.ainv[(tile * 3 + c) * TV + row];
+      const float k0 = ainv[0] * tscale, k1 = ainv[1] * tscale, k2 = ainv[2] * tscale;
+      const uint32_t buf = it & 1;
+      mbar_wait(&vp_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int bl0 = half * 32 + hh * 16;                  // first of this thread's 16 bodies inside the group
+        uint32_t d[3][16];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tmem_ld_32x16(tlane + buf * (3 * TC_NB) + c * TC_NB + bl0, d[c]);
+        tmem_ld_wait();
+        if (a.save_vposed && vok) {
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            const int gb = group * TC_NB + bl0 + b;
+            if (gb < a.B) {
+              float* sv = a.save_vposed + ((size_t)gb * V + v) * 3;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) sv[c] = __uint_as_float(d[c][b]) * ainv[c];
+            }
+          }
+        }
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r, ++nt) {
+          mbar_wait(t_full, nt & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {                       // 8 bodies = 32 columns of T per load
+            uint32_t t[32];
+            tmem_ld_32x32(tlane + T3_COL_T + hh * 64 + q * 32, t);
+            tmem_ld_wait();
+            if (q == 1) {                                     // T is in registers: the issuer may overwrite it
+              tc_fence_before();
+              mbar_arrive(t_empty);
+            }
+#pragma unroll
+            for (int bb = 0; bb < 8; ++bb) {
+              const int b = q * 8 + bb, gb = group * TC_NB + bl0 + b;
+              if (gb < a.B && vok) {
+                float acc = fmaf(__uint_as_float(t[bb * 4 + 3]), tscale, s_tr[(bl0 + b) * 3 + r]);
+                acc = fmaf(__uint_as_float(t[bb * 4 + 0]) * k0, __uint_as_float(d[0][b]), acc);
+                acc = fmaf(__uint_as_float(t[bb * 4 + 1]) * k1, __uint_as_float(d[1][b]), acc);
+                acc = fmaf(__uint_as_float(t[bb * 4 + 2]) * k2, __uint_as_float(d[2][b]), acc);
+                a.verts[((size_t)gb * V + v) * 3 + r] = acc;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&vp_empty[buf]);                            // this buffer's accumulators have been read
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace straps
 
 using namespace straps;
@@ -523,18 +834,34 @@ int straps::smpl_tc_forward(straps_smpl* m, const float* global_orient, int64_t 
   ca.go = global_orient; ca.bp = body_pose; ca.betas = betas; ca.transl = transl;
   ca.go_stride = go_stride; ca.bp_stride = bp_stride; ca.betas_stride = betas_stride;
   ca.B = batch; ca.B_pad = b_pad; ca.pose2rot = pose2rot; ca.joints = joints; ca.bimg = bimg; ca.atimg = atimg; ca.save_A = save_A;
+  // STRAPS_LBS_V=2: the one-CTA-per-item kernel (lbs_tc_kernel); default: the persistent pipelined one (lbs_tc3_kernel)
+  const char* ver = getenv("STRAPS_LBS_V");
+  const bool v3 = !(ver && ver[0] == '2');
+  ca.at_layout = v3 ? 1 : 0;
   smpl_chain_kernel<<<b_pad / CH_TB, 128, 0, st>>>(m->d, ca);
   STRAPS_LAUNCH_CHECK();
   static PerDeviceOnce attr_once;
+  static int num_sms[64];
   const int dev = current_device();
   if (attr_once.need(dev)) {
     STRAPS_CUDA(cudaFuncSetAttribute(lbs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    STRAPS_CUDA(cudaFuncSetAttribute(lbs_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
+    int n = 148;
+    STRAPS_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev));
+    if (dev >= 0 && dev < 64) num_sms[dev] = n;
     attr_once.done(dev);
   }
   LbsTcArgs la;
   la.apk = m->tc_apk; la.ainv = m->tc_ainv; la.wk = m->tc_wk; la.bimg = bimg; la.atimg = atimg;
   la.transl = transl; la.B = batch; la.verts = vertices; la.save_vposed = save_vposed;
-  lbs_tc_kernel<<<dim3(NTILES, groups), TC_THREADS, TC_SMEM, st>>>(la);
+  if (v3) {
+    LbsTc3Args a3;
+    a3.k = la; a3.n_items = groups * NTILES;
+    const int sms = (dev >= 0 && dev < 64 && num_sms[dev] > 0) ? num_sms[dev] : 148;
+    lbs_tc3_kernel<<<std::min(a3.n_items, sms), TC_THREADS, T3_SMEM, st>>>(a3);
+  } else {
+    lbs_tc_kernel<<<dim3(NTILES, groups), TC_THREADS, TC_SMEM, st>>>(la);
+  }
   STRAPS_LAUNCH_CHECK();
   return 0;
 }

@@ -172,13 +172,17 @@ def _lbs_mode(mode):
     """STRAPS_LBS is read by the library on every SMPL forward: 'simt' = the CUDA-core kernel, 'tc' = the tensor-core kernels at every
     batch size, unset = tensor cores from the batch size where they win."""
     import os
+    os.environ.pop('STRAPS_LBS_V', None)
     if mode is None:
         os.environ.pop('STRAPS_LBS', None)
+    elif mode == 'tc2':                                     # the one-CTA-per-item tensor-core kernel (lbs_tc_kernel) instead of the persistent one
+        os.environ['STRAPS_LBS'] = 'tc'
+        os.environ['STRAPS_LBS_V'] = '2'
     else:
         os.environ['STRAPS_LBS'] = mode
 
 
-@pytest.mark.parametrize('B', [1, 7, 32, 40, 64, 127, 200])
+@pytest.mark.parametrize('B', [1, 7, 32, 40, 64, 127, 200, 700])
 def test_tensor_core_lbs_against_oracle_and_cuda_core_kernel(assets_root, smpl_oracle, B):
     """Batches >= 32 take smpl_tc.cu (blend shapes as a 3-pass fp16-split tcgen05 GEMM).  Held to 1e-5 against the oracle
     (smplx lbs()) -- ten times tighter than north_star -- and compared with the CUDA-core kernel on the same
@@ -192,7 +196,7 @@ def test_tensor_core_lbs_against_oracle_and_cuda_core_kernel(assets_root, smpl_o
     t = torch.from_numpy(transl)[:, None]
     try:
         outs = {}
-        for mode in ('tc', 'simt'):
+        for mode in ('tc', 'tc2', 'simt'):
             _lbs_mode(mode)
             with torch.no_grad():
                 o = smpl(body_pose=Rg[:, 1:], global_orient=Rg[:, :1], betas=bg, transl=tg, pose2rot=False)
@@ -210,6 +214,8 @@ def test_tensor_core_lbs_against_oracle_and_cuda_core_kernel(assets_root, smpl_o
     assert rel_err(tc[3].numpy(), ja.numpy()) < 1e-5
     for a, b in zip(tc, simt):
         assert rel_err(a.numpy(), b.numpy()) < 3e-6
+    for a, b in zip(tc, outs['tc2']):                       # same MMAs in the same order per output: the two tensor-core kernels agree exactly
+        assert torch.equal(a, b)
     assert rel_err(tc[1][:, :24].numpy(), simt[1][:, :24].numpy()) < 1e-6   # chain kernel = the CUDA-core kernel's prologue
 
 

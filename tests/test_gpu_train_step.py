@@ -66,12 +66,20 @@ def _flat(reg, crit):
     return torch.cat([p.detach().reshape(-1) for p in list(reg.parameters()) + list(crit.parameters())]).cpu()
 
 
-def _updates_agree(a, b, start, steps):
+def _updates_agree(a, b, start, steps, names=None):
     """The mean update error is a small fraction of steps * lr and all but a sliver of the elements land within 0.1 lr of each other.
     (No max-norm bar: Adam's first updates are lr * sign-like, m / sqrt(v) = +-1, so an element whose gradient is rounding noise -- the
     weight-gradient kernels add partial tiles with fp32 atomics -- legitimately moves by +lr in one run and -lr in the other:
     measured on B200 9e-5 relative = 2 lr on one element between two runs of the same code.)"""
     d = ((a - start) - (b - start)).abs()
+    if names is not None:                                      # per-tensor picture of where two runs part (shown when an assertion fires)
+        o = 0
+        for n, k in names:
+            dd = d[o:o + k]
+            f = float((dd > 0.1 * LR).float().mean())
+            if f > 1e-3:
+                print('  %-44s %8d elements  %.3f beyond 0.1 lr  mean %.2e  max %.2e' % (n, k, f, float(dd.mean()), float(dd.max())))
+            o += k
     assert float(d.mean()) < 0.02 * steps * LR
     assert float((d > 0.1 * LR).float().mean()) < 5e-3, float((d > 0.1 * LR).float().mean())
     assert float(d.max()) <= 2.0 * steps * LR * 1.001
@@ -140,7 +148,8 @@ def test_graphed_training_step_follows_the_eager_loop(assets_root):
     assert opt_a.step_count == 5 and opt_b.step_count == 5
     assert abs(losses[-1] - float(loss_b)) < 1e-4 * abs(float(loss_b))
     assert losses[0] > losses[-1]                              # it trains
-    _updates_agree(_flat(reg_a, crit_a), _flat(reg_b, crit_b), start, 5)
+    names = [(n, p.numel()) for n, p in list(reg_a.named_parameters()) + list(crit_a.named_parameters())]
+    _updates_agree(_flat(reg_a, crit_a), _flat(reg_b, crit_b), start, 5, names)
     n_bn = int(reg_a.state_dict()['image_encoder.bn1.num_batches_tracked'])
     assert n_bn == 5, n_bn
     # eval-mode inference after replays sees the replayed weights and running statistics

@@ -2,7 +2,7 @@
 # LBS-only call: parity tests, the sweep by mode, per-kernel durations (ncu launch list) at B = 64 and 4096.
 TAG=${1:-r02}
 mkdir -p gpurun_out
-timeout -s KILL 180 python -m pytest tests/test_gpu_smpl.py -m gpu -q -x > gpurun_out/pytest_smpl_$TAG.log 2>&1; echo "smpl rc=$?"; tail -4 gpurun_out/pytest_smpl_$TAG.log
+timeout -s KILL 300 python -m pytest tests/test_gpu_smpl.py -m gpu -q -x > gpurun_out/pytest_smpl_$TAG.log 2>&1; echo "smpl rc=$?"; tail -4 gpurun_out/pytest_smpl_$TAG.log
 timeout -s KILL 300 python tools/bench_lbs.py --batches 1 8 32 64 128 --modes tc simt --iters 20 > gpurun_out/lbs_modes_$TAG.jsonl 2> gpurun_out/lbs_modes_$TAG.err; echo "lbs rc=$?"
 timeout -s KILL 300 python tools/bench_lbs.py --batches 256 1024 4096 --modes tc --iters 20 >> gpurun_out/lbs_modes_$TAG.jsonl 2>> gpurun_out/lbs_modes_$TAG.err; echo "lbs rc=$?"
 timeout -s KILL 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/lbs_launches_$TAG.csv \
