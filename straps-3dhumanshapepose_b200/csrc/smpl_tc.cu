@@ -469,12 +469,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc_kernel(const LbsTcArgs a
 // of ring = one L2 round trip (~1.5 us under load) per 80 KB, 54 GB/s per SM -- and the stream stood still during the transform
 // phases, the epilogue, the copy-out and the next CTA's start-up.  Here:
 //   * a CTA walks a contiguous range of items; the producer runs ahead across item boundaries, so the stream never stops;
-//   * every operand is streamed (Bm per K chunk, the transform operand per phase): the A ring gets 128 KB instead of 80;
+//   * every operand is streamed (Bm per K chunk, the transform operand per phase): the A ring gets 112 KB instead of 80;
 //   * v_posed accumulators are double buffered in TMEM (2 x 192 columns + 128 for T = 512), and because tcgen05.mma executes in
 //     issue order the issuer INTERLEAVES: six chunks of the next item's blend GEMM alternate with the six transform phases
 //     (half of the group x output row) of the current item, so the epilogue of phase p runs under blend chunk p + 1.
 // Producer and issuer follow the same operand order, so a full ring can only wait on work that has already been issued.
-constexpr int T3_NA = 8;                                    // A ring slots of 16 KB
+constexpr int T3_NA = 7;                                    // A ring slots of 16 KB
 constexpr int T3_BM_SLOT = 2 * TC_B_IMG;                    // Bm of one K chunk, hi + lo: 16 KB
 constexpr int T3_AT_SLOT = TC_AT_BYTES / 2;                 // transform operand of one phase (32 bodies x 4 columns, hi + lo): 16 KB
 constexpr int T3_OFF_BM = T3_NA * TC_A_IMG;                 // 2 slots
@@ -482,7 +482,11 @@ constexpr int T3_OFF_W = T3_OFF_BM + 2 * T3_BM_SLOT;        // 2 slots
 constexpr int T3_OFF_AT = T3_OFF_W + 2 * TC_W_BYTES;        // 2 slots
 constexpr int T3_OFF_BAR = T3_OFF_AT + 2 * T3_AT_SLOT;
 constexpr int T3_OFF_TR = T3_OFF_BAR + 512;
-constexpr int T3_SMEM = T3_OFF_TR + TC_NB * 3 * 4 + 1024;
+constexpr int T3_OFF_ST = T3_OFF_TR + TC_NB * 3 * 4;         // per epilogue warp: two slabs of 32 vertices x 3 floats (output transposition)
+constexpr int T3_EPI_WARPS = 16;                            // 4 TMEM lane quadrants x 4 body octets of a phase
+constexpr int T3_EPI_THREADS = T3_EPI_WARPS * 32;
+constexpr int T3_THREADS = 64 + T3_EPI_THREADS;             // warp 0 producer, warp 1 MMA issuer, warps 2..17 epilogue
+constexpr int T3_SMEM = T3_OFF_ST + T3_EPI_WARPS * 2 * 384 + 1024;
 constexpr int T3_TN = 128;                                  // transform GEMM N per phase
 constexpr int T3_COL_T = 2 * 3 * TC_NB;                     // TMEM: [0,192) v_posed buffer 0, [192,384) buffer 1, [384,512) T
 static_assert(T3_SMEM <= 232448 && T3_COL_T + T3_TN <= 512, "lbs_tc3_kernel resources");
@@ -492,7 +496,7 @@ struct LbsTc3Args {
   int n_items;                  // groups * NTILES, item = group * NTILES + tile
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc3_kernel(const LbsTc3Args args) {
+__global__ void __launch_bounds__(T3_THREADS, 1) lbs_tc3_kernel(const LbsTc3Args args) {
   const LbsTcArgs& a = args.k;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -518,9 +522,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc3_kernel(const LbsTc3Args
     for (int i = 0; i < T3_NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bm_full[i], 1); mbar_init(&bm_empty[i], 1); mbar_init(&wk_full[i], 1); mbar_init(&wk_empty[i], 1);
-      mbar_init(&at_full[i], 1); mbar_init(&at_empty[i], 1); mbar_init(&vp_full[i], 1); mbar_init(&vp_empty[i], TC_EPI_THREADS);
+      mbar_init(&at_full[i], 1); mbar_init(&at_empty[i], 1); mbar_init(&vp_full[i], 1); mbar_init(&vp_empty[i], T3_EPI_THREADS);
     }
-    mbar_init(t_full, 1); mbar_init(t_empty, TC_EPI_THREADS);
+    mbar_init(t_full, 1); mbar_init(t_empty, T3_EPI_THREADS);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -657,12 +661,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc3_kernel(const LbsTc3Args
   }
   __syncwarp();
 
-  // ================= epilogue, warps 2..9: thread = vertex row (TMEM lane) x 16 bodies per phase =================
+  // ================= epilogue, warps 2..17: thread = vertex row (TMEM lane) x 8 bodies per phase =================
   if (warp >= 2) {
-    const int quad = warp & 3, hh = (warp - 2) >> 2;    // a warp reads the TMEM lanes 32 (warp % 4) .. +31; hh = which 16 of a phase's 32 bodies
+    const int quad = warp & 3, hh = (warp - 2) >> 2;    // a warp reads the TMEM lanes 32 (warp % 4) .. +31; hh = which 8 of a phase's 32 bodies
     const int row = quad * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
     float* s_tr = reinterpret_cast<float*>(smem + T3_OFF_TR);
+    float* slab = reinterpret_cast<float*>(smem + T3_OFF_ST) + (warp - 2) * 192;      // two slabs of 96 floats
     constexpr float tscale = 1.f / (TC_WSCALE * TC_BSCALE);
     uint32_t nt = 0, it = 0;
     for (int item = i_beg; item < i_end; ++item, ++it) {
@@ -670,29 +675,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc3_kernel(const LbsTc3Args
       const int v = tile * TV + row;
       const bool vok = v < V;
       // transl of the group's bodies (everybody is past the previous item's reads of it after the first barrier)
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
-      for (int i = threadIdx.x - 64; i < TC_NB * 3; i += TC_EPI_THREADS) {
+      asm volatile("bar.sync 1, %0;" ::"n"(T3_EPI_THREADS) : "memory");
+      for (int i = threadIdx.x - 64; i < TC_NB * 3; i += T3_EPI_THREADS) {
         const int gb = group * TC_NB + i / 3;
         s_tr[i] = (a.transl && gb < a.B) ? a.transl[(size_t)gb * 3 + i % 3] : 0.f;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(T3_EPI_THREADS) : "memory");
       float ainv[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) ainv[c] = a.ainv[(tile * 3 + c) * TV + row];
       const float k0 = ainv[0] * tscale, k1 = ainv[1] * tscale, k2 = ainv[2] * tscale;
+      const int nf2 = (max(0, min(32, V - (tile * TV + quad * 32))) * 3) / 2;       // float2 of this warp's valid vertices (48 or 15)
       const uint32_t buf = it & 1;
       mbar_wait(&vp_full[buf], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        const int bl0 = half * 32 + hh * 16;                  // first of this thread's 16 bodies inside the group
-        uint32_t d[3][16];
+        const int bl0 = half * 32 + hh * 8;                   // first of this thread's 8 bodies inside the group
+        uint32_t d[3][8];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tmem_ld_32x16(tlane + buf * (3 * TC_NB) + c * TC_NB + bl0, d[c]);
+        for (int c = 0; c < 3; ++c) tmem_ld_32x8(tlane + buf * (3 * TC_NB) + c * TC_NB + bl0, d[c]);
         tmem_ld_wait();
         if (a.save_vposed && vok) {
 #pragma unroll
-          for (int b = 0; b < 16; ++b) {
+          for (int b = 0; b < 8; ++b) {
             const int gb = group * TC_NB + bl0 + b;
             if (gb < a.B) {
               float* sv = a.save_vposed + ((size_t)gb * V + v) * 3;
@@ -701,28 +707,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lbs_tc3_kernel(const LbsTc3Args
             }
           }
         }
-#pragma unroll 1
+        // The three output rows of a body are kept until the last one: a vertex's 12 bytes leave together, and a warp's 32 vertices
+        // (384 contiguous bytes of the output) go through a per-warp slab so that the stores are full 8-byte-per-lane lines.  Storing
+        // each coordinate as it was produced (4 bytes every 12: 36 partially written sectors per body and warp instead of 12 full
+        // ones) made the epilogue the pacing stage -- every FFMA waited for the store queue to release its register
+        // (profiles/r02_lbs_tc_ncu.txt).
+        float o01[2][8];
+#pragma unroll
         for (int r = 0; r < 3; ++r, ++nt) {
           mbar_wait(t_full, nt & 1);
           tc_fence_after();
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {                       // 8 bodies = 32 columns of T per load
-            uint32_t t[32];
-            tmem_ld_32x32(tlane + T3_COL_T + hh * 64 + q * 32, t);
+          {
+            uint32_t t[32];                                   // 8 bodies x 4 columns of T
+            tmem_ld_32x32(tlane + T3_COL_T + hh * 32, t);
             tmem_ld_wait();
-            if (q == 1) {                                     // T is in registers: the issuer may overwrite it
-              tc_fence_before();
-              mbar_arrive(t_empty);
-            }
+            tc_fence_before();
+            mbar_arrive(t_empty);                             // T is in registers: the issuer may overwrite it
 #pragma unroll
             for (int bb = 0; bb < 8; ++bb) {
-              const int b = q * 8 + bb, gb = group * TC_NB + bl0 + b;
-              if (gb < a.B && vok) {
-                float acc = fmaf(__uint_as_float(t[bb * 4 + 3]), tscale, s_tr[(bl0 + b) * 3 + r]);
-                acc = fmaf(__uint_as_float(t[bb * 4 + 0]) * k0, __uint_as_float(d[0][b]), acc);
-                acc = fmaf(__uint_as_float(t[bb * 4 + 1]) * k1, __uint_as_float(d[1][b]), acc);
-                acc = fmaf(__uint_as_float(t[bb * 4 + 2]) * k2, __uint_as_float(d[2][b]), acc);
-                a.verts[((size_t)gb * V + v) * 3 + r] = acc;
+              const int b = bb, gb = group * TC_NB + bl0 + b;
+              float acc = fmaf(__uint_as_float(t[bb * 4 + 3]), tscale, s_tr[(bl0 + b) * 3 + r]);
+              acc = fmaf(__uint_as_float(t[bb * 4 + 0]) * k0, __uint_as_float(d[0][b]), acc);
+              acc = fmaf(__uint_as_float(t[bb * 4 + 1]) * k1, __uint_as_float(d[1][b]), acc);
+              acc = fmaf(__uint_as_float(t[bb * 4 + 2]) * k2, __uint_as_float(d[2][b]), acc);
+              if (r == 0) o01[0][b] = acc;
+              else if (r == 1) o01[1][b] = acc;
+              else if (gb < a.B) {                            // warp-uniform
+                float* sl = slab + (b & 1) * 96;
+                sl[lane * 3 + 0] = o01[0][b]; sl[lane * 3 + 1] = o01[1][b]; sl[lane * 3 + 2] = acc;      // 3 words apart: conflict free
+                __syncwarp();
+                float2* dst = reinterpret_cast<float2*>(a.verts + ((size_t)gb * V + (size_t)tile * TV + quad * 32) * 3);
+                const float2* src = reinterpret_cast<const float2*>(sl);
+                if (lane < nf2) dst[lane] = src[lane];
+                if (lane + 32 < nf2) dst[lane + 32] = src[lane + 32];
               }
             }
           }
@@ -858,7 +875,7 @@ int straps::smpl_tc_forward(straps_smpl* m, const float* global_orient, int64_t 
     LbsTc3Args a3;
     a3.k = la; a3.n_items = groups * NTILES;
     const int sms = (dev >= 0 && dev < 64 && num_sms[dev] > 0) ? num_sms[dev] : 148;
-    lbs_tc3_kernel<<<std::min(a3.n_items, sms), TC_THREADS, T3_SMEM, st>>>(a3);
+    lbs_tc3_kernel<<<std::min(a3.n_items, sms), T3_THREADS, T3_SMEM, st>>>(a3);
   } else {
     lbs_tc_kernel<<<dim3(NTILES, groups), TC_THREADS, TC_SMEM, st>>>(la);
   }
