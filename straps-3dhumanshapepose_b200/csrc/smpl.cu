@@ -334,63 +334,35 @@ __global__ void __launch_bounds__(TV) lbs_kernel(const SmplDev m, const LbsArgs 
   }
 }
 
-// one warp per (group of JB bodies, superset joint 24..89): the CSR entries of a regressor row are read once and the JB gathers of an
-// iteration are in flight together (one body per warp was a chain of three dependent L2 round trips: 64 us at B = 4096)
-constexpr int JB = 8;
+// one warp per (body, superset joint 24..89).  (Eight bodies per warp -- CSR entries read once, eight gathers in flight -- measured
+// SLOWER on B200, 71 vs 64 us at B = 4096: the kernel is bound by the scattered 12-byte gathers from a 338 MB tensor, not by latency.)
 __global__ void __launch_bounds__(256) joints_kernel(const SmplDev m, const float* __restrict__ verts,
                                                      float* __restrict__ joints, int B) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int NOUT = STRAPS_NUM_EXTRA_PICKS + STRAPS_NUM_EXTRA_ROWS;   // 66
-  const int ngroups = (B + JB - 1) / JB;
-  if (warp >= ngroups * NOUT) return;
-  const int b0 = (warp / NOUT) * JB, q = warp % NOUT;
-  const int nb = min(JB, B - b0);
-  const size_t vstride = (size_t)V * 3, jstride = (size_t)STRAPS_NUM_SUPERSET_JOINTS * 3;
-  const float* vb = verts + (size_t)b0 * vstride;
-  float* out = joints + (size_t)b0 * jstride + (size_t)(NJ + q) * 3;
+  if (warp >= B * NOUT) return;
+  const int b = warp / NOUT, q = warp % NOUT;
+  const float* vb = verts + (size_t)b * V * 3;
+  float* out = joints + ((size_t)b * STRAPS_NUM_SUPERSET_JOINTS + NJ + q) * 3;
   if (q < STRAPS_NUM_EXTRA_PICKS) {
-    if (lane < 3) {
-      const size_t src = (size_t)m.pick_idx[q] * 3 + lane;
-      float v[JB];
-#pragma unroll
-      for (int b = 0; b < JB; ++b) v[b] = (b < nb) ? vb[b * vstride + src] : 0.f;   // plain copies: bit exact
-#pragma unroll
-      for (int b = 0; b < JB; ++b)
-        if (b < nb) out[b * jstride + lane] = v[b];
-    }
+    if (lane < 3) out[lane] = vb[(size_t)m.pick_idx[q] * 3 + lane];   // plain copy: bit exact
     return;
   }
   const int r = q - STRAPS_NUM_EXTRA_PICKS;
-  float sx[JB], sy[JB], sz[JB];
-#pragma unroll
-  for (int b = 0; b < JB; ++b) sx[b] = sy[b] = sz[b] = 0.f;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
   for (int i = m.csr_ptr[r] + lane; i < m.csr_ptr[r + 1]; i += 32) {
     const float w = m.csr_val[i];
     const float* p = vb + (size_t)m.csr_idx[i] * 3;
-    float px[JB], py[JB], pz[JB];
-#pragma unroll
-    for (int b = 0; b < JB; ++b) {
-      const float* pb = p + (b < nb ? b : 0) * vstride;
-      px[b] = pb[0]; py[b] = pb[1]; pz[b] = pb[2];
-    }
-#pragma unroll
-    for (int b = 0; b < JB; ++b) { sx[b] = fmaf(w, px[b], sx[b]); sy[b] = fmaf(w, py[b], sy[b]); sz[b] = fmaf(w, pz[b], sz[b]); }
+    sx = fmaf(w, p[0], sx); sy = fmaf(w, p[1], sy); sz = fmaf(w, p[2], sz);
   }
 #pragma unroll
-  for (int b = 0; b < JB; ++b) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sx[b] += __shfl_xor_sync(0xffffffffu, sx[b], o);
-      sy[b] += __shfl_xor_sync(0xffffffffu, sy[b], o);
-      sz[b] += __shfl_xor_sync(0xffffffffu, sz[b], o);
-    }
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    sz += __shfl_xor_sync(0xffffffffu, sz, o);
   }
-  if (lane == 0) {
-#pragma unroll
-    for (int b = 0; b < JB; ++b)
-      if (b < nb) { out[b * jstride + 0] = sx[b]; out[b * jstride + 1] = sy[b]; out[b * jstride + 2] = sz[b]; }
-  }
+  if (lane == 0) { out[0] = sx; out[1] = sy; out[2] = sz; }
 }
 
 __global__ void rot6d_kernel(const float* __restrict__ x, long long n, float* __restrict__ R) {
@@ -592,7 +564,7 @@ static int smpl_forward_impl(const straps_smpl_t* m, const float* global_orient,
       if (smpl_tc_forward(const_cast<straps_smpl*>(m), global_orient, go_stride, body_pose, bp_stride, betas, betas_stride, transl, batch,
                           pose2rot, vertices, joints, save_vposed, save_A, st))
         return 1;
-      const int warps = ceil_div(batch, JB) * (STRAPS_NUM_EXTRA_PICKS + STRAPS_NUM_EXTRA_ROWS);
+      const int warps = batch * (STRAPS_NUM_EXTRA_PICKS + STRAPS_NUM_EXTRA_ROWS);
       joints_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(m->d, vertices, joints, batch);
       STRAPS_LAUNCH_CHECK();
       return 0;
@@ -605,7 +577,7 @@ static int smpl_forward_impl(const straps_smpl_t* m, const float* global_orient,
   else if (batch >= 4) rc = launch_lbs<2>(m, a, st);
   else rc = launch_lbs<1>(m, a, st);
   if (rc) return rc;
-  const int warps = ceil_div(batch, JB) * (STRAPS_NUM_EXTRA_PICKS + STRAPS_NUM_EXTRA_ROWS);
+  const int warps = batch * (STRAPS_NUM_EXTRA_PICKS + STRAPS_NUM_EXTRA_ROWS);
   joints_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(m->d, vertices, joints, batch);
   STRAPS_LAUNCH_CHECK();
   return 0;

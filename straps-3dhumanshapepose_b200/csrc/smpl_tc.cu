@@ -117,9 +117,12 @@ struct ChainArgs {
   float* save_A;                // training: the transforms as fp32 [B][24][12] in the caller's tensor, or null
 };
 
-constexpr int CH_TB = 8;        // bodies per CTA of the chain kernel
+// 4 bodies per CTA of 256 threads: the kernel is a chain of short dependent phases (one CTA of 128 threads x 8 bodies took 18 us at any
+// batch size, instruction-latency bound), so the work per thread is what counts
+constexpr int CH_TB = 4;
+constexpr int CH_THREADS = 256;
 
-__global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const ChainArgs a) {
+__global__ void __launch_bounds__(CH_THREADS) smpl_chain_kernel(const SmplDev m, const ChainArgs a) {
   __shared__ float sR[CH_TB][NJ][9];
   __shared__ float sJ[CH_TB][NJ][3];
   __shared__ float sG[CH_TB][NJ][12];
@@ -127,12 +130,12 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
   const int tid = threadIdx.x;
   const int b0 = blockIdx.x * CH_TB;
   const int nb = max(0, min(CH_TB, a.B - b0));
-  for (int i = tid; i < CH_TB * STRAPS_NUM_BETAS; i += 128) {
+  for (int i = tid; i < CH_TB * STRAPS_NUM_BETAS; i += CH_THREADS) {
     int b = i / STRAPS_NUM_BETAS, l = i % STRAPS_NUM_BETAS;
     sbeta[b][l] = (b < nb) ? a.betas[(size_t)(b0 + b) * a.betas_stride + l] : 0.f;
   }
   if (a.pose2rot) {
-    for (int i = tid; i < CH_TB * NJ; i += 128) {
+    for (int i = tid; i < CH_TB * NJ; i += CH_THREADS) {
       int b = i / NJ, j = i % NJ;
       float r[3] = {0.f, 0.f, 0.f};
       if (b < nb) {
@@ -144,11 +147,11 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
   } else {
     // fully unrolled so that all of a thread's loads are in flight together: as a rolled loop every iteration waited for its own
     // L2 / HBM round trip (14 of them in a row -- most of this kernel's 20 us at any batch size)
-    constexpr int NIT = (CH_TB * NJ * 9 + 127) / 128;
+    constexpr int NIT = (CH_TB * NJ * 9 + CH_THREADS - 1) / CH_THREADS;
     float val[NIT];
 #pragma unroll
     for (int u = 0; u < NIT; ++u) {
-      const int i = tid + u * 128;
+      const int i = tid + u * CH_THREADS;
       const int b = i / (NJ * 9), r = i % (NJ * 9), j = r / 9, e = r % 9;
       float v = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
       if (i < CH_TB * NJ * 9 && b < nb)
@@ -157,23 +160,23 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
     }
 #pragma unroll
     for (int u = 0; u < NIT; ++u) {
-      const int i = tid + u * 128;
+      const int i = tid + u * CH_THREADS;
       if (i < CH_TB * NJ * 9) (&sR[0][0][0])[i] = val[u];
     }
   }
   // rest-joint regressors of this thread's outputs, fetched before the barrier for the same reason
-  constexpr int NJT = (CH_TB * NJ * 3 + 127) / 128;
+  constexpr int NJT = (CH_TB * NJ * 3 + CH_THREADS - 1) / CH_THREADS;
   float jsv[NJT][STRAPS_NUM_BETAS], jtv[NJT];
 #pragma unroll
   for (int u = 0; u < NJT; ++u) {
-    const int i = tid + u * 128, jc = (i % (NJ * 3));
+    const int i = tid + u * CH_THREADS, jc = (i % (NJ * 3));
 #pragma unroll
     for (int l = 0; l < STRAPS_NUM_BETAS; ++l) jsv[u][l] = m.js[jc * STRAPS_NUM_BETAS + l];
     jtv[u] = m.jt[jc];
   }
   __syncthreads();
   // Bm = [R_j - I (j = 1..23) | betas | 1 | 0...] * 2^10, fp16 hi / lo, in the SWIZZLE_128B image of its body group
-  for (int i = tid; i < CH_TB * TC_K; i += 128) {
+  for (int i = tid; i < CH_TB * TC_K; i += CH_THREADS) {
     const int b = i / TC_K, k = i % TC_K;
     const int gb = b0 + b;
     if (gb >= a.B_pad) continue;
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
   }
 #pragma unroll
   for (int u = 0; u < NJT; ++u) {
-    const int i = tid + u * 128;
+    const int i = tid + u * CH_THREADS;
     if (i < CH_TB * NJ * 3) {
       const int b = i / (NJ * 3), jc = i % (NJ * 3);
       float acc = 0.f;
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
   __syncthreads();
   for (int lvl = 0; lvl < m.nlevels; ++lvl) {
     const int j0 = m.lvl_start[lvl], nj = m.lvl_start[lvl + 1] - j0;
-    for (int i = tid; i < CH_TB * nj * 3; i += 128) {
+    for (int i = tid; i < CH_TB * nj * 3; i += CH_THREADS) {
       int b = i / (nj * 3), q = i % (nj * 3), j = m.lvl_joint[j0 + q / 3], r = q % 3;
       int p = m.parents[j];
       const float* Rj = &sR[b][j][0];
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(128) smpl_chain_kernel(const SmplDev m, const 
   // skinning transforms A = [G_rot | G_t - G_rot J_rest]: fp32 for the training path, and as the B operand of the transform GEMM --
   // image (group, r, hi | lo) = 256 rows n = (body in group) * 4 + column, 64 bytes each (32 joint slots), SWIZZLE_64B: the 16-byte
   // unit u of row n sits at physical unit u ^ ((n >> 1) & 3).  Joint slots 24..31 stay zero from the memset at allocation.
-  for (int i = tid; i < CH_TB * NJ * 3; i += 128) {
+  for (int i = tid; i < CH_TB * NJ * 3; i += CH_THREADS) {
     int b = i / (NJ * 3), q = i % (NJ * 3), j = q / 3, r = q % 3;
     const int gb = b0 + b;
     if (gb >= a.B_pad) continue;
@@ -855,7 +858,7 @@ int straps::smpl_tc_forward(straps_smpl* m, const float* global_orient, int64_t 
   const char* ver = getenv("STRAPS_LBS_V");
   const bool v3 = !(ver && ver[0] == '2');
   ca.at_layout = v3 ? 1 : 0;
-  smpl_chain_kernel<<<b_pad / CH_TB, 128, 0, st>>>(m->d, ca);
+  smpl_chain_kernel<<<b_pad / CH_TB, CH_THREADS, 0, st>>>(m->d, ca);
   STRAPS_LAUNCH_CHECK();
   static PerDeviceOnce attr_once;
   static int num_sms[64];
