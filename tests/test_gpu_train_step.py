@@ -157,8 +157,14 @@ def test_graphed_training_step_follows_the_eager_loop(assets_root):
     _updates_agree(_flat(reg_a, crit_a), _flat(reg_b, crit_b), start, 5, names)
     n_bn = int(reg_a.state_dict()['image_encoder.bn1.num_batches_tracked'])
     assert n_bn == 5, n_bn
-    # eval-mode inference after replays sees the replayed weights and running statistics
+    # eval-mode inference after replays sees the replayed weights and running statistics: against the oracle on the replayed module's
+    # OWN state_dict (the eager twin is 3e-4 away by now -- two runs part through ReLU decisions, see _updates_agree -- while a stale
+    # packed copy of the weights would be percents away)
     reg_a.eval(); reg_b.eval()
     with torch.no_grad():
         pa, pb = reg_a(x)[1], reg_b(x)[1]
-    assert rel_err(pa.cpu().numpy(), pb.cpu().numpy()) < 1e-4
+        sd_a = {k: v.detach().cpu() for k, v in reg_a.state_dict().items()}
+        feat_o = O.encoder_forward(x.cpu(), sd_a, train=False)
+        po = O.split_params(O.ief_forward(feat_o, sd_a, reg_a.ief_module.initial_params_estimate.detach().cpu().reshape(-1)))[1]
+    assert rel_err(pa.cpu().numpy(), po.numpy()) < 1e-4
+    assert rel_err(pa.cpu().numpy(), pb.cpu().numpy()) < 3e-3
