@@ -1354,7 +1354,7 @@ int tc_read_activation(straps_regressor* r, int buf, int batch, float* out, cuda
 // SWIZZLE_128B MN-major atom layout (no transposes anywhere).  A = X patches (M = 128 = two 64-wide (tap, ci-chunk) columns of
 // the weight matrix, the same 4-D boxes the forward uses, 64 pixels deep), B = dY (N = BN output channels), D = dW^T tile.
 // 3-pass fp16 split as in the forward:  X_hi.[dY_hi | dY_lo]  (one MMA of width 2 BN)  +  X_lo.dY_hi , separate accumulators.
-// dY is pre-scaled by a power of two (split_scaled_kernel); the inverse is applied by unpack_dw_tc_kernel.
+// dY is pre-scaled by a power of two (split_scaled_kernel); the inverse is applied by unpack_dw_all_kernel.
 // Split-K: an item = (M-tile, N-tile, range of <= 128 K-tiles of 64 pixels); partial tiles are added to dW[cout][k_eff] with
 // coalesced fp32 reductions (a warp = 32 consecutive ci of one co).  Short K ranges also bound the truncation bias of the
 // tensor-core accumulator (-1e-8 relative per MMA).
@@ -1533,23 +1533,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
 }
 
 // dW[cout][k_eff] (x dY scale) -> OIHW fp32
-__global__ void unpack_dw_tc_kernel(const float* __restrict__ dw, const unsigned* __restrict__ maxbits, int cout, int cin, int ks, int conv1,
-                                    int k_eff, float* __restrict__ out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)cout * cin * ks * ks) return;
-  int e = 0;
-  const float mx = __uint_as_float(*maxbits);
-  if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); e = max(-100, min(100, 14 - e)); }
-  const int kw = (int)(i % ks);
-  size_t t = i / ks;
-  const int kh = (int)(t % ks); t /= ks;
-  const int c = (int)(t % cin);
-  const int n = (int)(t / cin);
-  const int k = conv1 ? kh * C1_KROW + kw * XP_C + c : (kh * ks + kw) * cin + c;
-  out[i] = dw[(size_t)n * k_eff + k] * ldexpf(1.f, -e);
-}
-
-// the same for every convolution of a backward pass in one launch (20 launches of 3-10 us before)
+// [cout][k_eff] fp32 accumulators (scaled by the power of two of max |dY|) -> OIHW, every convolution of a backward pass in one launch
 struct DwUnpackTable {
   const float* src[NCONV];
   float* dst[NCONV];            // null: skipped
@@ -1620,41 +1604,6 @@ static void tc_train_free(TcState* t) {
   t->train = nullptr;
 }
 
-// per INPUT channel of the forward conv: power-of-two scale for the rows of the data-gradient weight matrix
-__global__ void w_colscale_kernel(const float* __restrict__ w, int cout, int cin, int kk, float* __restrict__ pscale,
-                                  float* __restrict__ unscale) {
-  __shared__ float red[256];
-  const int ci = blockIdx.x;
-  float m = 0.f;
-  for (int i = threadIdx.x; i < cout * kk; i += blockDim.x) m = fmaxf(m, fabsf(w[((size_t)(i / kk) * cin + ci) * kk + (i % kk)]));
-  red[threadIdx.x] = m;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const float mx = red[0];
-    int e = 0;
-    if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); e = max(-60, min(60, 14 - e)); }
-    pscale[ci] = ldexpf(1.f, e);
-    unscale[ci] = ldexpf(1.f, -e);
-  }
-}
-// OIHW fp32 -> [Cin][(kh',kw',co)] fp16 hi/lo with the taps flipped
-__global__ void pack_w_dgrad_tc_kernel(const float* __restrict__ w, const float* __restrict__ pscale, int cout, int cin, int ks,
-                                       __half* __restrict__ hi, __half* __restrict__ lo) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int k_eff = ks * ks * cout;
-  if (i >= (size_t)cin * k_eff) return;
-  const int ci = (int)(i / k_eff), k = (int)(i % k_eff);
-  const int tap = k / cout, co = k % cout, kh = ks - 1 - tap / ks, kw = ks - 1 - tap % ks;
-  const float v = w[(((size_t)co * cin + ci) * ks + kh) * ks + kw] * pscale[ci];
-  __half h, l;
-  split_f16(v, h, l);
-  hi[i] = h;
-  lo[i] = l;
-}
 // fp32 NHWC -> split planes, scaled by the power of two derived from *maxbits (null: no scaling); up = 1 writes pixel (h, w) to
 // (2h, 2w) of a [B, 2H, 2W, C] tensor (zeroed beforehand).  Block 0 also publishes the epilogue scales of the data gradient.
 __global__ void split_scaled_kernel(const float* __restrict__ src, const unsigned* __restrict__ maxbits, long long n4, int C, int H, int W,
@@ -1699,10 +1648,8 @@ struct WPrepLayer {
 };
 struct WPrepTable {
   WPrepLayer L[NCONV];
-  int row_start[NCONV + 1];     // scale kernel: blocks [row_start[i], row_start[i+1]) = output channels of conv i ...
+  int row_start[NCONV + 1];     // blocks [row_start[i], row_start[i+1]) = output channels of conv i (forward operand rows) ...
   int col_start[NCONV + 1];     // ... followed by rows_total + [col_start[i], col_start[i+1]) = input channels of conv i (i >= 1)
-  int fblk_start[NCONV + 1];    // pack kernel: blocks of 256 forward elements, then blocks of 256 data-gradient elements
-  int dblk_start[NCONV + 1];
   float* wf_scale; float* wf_unscale; float* wd_scale; float* wd_unscale;
 };
 
@@ -1860,7 +1807,7 @@ int tc_train_begin(straps_regressor* r, int B, cudaStream_t st) {
   // convolutions in one launch
   {
     WPrepTable wt;
-    int rows = 0, cols = 0, fb = 0, db = 0;
+    int rows = 0, cols = 0;
     for (int i = 0; i < NCONV; ++i) {
       const ConvSpec& c = r->conv[i];
       WPrepLayer& L = wt.L[i];
@@ -1869,12 +1816,9 @@ int tc_train_begin(straps_regressor* r, int B, cudaStream_t st) {
       L.ch_off = (int)t->ch_off[i]; L.wd_off = (i == 0) ? 0 : (int)tt->wd_off[i];
       wt.row_start[i] = rows; rows += c.cout;
       wt.col_start[i] = cols; cols += (i == 0) ? 0 : c.cin;
-      wt.fblk_start[i] = fb; fb += (int)(((size_t)c.cout * c.k_eff + 255) / 256);
-      wt.dblk_start[i] = db; db += (i == 0) ? 0 : (int)(((size_t)c.cin * c.ksize * c.ksize * c.cout + 255) / 256);
     }
-    wt.row_start[NCONV] = rows; wt.col_start[NCONV] = cols; wt.fblk_start[NCONV] = fb; wt.dblk_start[NCONV] = db;
+    wt.row_start[NCONV] = rows; wt.col_start[NCONV] = cols;
     wt.wf_scale = tt->wf_scale; wt.wf_unscale = tt->wf_unscale; wt.wd_scale = tt->wd_scale; wt.wd_unscale = tt->wd_unscale;
-    (void)fb; (void)db;
     pack_w_all_kernel<<<rows + cols, 256, 0, st>>>(wt);
     STRAPS_LAUNCH_CHECK();
   }
