@@ -285,6 +285,9 @@ def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_ov
     crit = Loss(tasks, init_loss_weights=weights).to(dev)
     smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(dev)
     opt = DataParallelAdam(list(reg.parameters()) + list(crit.parameters()), lr=1e-4)
+    overlap = opt.enable_overlap(reg) and os.environ.get('STRAPS_DP_OVERLAP', '1') != '0'
+    if not overlap:
+        opt.disable_overlap()
     rng = np.random.RandomState(500 + rank)
     with torch.no_grad():                                   # target side (train/...:121-145), once: seeded random pose / shape
         t_betas = torch.from_numpy(rng.normal(0, 1, (B, 10)).astype(np.float32)).to(dev)
@@ -347,7 +350,7 @@ def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_ov
     out = {'config': 'BASELINE configs[%d]: training step (encoder+IEF+rot6d+SMPL+projection+multi-task loss, no renderer), B=%d per GPU, '
                      '%d GPU(s), conv mode %s, %s, fused Adam'
                      % (3 if world > 1 else 2, B, world, conv_mode,
-                        'one NCCL all-reduce of %d fp32 gradients per step' % opt.bucket.numel if world > 1 else 'no collective (1 GPU)'),
+                        ('NCCL all-reduce of %d fp32 gradients per step%s' % (opt.bucket.numel, ', layer4 + IEF part (%d) started inside the backward pass on a side stream' % (opt._early_range[1] - opt._early_range[0]) if opt._early_range else '')) if world > 1 else 'no collective (1 GPU)'),
            'ms_per_step': ms, 'value': world * B / (ms * 1e-3), 'unit': 'bodies/s', 'steps': steps, 'global_batch': world * B,
            'mode': 'CUDA-graph replay of the whole step (GraphedTrainStep)' if ms_graph is not None else 'eager PyTorch loop',
            'ms_per_step_eager': ms_eager, 'ms_per_step_graphed': ms_graph, 'graph_note': graph_note,
@@ -428,12 +431,37 @@ def run_gpu(args):
         e1.record()
         barrier()
         launches = _lib.launch_count() - n0
-        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        ms_total_eager = max_over_ranks(e0.elapsed_time(e1))
+        # ---- the same step as a CUDA-graph replay (straps_b200.graphs.GraphedCallable, the repo's public capture API): the ~28 launches
+        # of a step leave ~2 % of host-induced gaps in the eager loop.  The replay reads the graph's own input buffer (inputs resident).
+        ms_total, enc_graph, value_mode = ms_total_eager, None, 'eager PyTorch loop'
+        if not args.no_graph:
+            try:
+                from straps_b200.graphs import GraphedCallable
+                g_hot = GraphedCallable(hot_path, x_dev)
+                xs = g_hot.static_inputs[0]
+                for _ in range(3):
+                    g_hot(xs)
+                barrier()
+                e0.record()
+                for i in range(args.steps):
+                    g_hot(xs)
+                e1.record()
+                barrier()
+                ms_total = max_over_ranks(e0.elapsed_time(e1))
+                value_mode = 'CUDA-graph replay of the step (GraphedCallable)'
+                enc_graph = GraphedCallable(lambda t: reg.image_encoder(t), x_dev)
+            except Exception as e:                                  # noqa: BLE001 -- the eager figure stands on its own
+                value_mode = 'eager PyTorch loop (graph capture failed: %s)' % (str(e)[:120],)
+                ms_total, enc_graph = ms_total_eager, None
         clocks = sampler.stop() if rank == 0 else None
         # ---- roofline of the convolution stack: time the encoder alone, same stream, CUDA events ----
+        enc_fn, enc_in = (enc_graph, enc_graph.static_inputs[0]) if enc_graph is not None else (reg.image_encoder, x_dev)
+        for i in range(3):
+            enc_fn(enc_in)
         for i in range(args.steps):
             ev[i][0].record()
-            reg.image_encoder(x_dev)
+            enc_fn(enc_in)
             ev[i][1].record()
         barrier()
         enc_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
@@ -560,6 +588,7 @@ def run_gpu(args):
             'warmup': max(3, args.warmup), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'fp16x3 split (fp32-equivalent) convs, fp32 elsewhere' if args.conv_mode == 'f16x3_tc' else 'f32',
             'data': 'synthetic', 'config': cfg, 'conv_mode': args.conv_mode,
+            'value_mode': value_mode, 'ms_per_step_eager': ms_total_eager / args.steps,
             'e2e': {'value': e2e, 'unit': 'bodies/s', 'h2d_bytes_per_step': int(x_host.numel() * 4),
                     'd2h_bytes_per_step': int(sum(h.numel() for h in out_host) * 4),
                     'h2d_copy_alone_gbs_per_rank': {'min': h2d_min, 'max': h2d_max,
@@ -570,7 +599,7 @@ def run_gpu(args):
                 'h2d_bytes_per_step': int(B * 256 * 256 * 4 + B * (C - 1) * 2 * 4), 'd2h_bytes_per_step': int(sum(h.numel() for h in out_host) * 4),
                 'note': 'SingleInputRegressor.forward_from_labels: host segmentation labels + 2-D joints; the proxy representation is generated '
                         'inside the stem input pack (SURVEY 8f N1), double-buffered like e2e'},
-            'gpu_launches': int(launches),
+            'gpu_launches': int(launches),      # library kernels of the timed steps (counted in the eager loop; a replay launches the same ones)
             'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': achieved_tf / peak_tf,
                          'traffic': traffic['dram_bytes_per_launch'] if traffic else None, 'peak_kind': peak_kind,
@@ -598,6 +627,7 @@ def main():
     ap.add_argument('--cpu-reps', type=int, default=3)
     ap.add_argument('--train-steps', type=int, default=10, help='timed steps of the training-step arm (0 = skip)')
     ap.add_argument('--no-lbs-sweep', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='time the eager loop only (ncu launch lists: replays hide the kernels)')
     ap.add_argument('--no-train-graph', action='store_true', help='time the eager training loop only (ncu launch lists: replays hide the kernels)')
     ap.add_argument('--no-numa-bind', action='store_true', help='leave the process unbound (A/B of the NUMA binding)')
     args = ap.parse_args()

@@ -212,6 +212,12 @@ int straps_encoder_train_forward(straps_regressor_t* r, const float* x, int batc
  * ReLU / max-pool flip noise); the tensor-core backward needs a tensor-core forward.  May be called repeatedly. */
 int straps_encoder_backward(straps_regressor_t* r, const float* dfeat, int batch, int conv_mode,
                             float* const* d_conv_w, float* const* d_bn, void* stream);
+/* The same pass in pieces: BasicBlocks block_hi .. block_lo (7 = layer4.1 ... 0 = layer1.0, processed last-first), `first` != 0 on the
+ * call that starts the pass, `stem` != 0 on the call that ends it (max-pool / bn1 / conv1).  Only the gradients of the blocks covered
+ * are written.  (straps_b200/parallel.py starts the all-reduce of layer4 + IEF between blocks 7..6 and 5..0.) */
+int straps_encoder_backward_range(straps_regressor_t* r, const float* dfeat, int batch, int conv_mode,
+                                  float* const* d_conv_w, float* const* d_bn, int block_hi, int block_lo, int first, int stem,
+                                  void* stream);
 /* IEF forward that also saves, per iteration, { p_k [B,157] | h1_k [B,512] | h2_k [B,512] } into
  * saved dev [iters * B * 1181] for straps_ief_backward. */
 int straps_ief_forward_train(straps_regressor_t* r, const float* feat, int batch, int iters, float* params,

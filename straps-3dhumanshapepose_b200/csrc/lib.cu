@@ -15,5 +15,5 @@ void set_error(const char* fmt, ...) {
 }  // namespace straps
 
 extern "C" const char* straps_last_error(void) { return straps::g_err; }
-extern "C" int straps_abi_version(void) { return 4; }
+extern "C" int straps_abi_version(void) { return 5; }
 extern "C" unsigned long long straps_launch_count(void) { return straps::g_launches.load(); }

@@ -755,9 +755,13 @@ extern "C" int straps_encoder_train_forward(straps_regressor_t* r, const float* 
 }
 
 // d_conv_w[20]: OIHW gradients (state_dict order); d_bn[40]: (dgamma, dbeta) per BatchNorm.  All PyTorch-owned, overwritten.
-extern "C" int straps_encoder_backward(straps_regressor_t* r, const float* dfeat, int batch, int conv_mode, float* const* d_conv_w,
-                                       float* const* d_bn, void* stream) {
+// The backward pass in two halves if the caller wishes (block_hi .. block_lo of the 8 BasicBlocks, last first; `first` = this call
+// starts the pass, `stem` = it also ends it with the stem): a data-parallel caller starts the all-reduce of the layer4 + IEF gradients
+// -- 76 % of the bucket, complete after the first two blocks -- while the rest of the pass runs.
+extern "C" int straps_encoder_backward_range(straps_regressor_t* r, const float* dfeat, int batch, int conv_mode, float* const* d_conv_w,
+                                             float* const* d_bn, int block_hi, int block_lo, int first, int stem, void* stream) {
   STRAPS_CHECK(r && dfeat && d_conv_w && d_bn, "straps_encoder_backward: null argument");
+  STRAPS_CHECK(block_hi <= 7 && block_lo >= 0 && block_lo <= block_hi + 1, "straps_encoder_backward_range: blocks %d..%d", block_hi, block_lo);
   TrainState* t = static_cast<TrainState*>(r->train);
   STRAPS_CHECK(t && t->last_batch == batch, "straps_encoder_backward: no matching straps_encoder_train_forward (batch %d)", batch);
   STRAPS_CHECK(conv_mode == -1 || conv_mode == t->mode || (conv_mode == STRAPS_CONV_FP32_SIMT && t->mode == STRAPS_CONV_F16X3_TC),
@@ -771,14 +775,14 @@ extern "C" int straps_encoder_backward(straps_regressor_t* r, const float* dfeat
     t->xin_valid = 1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (t->mode == STRAPS_CONV_F16X3_TC && straps::tc_train_pack_dgrad(r, st)) return 1;
-  for (int i = 1; i < NCONV && t->mode != STRAPS_CONV_F16X3_TC; ++i) {   // data-gradient weight layout (conv1 needs none)
+  if (first && t->mode == STRAPS_CONV_F16X3_TC && straps::tc_train_pack_dgrad(r, st)) return 1;
+  for (int i = 1; first && i < NCONV && t->mode != STRAPS_CONV_F16X3_TC; ++i) {   // data-gradient weight layout (conv1 needs none)
     const ConvSpec& c = r->conv[i];
     const int total = c.ksize * c.ksize * c.cout * c.cin;
     pack_w_dgrad_kernel<<<ceil_div(total, 256), 256, 0, st>>>(c.w_oihw, c.cout, c.cin, c.ksize, t->w_dgrad[i]);
     STRAPS_LAUNCH_CHECK();
   }
-  {
+  if (first) {
     const long long n = (long long)batch * 64 * 512;
     avgpool_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dfeat, batch, 64, 512, t->gbuf[r->buf_final]);
     STRAPS_LAUNCH_CHECK();
@@ -786,7 +790,7 @@ extern "C" int straps_encoder_backward(straps_regressor_t* r, const float* dfeat
   // blocks in reverse
   int starts[8], nblk = 0;
   for (int i = 1; i < NCONV;) { starts[nblk++] = i; i += ((i + 2 < NCONV) && r->conv[i + 2].ksize == 1) ? 3 : 2; }
-  for (int bi = nblk - 1; bi >= 0; --bi) {
+  for (int bi = std::min(nblk - 1, block_hi); bi >= block_lo; --bi) {
     const int i = starts[bi];
     const bool ds = (i + 2 < NCONV) && r->conv[i + 2].ksize == 1;
     const ConvSpec &c1 = r->conv[i], &c2 = r->conv[i + 1];
@@ -809,7 +813,7 @@ extern "C" int straps_encoder_backward(straps_regressor_t* r, const float* dfeat
     }
   }
   // stem: maxpool backward -> bn1 (relu mask from the stem activation) -> conv1 weight gradient
-  {
+  if (stem) {
     const size_t nstem = (size_t)batch * 128 * 128 * 64;
     STRAPS_CUDA(cudaMemsetAsync(t->gbuf[r->buf_stem], 0, nstem * sizeof(float), st));
     const long long n = (long long)batch * 64 * 64 * 64;
@@ -819,8 +823,13 @@ extern "C" int straps_encoder_backward(straps_regressor_t* r, const float* dfeat
     if (bn_backward(r, t, 0, batch, t->gbuf[r->buf_stem], act_ptr(r, r->buf_stem), nullptr, d_bn[0], d_bn[1], st)) return 1;
     if (conv_wgrad(r, t, 0, batch, d_conv_w[0], st)) return 1;
   }
-  if (t->mode == STRAPS_CONV_F16X3_TC && straps::tc_train_unpack_all(r, st)) return 1;
+  if (t->mode == STRAPS_CONV_F16X3_TC && straps::tc_train_unpack_all(r, st)) return 1;     // the weight gradients computed by THIS call
   return 0;
+}
+
+extern "C" int straps_encoder_backward(straps_regressor_t* r, const float* dfeat, int batch, int conv_mode, float* const* d_conv_w,
+                                       float* const* d_bn, void* stream) {
+  return straps_encoder_backward_range(r, dfeat, batch, conv_mode, d_conv_w, d_bn, 7, 0, 1, 1, stream);
 }
 
 // saved: dev [iters] x { p_k [B,157] | h1_k [B,512] | h2_k [B,512] } written by straps_ief_forward_train.

@@ -50,6 +50,8 @@ SIGNATURES = {
                                                            _vp, _vp, _vp]),
     'straps_encoder_train_forward': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     'straps_encoder_backward': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp]),
+    'straps_encoder_backward_range': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     'straps_ief_forward_train': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     'straps_ief_backward': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.POINTER(_vp),
                                            ctypes.POINTER(_vp), _vp, _vp]),

@@ -137,6 +137,12 @@ class RegressorEngine(object):
         self._train_steps += 1
 
 
+# positions, in _RegressorTrain's flat parameter order (20 conv weights, 20 BN weights, 20 BN biases, 3 fc weights, 3 fc biases), of the
+# parameters whose gradients are final after blocks 7..6 of the backward pass: layer4's five convolutions and BatchNorms, and the IEF
+_EARLY_PARAMS = tuple(range(15, 20)) + tuple(range(35, 40)) + tuple(range(55, 60)) + tuple(range(60, 66))
+_EARLY_HOOKS = {}      # id(layer4.0.conv1.weight) -> callable; registered by DataParallelAdam.enable_overlap
+
+
 class _RegressorTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, handle, x, iters, want, *params):
@@ -174,8 +180,20 @@ class _RegressorTrain(torch.autograd.Function):
         else:
             feat, saved = ctx.saved_tensors
             d_feat, dfw, dfb = h.ief_backward(feat, saved, g, ctx.iters, out_w=slot[60:63], out_b=slot[63:66])
-        dws, dbn = h.encoder_backward(d_feat, ctx.conv_shapes, ctx.bn_channels, out_w=slot[:20],
-                                      out_bn=list(zip(slot[20:40], slot[40:60])))
+        # A data-parallel optimiser (straps_b200.parallel.DataParallelAdam, world > 1) asks to be told when the deep end of the bucket is
+        # complete: layer4 (convolutions 15..19) + IEF = 76 % of the gradient bytes after the first two blocks of the pass.  Its
+        # all-reduce then runs on a side stream under the rest of the pass.
+        early = _EARLY_HOOKS.get(id(ctx.params[15])) if ctx.want != 'feat' else None
+        if early is not None and all(slot[i] is not None for i in _EARLY_PARAMS):
+            dws, dbn = h.encoder_backward(d_feat, ctx.conv_shapes, ctx.bn_channels, out_w=slot[:20], out_bn=list(zip(slot[20:40], slot[40:60])),
+                                          blocks=(7, 6, 1, 0))
+            for i in _EARLY_PARAMS:
+                ctx.params[i].grad = slot[i]
+            early()
+            dws, dbn = h.encoder_backward(d_feat, ctx.conv_shapes, ctx.bn_channels, blocks=(5, 0, 0, 1), dws=dws, dbn=dbn)
+        else:
+            dws, dbn = h.encoder_backward(d_feat, ctx.conv_shapes, ctx.bn_channels, out_w=slot[:20],
+                                          out_bn=list(zip(slot[20:40], slot[40:60])))
         grads = list(dws) + [p[0] for p in dbn] + [p[1] for p in dbn] + list(dfw) + list(dfb)
         # Slot gradients are handed to .grad HERE and reported to autograd as None: AccumulateGrad would not adopt a view that other
         # references keep alive (it clones it -- measured on B200: 0 of 66 adopted), and skipping it also keeps the parameters'

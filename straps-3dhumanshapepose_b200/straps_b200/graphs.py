@@ -40,6 +40,12 @@ class GraphedCallable(object):
         if not _tensors(self._static_out):
             raise StrapsError('GraphedCallable: the captured function returned no tensors')
 
+    @property
+    def static_inputs(self):
+        """The captured input buffers: a caller that writes its inputs straight into them (e.g. as the destination of its host->device
+        copy) and passes them back skips the copy `__call__` otherwise makes."""
+        return list(self._static_in)
+
     def __call__(self, *inputs):
         if len(inputs) != len(self._static_in):
             raise StrapsError('GraphedCallable was captured with %d inputs, called with %d' % (len(self._static_in), len(inputs)))
@@ -91,13 +97,24 @@ class GraphedTrainStep(object):
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._split = optimiser.world > 1
-        self._graph = torch.cuda.CUDAGraph()
         optimiser._deferred = self._split
         # capture on the warm-up stream: autograd nodes that outlive a step (AccumulateGrad of the criterion's log-variances) were
         # created there, and a node on ANOTHER stream makes the engine synchronise with it, which invalidates the capture
         try:
-            with torch.cuda.graph(self._graph, stream=side):
-                self._static_out = step_fn(*self._static_in)
+            try:
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph, stream=side):
+                    self._static_out = step_fn(*self._static_in)
+            except Exception:
+                # an early all-reduce inside the backward pass (DataParallelAdam.enable_overlap) is an NCCL collective inside the
+                # capture; if this build of torch / NCCL refuses that, capture again with the whole collective between the graphs
+                if optimiser._early_range is None:
+                    raise
+                optimiser.disable_overlap()
+                torch.cuda.synchronize(dev)
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph, stream=side):
+                    self._static_out = step_fn(*self._static_in)
         finally:
             optimiser._deferred = False
         self._graph_b = None

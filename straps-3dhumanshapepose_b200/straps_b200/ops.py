@@ -450,21 +450,24 @@ class RegressorHandle(object):
                                                           _stream(self.device)), 'straps_encoder_train_forward')
         return feat
 
-    def encoder_backward(self, dfeat, conv_shapes, bn_channels, mode=None, out_w=None, out_bn=None):
+    def encoder_backward(self, dfeat, conv_shapes, bn_channels, mode=None, out_w=None, out_bn=None, blocks=None, dws=None, dbn=None):
         """-> (list of 20 OIHW weight gradients, list of 20 (d_weight, d_bias)).  mode None = the mode of the forward.
-        out_w / out_bn: optional pre-allocated destinations (None entries are allocated here); every gradient is OVERWRITTEN."""
+        out_w / out_bn: optional pre-allocated destinations (None entries are allocated here); every gradient is OVERWRITTEN.
+        blocks = (block_hi, block_lo, first, stem): one piece of the pass (straps_encoder_backward_range)."""
         dfeat = dfeat.contiguous()
         B = dfeat.shape[0]
         new = lambda s: torch.empty(s, dtype=torch.float32, device=self.device)
-        dws = [out_w[i] if out_w is not None and out_w[i] is not None else new(s) for i, s in enumerate(conv_shapes)]
-        dbn = [((out_bn[i][0] if out_bn is not None and out_bn[i][0] is not None else new(c)),
-                (out_bn[i][1] if out_bn is not None and out_bn[i][1] is not None else new(c))) for i, c in enumerate(bn_channels)]
+        if dws is None:             # (a second call of a pass in pieces hands the first call's tensors back in)
+            dws = [out_w[i] if out_w is not None and out_w[i] is not None else new(s) for i, s in enumerate(conv_shapes)]
+            dbn = [((out_bn[i][0] if out_bn is not None and out_bn[i][0] is not None else new(c)),
+                    (out_bn[i][1] if out_bn is not None and out_bn[i][1] is not None else new(c))) for i, c in enumerate(bn_channels)]
         flat_bn = [t for pair in dbn for t in pair]
         arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        hi, lo, first, stem = (7, 0, 1, 1) if blocks is None else blocks
         with torch.cuda.device(self.device):
-            check(_lib.lib().straps_encoder_backward(self._h, _p(dfeat), B, -1 if mode is None else conv_mode_id(mode), arr(dws), arr(flat_bn),
-                                                     _stream(self.device)),
-                  'straps_encoder_backward')
+            check(_lib.lib().straps_encoder_backward_range(self._h, _p(dfeat), B, -1 if mode is None else conv_mode_id(mode), arr(dws),
+                                                           arr(flat_bn), hi, lo, first, stem, _stream(self.device)),
+                  'straps_encoder_backward_range')
         return dws, dbn
 
     def ief_forward_train(self, feat, iters=3):

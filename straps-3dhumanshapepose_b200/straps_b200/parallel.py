@@ -109,10 +109,71 @@ class DataParallelAdam(object):
     def zero_grad(self, set_to_none=True):
         self.bucket.zero_grad()
 
+    # ---- overlap of the collective with the backward pass -------------------------------------------------------------------------
+    _early_range = None      # [lo, hi) of the bucket that is complete after the first two blocks of the encoder's backward pass
+    _early_pending = False   # its all-reduce has been started (side stream) during the current backward pass
+    _early_in_graph = False  # ... and was captured into the step's first CUDA graph (GraphedTrainStep): replays need only the rest
+    _side = None
+    _hook_key = None
+
+    def enable_overlap(self, regressor):
+        """Start the all-reduce of layer4 + IEF -- 9.1 M of the 11.9 M gradients, final after the first two blocks of the encoder's
+        backward pass -- on a side stream while the remaining six blocks and the stem run (straps_b200.engine._RegressorTrain splits
+        its pass there and calls back); `step()` then reduces only the rest.  Returns False (and changes nothing) when it does not
+        apply: one rank, CPU buckets, or a parameter order in which that range is not contiguous."""
+        from . import engine
+        b = self.bucket
+        if self.world <= 1 or not b.params.is_cuda:
+            return False
+        try:
+            early = list(regressor.image_encoder.layer4.parameters()) + list(regressor.ief_module.parameters())
+            key = id(regressor.image_encoder.layer4[0].conv1.weight)
+        except AttributeError:
+            return False
+        ids = {id(p) for p in early}
+        pos = [k for k, p in enumerate(b.plist) if id(p) in ids]
+        if len(pos) != len(ids) or pos != list(range(pos[0], pos[0] + len(pos))):
+            return False
+        self._early_range = (b.offsets[pos[0]], b.offsets[pos[-1]] + b.plist[pos[-1]].numel())
+        self._side = torch.cuda.Stream(device=b.params.device)
+        self._hook_key = key
+        engine._EARLY_HOOKS[key] = self._on_early_grads
+        return True
+
+    def disable_overlap(self):
+        from . import engine
+        if self._hook_key is not None:
+            engine._EARLY_HOOKS.pop(self._hook_key, None)
+        self._early_range, self._hook_key, self._early_pending, self._early_in_graph = None, None, False, False
+
+    def _on_early_grads(self):
+        """Called from inside the backward pass (autograd's thread, on the stream of the forward) once bucket[lo:hi) is final."""
+        lo, hi = self._early_range
+        self._side.wait_stream(torch.cuda.current_stream(self.bucket.params.device))
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.bucket.grads[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        self._early_pending = True
+
+    def _join_early(self):
+        torch.cuda.current_stream(self.bucket.params.device).wait_stream(self._side)
+        self._early_pending = False
+
     def exchange(self):
-        """THE one collective of the step: sum the flat gradient bucket over ranks (NCCL all-reduce over NVLink / NVSwitch)."""
-        if self.world > 1:
-            dist.all_reduce(self.bucket.grads, op=dist.ReduceOp.SUM, group=self.group)
+        """THE collective of the step: sum the flat gradient bucket over ranks (NCCL all-reduce over NVLink / NVSwitch) -- all of it,
+        or what the early all-reduce of this step has not covered."""
+        if self.world <= 1:
+            return
+        g = self.bucket.grads
+        if self._early_pending or self._early_in_graph:
+            lo, hi = self._early_range
+            if lo > 0:
+                dist.all_reduce(g[:lo], op=dist.ReduceOp.SUM, group=self.group)
+            if hi < g.numel():
+                dist.all_reduce(g[hi:], op=dist.ReduceOp.SUM, group=self.group)
+            if self._early_pending:
+                self._join_early()
+        else:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
 
     def all_reduce(self):
         self.bucket.gather()
@@ -123,6 +184,9 @@ class DataParallelAdam(object):
     def step(self):
         if self._deferred:
             self.bucket.gather()             # captured with the backward; exchange() + apply_update() are driven by the graph wrapper
+            if self._early_pending:          # the side stream's all-reduce is part of this capture: join it before the capture ends
+                self._join_early()
+                self._early_in_graph = True
             return
         self.all_reduce()
         self.apply_update()

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     L = _lib.lib()
-    assert L.straps_abi_version() == 4
+    assert L.straps_abi_version() == 5
     assert isinstance(L.straps_last_error(), bytes)
     assert L.straps_launch_count() >= 0
     # argument validation happens before any CUDA call, so it is testable without a GPU

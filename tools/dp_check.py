@@ -43,6 +43,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--channels', type=int, default=17)
     ap.add_argument('--oracle-batch', type=int, default=0)
+    ap.add_argument('--overlap', action='store_true', help='also check and time the early all-reduce of layer4 + IEF inside the backward pass')
     ap.add_argument('--conv-mode', default='f16x3_tc', choices=['fp32_simt', 'f16x3_tc'])
     args = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
@@ -109,8 +110,20 @@ def main():
         ok['reduced_bit_identical'] = all(torch.equal(all_red[0], t) for t in all_red)
         s = torch.stack(all_loc).double().sum(0)
         ok['reduced_vs_sum_rel_err'] = float((reduced.double() - s).abs().max() / s.abs().max())
-    opt.bucket.grads.copy_(local_grads)          # step() performs the all-reduce itself
-    opt.step()
+    if args.overlap and world > 1:
+        # the same exchange with the layer4 + IEF part started inside the backward pass on a side stream (DataParallelAdam.enable_overlap):
+        # same inputs, same weights -> the reduced bucket must agree with the plain one (to the run-to-run noise of the atomics)
+        ok['overlap_enabled'] = bool(opt.enable_overlap(reg))
+        forward_backward(x, tg)
+        opt.all_reduce()
+        ok['overlap_reduced_rel_err'] = float((opt.bucket.grads.double() - reduced.double()).abs().max() / reduced.double().abs().max())
+        all_red2 = [torch.empty_like(reduced) for _ in range(world)]
+        dist.all_gather(all_red2, opt.bucket.grads.clone())
+        ok['overlap_reduced_bit_identical_across_ranks'] = all(torch.equal(all_red2[0], t) for t in all_red2)
+        opt.apply_update()
+    else:
+        opt.bucket.grads.copy_(local_grads)          # step() performs the all-reduce itself
+        opt.step()
     if world > 1:
         allp = [torch.empty_like(opt.bucket.params) for _ in range(world)]
         dist.all_gather(allp, opt.bucket.params)

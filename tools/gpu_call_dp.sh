@@ -6,7 +6,7 @@ TAG=${2:-r02}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_${N}gpu_$TAG.txt 2>&1
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
-timeout -s KILL 400 $RUN tools/dp_check.py --batch 64 --steps 5 > gpurun_out/dp_check_${N}gpu_$TAG.json 2> gpurun_out/dp_check_${N}gpu_$TAG.err; echo "dp_check rc=$?"; tail -c 600 gpurun_out/dp_check_${N}gpu_$TAG.json
+timeout -s KILL 400 $RUN tools/dp_check.py --batch 64 --steps 5 --overlap > gpurun_out/dp_check_${N}gpu_$TAG.json 2> gpurun_out/dp_check_${N}gpu_$TAG.err; echo "dp_check rc=$?"; tail -c 600 gpurun_out/dp_check_${N}gpu_$TAG.json
 timeout -s KILL 600 $RUN bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_${N}gpu_$TAG.json 2> gpurun_out/bench_${N}gpu_$TAG.err; echo "bench rc=$?"; tail -c 400 gpurun_out/bench_${N}gpu_$TAG.err
 python - <<PY
 import json
