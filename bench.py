@@ -389,6 +389,22 @@ def run_gpu(args):
     x_host = torch.from_numpy(synthetic_inputs.make_proxy_batch(B, C, seed=100 + rank)).pin_memory()
     x_dev = x_host.to(dev)
 
+    if args.train_only:             # development shortcut (multi-GPU A/B runs of the training arm): not the driver's line
+        barrier0 = (lambda: (dist.barrier() if world > 1 else None, torch.cuda.synchronize()))
+
+        def mx(ms):
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t.item())
+            return ms
+        train = train_bench(dev, rank, world, B, C, args.conv_mode, args.train_steps, x_dev, barrier0, mx, no_graph=args.no_train_graph)
+        if rank == 0:
+            print(json.dumps({'train': train, 'n_gpus': world}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     def hot_path(x):
         cam, pose, shape = reg(x)
         R = rot6d_to_rotmat(pose.contiguous()).view(-1, 24, 3, 3)
@@ -627,6 +643,7 @@ def main():
     ap.add_argument('--cpu-reps', type=int, default=3)
     ap.add_argument('--train-steps', type=int, default=10, help='timed steps of the training-step arm (0 = skip)')
     ap.add_argument('--no-lbs-sweep', action='store_true')
+    ap.add_argument('--train-only', action='store_true', help='run only the training arm and print {"train": ...} (development)')
     ap.add_argument('--no-graph', action='store_true', help='time the eager loop only (ncu launch lists: replays hide the kernels)')
     ap.add_argument('--no-train-graph', action='store_true', help='time the eager training loop only (ncu launch lists: replays hide the kernels)')
     ap.add_argument('--no-numa-bind', action='store_true', help='leave the process unbound (A/B of the NUMA binding)')
