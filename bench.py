@@ -285,9 +285,10 @@ def train_bench(dev, rank, world, B, C, conv_mode, steps, x_dev, barrier, max_ov
     crit = Loss(tasks, init_loss_weights=weights).to(dev)
     smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=B).to(dev)
     opt = DataParallelAdam(list(reg.parameters()) + list(crit.parameters()), lr=1e-4)
-    overlap = opt.enable_overlap(reg) and os.environ.get('STRAPS_DP_OVERLAP', '1') != '0'
-    if not overlap:
-        opt.disable_overlap()
+    # STRAPS_DP_OVERLAP=1: start the all-reduce of layer4 + IEF inside the backward pass (DataParallelAdam.enable_overlap).  Off by
+    # default: measured on 8 x B200 it changes nothing (8.04 vs 8.05 ms, profiles/r02_train_8gpu_overlap.jsonl)
+    if os.environ.get('STRAPS_DP_OVERLAP', '0') != '0':
+        opt.enable_overlap(reg)
     rng = np.random.RandomState(500 + rank)
     with torch.no_grad():                                   # target side (train/...:121-145), once: seeded random pose / shape
         t_betas = torch.from_numpy(rng.normal(0, 1, (B, 10)).astype(np.float32)).to(dev)
