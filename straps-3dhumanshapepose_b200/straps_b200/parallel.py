@@ -125,20 +125,28 @@ class DataParallelAdam(object):
         b = self.bucket
         if self.world <= 1 or not b.params.is_cuda:
             return False
+        rng = self.early_range_of(regressor)
+        if rng is None:
+            return False
+        self._early_range = rng
+        self._side = torch.cuda.Stream(device=b.params.device)
+        self._hook_key = id(regressor.image_encoder.layer4[0].conv1.weight)
+        engine._EARLY_HOOKS[self._hook_key] = self._on_early_grads
+        return True
+
+    def early_range_of(self, regressor):
+        """[lo, hi) of the flat bucket that holds exactly the parameters of layer4 and of the IEF module, or None if they are not one
+        contiguous run of it (they are for `list(regressor.parameters()) + list(criterion.parameters())`, the reference's order)."""
+        b = self.bucket
         try:
             early = list(regressor.image_encoder.layer4.parameters()) + list(regressor.ief_module.parameters())
-            key = id(regressor.image_encoder.layer4[0].conv1.weight)
         except AttributeError:
-            return False
-        ids = {id(p) for p in early}
+            return None
+        ids = {id(p) for p in early if p.requires_grad}
         pos = [k for k, p in enumerate(b.plist) if id(p) in ids]
-        if len(pos) != len(ids) or pos != list(range(pos[0], pos[0] + len(pos))):
-            return False
-        self._early_range = (b.offsets[pos[0]], b.offsets[pos[-1]] + b.plist[pos[-1]].numel())
-        self._side = torch.cuda.Stream(device=b.params.device)
-        self._hook_key = key
-        engine._EARLY_HOOKS[key] = self._on_early_grads
-        return True
+        if not pos or len(pos) != len(ids) or pos != list(range(pos[0], pos[0] + len(pos))):
+            return None
+        return (b.offsets[pos[0]], b.offsets[pos[-1]] + b.plist[pos[-1]].numel())
 
     def disable_overlap(self):
         from . import engine

@@ -80,3 +80,43 @@ def test_conv1_pair_layout_scheme_matches_conv2d():
     from conftest import REPO
     res = subprocess.run([sys.executable, os.path.join(REPO, 'tools', 'conv1_s2d_emulation.py')], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and 'pair-layout conv1 == conv2d' in res.stdout, res.stdout[-1000:] + res.stderr[-1000:]
+
+
+def test_select_joints_is_the_reference_list_indexing():
+    """straps_b200.ops.select_joints (one cached index_select, graph-capturable) == the reference's chained list indexing of the joint
+    superset (train/train_synthetic_otf_rendering.py:207-215), values and gradients."""
+    import config
+    from straps_b200.ops import select_joints
+    rng = np.random.RandomState(0)
+    j = torch.from_numpy(rng.normal(0, 1, (3, 90, 3)).astype(np.float32)).requires_grad_(True)
+    j2 = j.detach().clone().requires_grad_(True)
+    a = select_joints(j, config.ALL_JOINTS_TO_H36M_MAP, config.H36M_TO_J14)
+    b = j2[:, config.ALL_JOINTS_TO_H36M_MAP, :][:, config.H36M_TO_J14, :]
+    assert torch.equal(a, b)
+    c = select_joints(j, config.ALL_JOINTS_TO_COCO_MAP)
+    assert torch.equal(c, j2[:, config.ALL_JOINTS_TO_COCO_MAP, :])
+    w = torch.from_numpy(rng.normal(0, 1, tuple(a.shape)).astype(np.float32))
+    (a * w).sum().backward()
+    (b * w).sum().backward()
+    assert torch.allclose(j.grad, j2.grad, atol=1e-6)
+
+
+def test_early_all_reduce_range_is_layer4_plus_ief(assets_root):
+    """DataParallelAdam.early_range_of: in the reference's parameter order (regressor.parameters() + criterion.parameters()) layer4 and the
+    IEF module are one contiguous run at the deep end of the flat bucket -- what the overlapped all-reduce relies on -- and any other order
+    is refused."""
+    from models.regressor import SingleInputRegressor
+    from losses.multi_task_loss import HomoscedasticUncertaintyWeightedMultiTaskLoss as Loss
+    from straps_b200.parallel import DataParallelAdam
+    reg = SingleInputRegressor(17, 18, 3)
+    crit = Loss(['verts', 'joints2D'], init_loss_weights=None)
+    opt = DataParallelAdam(list(reg.parameters()) + list(crit.parameters()), broadcast=False)
+    lo, hi = opt.early_range_of(reg)
+    n_l4 = sum(p.numel() for p in reg.image_encoder.layer4.parameters())
+    n_ief = sum(p.numel() for p in reg.ief_module.parameters())
+    n_enc = sum(p.numel() for p in reg.image_encoder.parameters())
+    assert hi - lo == n_l4 + n_ief == 9079965 and lo == n_enc - n_l4 and hi == n_enc + n_ief
+    assert not opt.enable_overlap(reg)                      # one process, CPU bucket: nothing to overlap
+    reg2 = SingleInputRegressor(17, 18, 3)
+    shuffled = list(reg2.ief_module.parameters()) + list(reg2.image_encoder.parameters())
+    assert DataParallelAdam(shuffled, broadcast=False).early_range_of(reg2) is None
