@@ -76,6 +76,7 @@ struct TcConvParams {
   const float* res_f32;     // fp32 NHWC tensor added to the result (data-gradient accumulation) or null
   int relu;
   int debug;        // timing experiments only (STRAPS_TC_DEBUG bit mask): 1 = no TMA traffic, 2 = no MMAs, 4 = no epilogue global I/O
+  int epi_slab;     // split planes leave through per-warp shared-memory slabs as full 64-byte runs per pixel (STRAPS_TC_EPI=slab)
 };
 
 // BN = output-channel tile (64 for the Cout = 64 layers, else 128); an M-tile is 128 output pixels.
@@ -91,7 +92,8 @@ struct TcCfg {
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int STAGES = (220 * 1024 / STAGE_BYTES) > 4 ? 4 : (220 * 1024 / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int SLAB_OFF = STAGES * STAGE_BYTES + 256;     // 4 epilogue warps x (2 KB hi + 2 KB lo)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4 * 4096;
   static constexpr int ACC_COLS = 2 * BN;               // per accumulator stage: [hi.hi | lo terms]
   static constexpr int TMEM_COLS = 2 * ACC_COLS;        // two accumulator stages
   static constexpr int C1_CHUNKS = C1_KROW / BK;        // K-blocks per filter row of conv1 (im2col form)
@@ -239,6 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     constexpr int NCHUNK = BN / 32;              // 32-column chunks per work item
+    uint4* slab = reinterpret_cast<uint4*>(smem + Cfg::SLAB_OFF) + (warp - 2) * 256;
     uint32_t ti = 0;
     for (int item = item0; item < n_items; item += item_step, ++ti) {
       const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
@@ -323,14 +326,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               ph[i] = pack_f16(h0, h1);
               pl[i] = pack_f16(l0, l1);
             }
-            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
-            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
+            if (!p.epi_slab) {
+              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
+              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
-              ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
+              for (int q = 0; q < 4; ++q) {
+                oh[q] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
+                ol[q] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
+              }
+            } else {
+              // own pixel's 64 bytes per plane into the warp's slab (16-byte unit u of pixel r at unit u ^ ((r >> 1) & 3): conflict free)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int u = q ^ ((lane >> 1) & 3);
+                slab[lane * 4 + u] = make_uint4(ph[q * 4], ph[q * 4 + 1], ph[q * 4 + 2], ph[q * 4 + 3]);
+                slab[128 + lane * 4 + u] = make_uint4(pl[q * 4], pl[q * 4 + 1], pl[q * 4 + 2], pl[q * 4 + 3]);
+              }
             }
           }
+        }
+        if (p.epi_slab && !p.out_f32 && TC_EPI_IO(p)) {
+          // four lanes write one pixel's 64-byte run: every store instruction covers 16 FULL sectors (a thread storing its own
+          // pixel's 16 bytes at a time writes 32 half sectors per instruction, each sector in two visits)
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int pix = (lane >> 2) + 8 * k, part = lane & 3;
+            const long long mm = (long long)mg * BM_TC + quad * 32 + pix;
+            if (mm < p.m_total) {
+              const size_t o = (size_t)mm * p.cout + (size_t)nt * BN + c0 + part * 8;
+              const int u = pix * 4 + (part ^ ((pix >> 1) & 3));
+              *reinterpret_cast<uint4*>(p.out_hi + o) = slab[u];
+              *reinterpret_cast<uint4*>(p.out_lo + o) = slab[128 + u];
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -1058,14 +1088,16 @@ static TcGeom geom_dgrad(const ConvSpec& c) {
 // One host thread per GPU drives the library, so a plain global is enough.
 struct TcSwitches {
   int debug;          // STRAPS_TC_DEBUG (experiment builds)
+  int epi_slab;       // STRAPS_TC_EPI=slab: full-sector plane stores through per-warp slabs (conv_tc_kernel)
   int conv1;          // STRAPS_TC_CONV1: 2 = "s2dp" pair layout + fused max pool (default), 1 = "s2d" pair layout, stem tensor written,
                       // 0 = "im2col" the round-1 form through conv_tc_kernel
 };
-static TcSwitches g_sw = {0, 2};
+static TcSwitches g_sw = {0, 0, 2};
 
 static void tc_refresh_switches() {
   const char* e;
   e = getenv("STRAPS_TC_DEBUG");      g_sw.debug = e ? atoi(e) : 0;
+  e = getenv("STRAPS_TC_EPI");        g_sw.epi_slab = (e && e[0] == 's') ? 1 : 0;
   e = getenv("STRAPS_TC_CONV1");
   g_sw.conv1 = !e ? 2 : (strcmp(e, "im2col") == 0 ? 0 : strcmp(e, "s2d") == 0 ? 1 : 2);
 }
@@ -1159,6 +1191,7 @@ static int run_tc(TcState* t, const TcGeom& c, const TcLayerMaps& m, TcConvParam
   p.th = (c.hout * c.wout >= BM_TC) ? BM_TC / c.wout : c.hout;
   p.cout = c.cout;
   p.debug = g_sw.debug;
+  p.epi_slab = g_sw.epi_slab;
   return bn == 64 ? launch_conv_tc<64>(m, p, t->num_sms, st) : launch_conv_tc<128>(m, p, t->num_sms, st);
 }
 
