@@ -76,7 +76,7 @@ struct TcConvParams {
   const float* res_f32;     // fp32 NHWC tensor added to the result (data-gradient accumulation) or null
   int relu;
   int debug;        // timing experiments only (STRAPS_TC_DEBUG bit mask): 1 = no TMA traffic, 2 = no MMAs, 4 = no epilogue global I/O
-  int epi_slab;     // split planes leave through per-warp shared-memory slabs as full 64-byte runs per pixel (STRAPS_TC_EPI=slab)
+  int epi_slab;     // outputs leave through per-warp shared-memory slabs as full 64 / 128-byte runs per pixel (default on)
 };
 
 // BN = output-channel tile (64 for the Cout = 64 layers, else 128); an M-tile is 128 output pixels.
@@ -313,9 +313,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.f);
           }
           if (p.out_f32) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
+            if (!p.epi_slab) {
+              float4* o = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+              for (int q = 0; q < 8; ++q) o[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+            } else {
+              // own pixel's 128 bytes into the warp's slab (unit u of pixel r at unit u ^ (r & 7): conflict free)
+              float4* sf = reinterpret_cast<float4*>(slab);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) sf[lane * 8 + (q ^ (lane & 7))] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+            }
           } else {
             uint32_t ph[16], pl[16];
 #pragma unroll
@@ -344,6 +351,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               }
             }
           }
+        }
+        if (p.epi_slab && p.out_f32 && TC_EPI_IO(p)) {
+          // fp32 output (training forward, data gradient): eight lanes write one pixel's 128-byte run
+          __syncwarp();
+          const float4* sf = reinterpret_cast<const float4*>(slab);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int pix = (lane >> 3) + 4 * k, part = lane & 7;
+            const long long mm = (long long)mg * BM_TC + quad * 32 + pix;
+            if (mm < p.m_total)
+              *reinterpret_cast<float4*>(p.out_f32 + (size_t)mm * p.cout + (size_t)nt * BN + c0 + part * 4) = sf[pix * 8 + (part ^ (pix & 7))];
+          }
+          __syncwarp();
         }
         if (p.epi_slab && !p.out_f32 && TC_EPI_IO(p)) {
           // four lanes write one pixel's 64-byte run: every store instruction covers 16 FULL sectors (a thread storing its own
@@ -1088,16 +1108,16 @@ static TcGeom geom_dgrad(const ConvSpec& c) {
 // One host thread per GPU drives the library, so a plain global is enough.
 struct TcSwitches {
   int debug;          // STRAPS_TC_DEBUG (experiment builds)
-  int epi_slab;       // STRAPS_TC_EPI=slab: full-sector plane stores through per-warp slabs (conv_tc_kernel)
+  int epi_slab;       // outputs leave through per-warp shared-memory slabs as full runs per pixel (default; STRAPS_TC_EPI=direct: off)
   int conv1;          // STRAPS_TC_CONV1: 2 = "s2dp" pair layout + fused max pool (default), 1 = "s2d" pair layout, stem tensor written,
                       // 0 = "im2col" the round-1 form through conv_tc_kernel
 };
-static TcSwitches g_sw = {0, 0, 2};
+static TcSwitches g_sw = {0, 1, 2};
 
 static void tc_refresh_switches() {
   const char* e;
   e = getenv("STRAPS_TC_DEBUG");      g_sw.debug = e ? atoi(e) : 0;
-  e = getenv("STRAPS_TC_EPI");        g_sw.epi_slab = (e && e[0] == 's') ? 1 : 0;
+  e = getenv("STRAPS_TC_EPI");        g_sw.epi_slab = (e && e[0] == 'd') ? 0 : 1;      // "direct": per-thread 16-byte stores (round 1)
   e = getenv("STRAPS_TC_CONV1");
   g_sw.conv1 = !e ? 2 : (strcmp(e, "im2col") == 0 ? 0 : strcmp(e, "s2d") == 0 ? 1 : 2);
 }
