@@ -92,15 +92,15 @@ struct TcCfg {
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int STAGES = (220 * 1024 / STAGE_BYTES) > 4 ? 4 : (220 * 1024 / STAGE_BYTES);
-  static constexpr int SLAB_OFF = STAGES * STAGE_BYTES + 256;     // 4 epilogue warps x (2 KB hi + 2 KB lo)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4 * 4096;
+  static constexpr int SLAB_OFF = STAGES * STAGE_BYTES + 256;     // 4 epilogue warps x 4 KB output slabs, then 4 x 4 KB residual slabs
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 8 * 4096;
   static constexpr int ACC_COLS = 2 * BN;               // per accumulator stage: [hi.hi | lo terms]
   static constexpr int TMEM_COLS = 2 * ACC_COLS;        // two accumulator stages
   static constexpr int C1_CHUNKS = C1_KROW / BK;        // K-blocks per filter row of conv1 (im2col form)
   // conv1: the 168 real elements of a filter row end inside the last chunk; its all-padding K=16 steps are skipped
   static constexpr int C1_LAST_KSTEPS = (7 * XP_C - (C1_CHUNKS - 1) * BK + 15) / 16;
   static_assert(BN == 64 || BN == 128, "tile shapes of the ResNet-18 layers");
-  static_assert(STAGES >= 2 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "bad tile configuration");
+  static_assert(STAGES >= 2 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && SMEM_BYTES <= 232448, "bad tile configuration");
   static_assert(2 * STAGES * 8 + 40 <= 256, "barrier block too small");
 };
 
@@ -241,7 +241,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     constexpr int NCHUNK = BN / 32;              // 32-column chunks per work item
-    uint4* slab = reinterpret_cast<uint4*>(smem + Cfg::SLAB_OFF) + (warp - 2) * 256;
+    uint4* slab = reinterpret_cast<uint4*>(smem + Cfg::SLAB_OFF) + (warp - 2) * 256;          // output slab of this warp (4 KB)
+    uint4* rslab = reinterpret_cast<uint4*>(smem + Cfg::SLAB_OFF) + (4 + warp - 2) * 256;     // residual slab (hi 2 KB | lo 2 KB)
     uint32_t ti = 0;
     for (int item = item0; item < n_items; item += item_step, ++ti) {
       const int mg = item / p.n_ntiles, nt = item % p.n_ntiles;
@@ -254,6 +255,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       // showed the un-pipelined residual latency exposed on the short-K layers.
       uint4 rh[4], rl[4];
       auto fetch_residual = [&](int chunk) {
+        if (p.epi_slab) {
+          // four lanes fetch one pixel's 64-byte run per plane straight into the warp's residual slab (cp.async, full sectors, no
+          // registers held across the MMA wait); the owner reads its pixel back when the chunk is processed
+          if (p.res_hi && chunk < NCHUNK && TC_EPI_IO(p)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int pix = (lane >> 2) + 8 * k, part = lane & 3;
+              const long long mm = (long long)mg * BM_TC + quad * 32 + pix;
+              if (mm < p.m_total) {
+                const size_t o = (size_t)mm * p.cout + (size_t)nt * BN + chunk * 32 + part * 8;
+                const int u = pix * 4 + (part ^ ((pix >> 1) & 3));
+                cp_async_16(&rslab[u], p.res_hi + o);
+                cp_async_16(&rslab[128 + u], p.res_lo + o);
+              }
+            }
+          }
+          cp_async_commit();
+          return;
+        }
         if (p.res_hi && chunk < NCHUNK && valid && TC_EPI_IO(p)) {
           const size_t o = obase + chunk * 32;
 #pragma unroll
@@ -284,6 +304,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           y[q * 4 + 1] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 1]), LO_UNSCALE, __uint_as_float(v[q * 4 + 1])), u4.y, s4.y);
           y[q * 4 + 2] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 2]), LO_UNSCALE, __uint_as_float(v[q * 4 + 2])), u4.z, s4.z);
           y[q * 4 + 3] = fmaf(fmaf(__uint_as_float(vl[q * 4 + 3]), LO_UNSCALE, __uint_as_float(v[q * 4 + 3])), u4.w, s4.w);
+        }
+        if (p.epi_slab && p.res_hi && TC_EPI_IO(p)) {       // this chunk's residual has landed in the slab: own pixel back into registers
+          cp_async_wait_all();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int u = lane * 4 + (q ^ ((lane >> 1) & 3));
+            rh[q] = rslab[u];
+            rl[q] = rslab[128 + u];
+          }
+          __syncwarp();                                     // the next fetch may overwrite the slab
         }
         if (valid && TC_EPI_IO(p)) {
           if (p.res_hi) {
