@@ -241,3 +241,37 @@ def test_tensor_core_lbs_training_outputs(assets_root):
         _lbs_mode(None)
     for a, b in zip(grads[None], grads['simt']):
         assert rel_err(a.numpy(), b.numpy()) < 1e-5
+
+
+def test_tensor_core_lbs_at_the_sweep_size(assets_root):
+    """BASELINE config 5's largest batch (B = 4096: 64 body groups x 54 vertex tiles, 23 work items per persistent CTA): the
+    size-independent properties -- identity pose => shape blend, a root rotation is a rigid motion -- and agreement with the CUDA-core
+    kernel on random poses."""
+    B = 4096
+    smpl = _smpl(B)
+    rng = np.random.RandomState(12)
+    betas = torch.from_numpy(rng.normal(0, 1, (B, 10)).astype(np.float32)).to(DEV)
+    R = torch.eye(3, device=DEV).repeat(B, 24, 1, 1)
+    from utils.rigid_transform_utils import rot6d_to_rotmat
+    with torch.no_grad():
+        out = smpl(body_pose=R[:, 1:], global_orient=R[:, :1], betas=betas, pose2rot=False)
+        v_shaped = smpl.v_template + torch.einsum('bl,mkl->bmk', betas, smpl.shapedirs)
+        J = torch.einsum('bik,ji->bjk', v_shaped, smpl.J_regressor)
+        assert rel_err(out.vertices.cpu().numpy(), v_shaped.cpu().numpy()) < 1e-5
+        assert rel_err(out.joints[:, :24].cpu().numpy(), J.cpu().numpy()) < 1e-5
+        R0 = rot6d_to_rotmat(torch.from_numpy(rng.normal(0, 1, (B, 6)).astype(np.float32)).to(DEV))
+        R2 = R.clone()
+        R2[:, 0] = R0
+        out2 = smpl(body_pose=R2[:, 1:], global_orient=R2[:, :1], betas=betas, pose2rot=False)
+        expect = torch.einsum('bij,bvj->bvi', R0, v_shaped - J[:, :1]) + J[:, :1]
+        assert rel_err(out2.vertices.cpu().numpy(), expect.cpu().numpy()) < 1e-5
+        Rr = rot6d_to_rotmat(torch.from_numpy(rng.normal(0, 1, (B, 144)).astype(np.float32)).to(DEV)).view(B, 24, 3, 3)
+        try:
+            _lbs_mode('tc')
+            a = smpl(body_pose=Rr[:, 1:], global_orient=Rr[:, :1], betas=betas, pose2rot=False)
+            _lbs_mode('simt')
+            b = smpl(body_pose=Rr[:, 1:], global_orient=Rr[:, :1], betas=betas, pose2rot=False)
+        finally:
+            _lbs_mode(None)
+        assert float((a.vertices - b.vertices).abs().max() / b.vertices.abs().max()) < 3e-6
+        assert float((a.joints - b.joints).abs().max() / b.joints.abs().max()) < 3e-6
