@@ -8,20 +8,22 @@
 //   v_posed[b, (v,c)] = sum_k  Apk[(v,c), k] * Bm[b, k]      k = 0..206 pose feature (R_j - I), 207..216 betas, 217 the constant 1
 //                                                            Apk = [posedirs ; shapedirs ; v_template], K padded to 256
 //
-// Kernel 1 (smpl_chain_kernel, 8 bodies per CTA): rotations (Rodrigues or given), pre-reduced rest joints, the 24-joint kinematic
-//   chain (the code of lbs_kernel's prologue, same arithmetic order) -> the 24 posed joints and the skinning transforms A[b][24][3x4];
-//   writes BOTH tensor-core operands of its body group as ready-made swizzled shared-memory images: Bm (fp16 hi / lo, x 2^10,
-//   SWIZZLE_128B) and, per output row r, the transposed transforms AT_r[(body, column)][joint] (fp16 hi / lo, x 2^10, SWIZZLE_64B).
-// Kernel 2 (lbs_tc_kernel, CTA = 128 vertices x 64 bodies), two GEMMs into TMEM:
-//   (i)  blend: for each coordinate plane c an M = 128, N = 64 accumulator; K = 14 steps of 16 with the 3-pass fp16 split
-//        (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi: 22 mantissa bits; the rows of Apk are pre-scaled by a power of two so that both halves
-//        are fp16-normal).  Apk is packed ONCE at create time as swizzled 16 KB images, so operands arrive by plain bulk-async copies
-//        (no tensor maps) through a 5-stage ring.
-//   (ii) skinning transforms: T_r[v][(body, column)] = sum_j W[v][j] A[body][j][r][column] -- M = 128 vertices, N = 256, K = 24 (32),
-//        again 3 passes, one output row r at a time (TMEM holds 192 + 256 columns).  The first version of this kernel blended the
-//        transforms on the CUDA cores from shared memory (4 joints x 3 float4 per vertex and body): 12 bank-conflicted LDS.128 per
-//        output made the epilogue the whole cost (B = 4096: 563 us, 24 us per CTA against 3 us of MMAs).
-//   Epilogue (all 8 warps): v_posed from TMEM once (96 registers), then per row r: T_r from TMEM, 4 FMAs, + transl, store.
+//   T[b, v, (r,c4)]   = sum_j  W[v, j] * A[b, j, (r,c4)]     W = skinning weights, A = the 24 3x4 transforms of the kinematic chain
+//   out[b, v, r]      = T[b,v,(r,0..2)] . v_posed[b,v,:] + T[b,v,(r,3)] + transl[b,r]
+//
+// Kernel 1 (smpl_chain_kernel, 4 bodies per CTA of 256 threads): rotations (Rodrigues or given), pre-reduced rest joints, the 24-joint
+//   kinematic chain (the code of lbs_kernel's prologue, same arithmetic order) -> the 24 posed joints and the transforms A; writes BOTH
+//   per-body tensor-core operands as ready-made swizzled shared-memory images: Bm (fp16 hi / lo, x 2^10, SWIZZLE_128B) and the
+//   transposed transforms A^T[(body, column)][joint] (fp16 hi / lo, x 2^10, SWIZZLE_64B rows of 32 joint slots).
+// Kernel 2, two GEMMs into TMEM (M = 128 vertices, 3-pass fp16 split A_hi.B_hi + A_hi.B_lo + A_lo.B_hi: 22 mantissa bits; the rows of Apk
+//   and W are pre-scaled by a power of two so that both halves are fp16-normal), constants packed ONCE at create time as swizzled
+//   images so that every operand arrives by a plain bulk-async copy (no tensor maps):
+//   * lbs_tc3_kernel (default): persistent, software pipelined -- see its own comment below;
+//   * lbs_tc_kernel (STRAPS_LBS_V=2): one CTA per (vertex tile, body group), blend GEMM through a 5-stage ring, then the transform
+//     GEMM one output row at a time (N = 256), epilogue = T_r . v_posed from TMEM, output staged in shared memory.  Kept because it
+//     is the simple form of the same arithmetic (bit-identical results) and the base line of profiles/r02_lbs_tc_ncu.txt.
+//   The first version blended the transforms on the CUDA cores from shared memory and looked LDS-bound (B = 4096: 563 us); the real
+//   critical path was a per-body __ldg of transl inside the row loop (see lbs_tc_kernel's epilogue).
 // Roofline: HBM by contract (20,587,320 B + 84,664 B per body per launch); tensor work 3 x 2 x (224 x 20736 + 32 x 128 x 54 x 12) FLOP / body.
 #include "smpl.h"
 #include <cuda_fp16.h>
